@@ -1,0 +1,657 @@
+// bposd_capi.cu -- host side of libbposd_b200.so: the C ABI declared in include/bposd_b200.h.
+//
+// Compiles the Tanner graph once per parity-check matrix (CSR + CSC + slot maps on the device),
+// picks a BP kernel variant and launch geometry from the code size, owns the workspaces, and
+// sequences BP -> OSD (-> logical check) on the caller's stream.  There is no CPU fallback:
+// every entry point either runs the CUDA kernels or returns an error.
+#include "../../include/bposd_b200.h"
+#include "bposd_kernels.cuh"
+#include "bp_fast_kernel.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bposd;
+
+struct bposd_handle {
+    int device = 0, sm_count = 0, smem_optin = 0;
+    int m = 0, n = 0, nnz = 0, rank = 0, k = 0;
+    int max_iter = 0, bp_method = 1, osd_method = 0, osd_order = 0, precision = 64;
+    double alpha = 1.0;
+    std::vector<int> row_ptr, col_idx, col_ptr, row_idx, csc_slot;
+    std::vector<double> probs;
+    int max_row_deg = 0, max_col_deg = 0;
+    // device copies
+    int *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_col_ptr = nullptr, *d_row_idx = nullptr, *d_csc_slot = nullptr;
+    double *d_prior64 = nullptr, *d_weight = nullptr;
+    float *d_prior32 = nullptr;
+    int uniform = 0;
+    // fast-kernel tables
+    FastTables fast;
+    // control words: [0] queue, [1] converged, [2] iterations, [3] osd invocations, then int fail_count
+    unsigned long long *d_ctrl = nullptr;
+    int *d_fail_count = nullptr;
+    int *d_fail_list = nullptr;
+    void *d_fail_llr = nullptr;
+    long long fail_cap = 0; // shots per chunk the failed-shot workspace can hold
+    long long workspace_bytes = 2ll << 30;
+    void *d_scratch = nullptr; // global-mode BP scratch
+    uint8_t *d_scratch_dec = nullptr;
+    size_t scratch_bytes = 0;
+    // launch geometry
+    int bp_kernel = 1, bp_threads = 256, bp_ctas_per_sm = 1, bp_smem = 0, bp_grid = 0;
+    int osd_threads = 256, osd_smem = 0, osd_ctas_per_sm = 1, osd_S = 0, osd_St = 0;
+    bool osd_supported = true;
+    int force_kernel = 0, force_threads = 0;
+    bool geometry_ready = false;
+    // harness
+    uint32_t *d_t1 = nullptr, *d_t2 = nullptr, *d_t3 = nullptr;
+    int *d_l_ptr = nullptr, *d_l_idx = nullptr;
+    int K = 0;
+    // internal buffers for decode_host / sample_and_decode
+    uint8_t *b_synd = nullptr, *b_err = nullptr, *b_osdw = nullptr, *b_osd0 = nullptr, *b_bp = nullptr, *b_conv = nullptr;
+    void *b_llr = nullptr;
+    int32_t *b_iter = nullptr;
+    long long b_cap = 0, fail_list_cap = 0;
+    unsigned long long *d_counters = nullptr; // 8 words
+    int *d_minw = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bposd_stats_t stats{};
+    std::string err;
+};
+
+#define CU_TRY(h, call)                                                                          \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
+            return BPOSD_ECUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+static int fail(bposd_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+static thread_local std::string g_create_err;
+
+template <typename T>
+static cudaError_t upload(T **dst, const std::vector<T> &src) {
+    size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)dst, bytes);
+    if (e != cudaSuccess) return e;
+    if (!src.empty()) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static int host_rank(const bposd_handle *h) {
+    // GF(2) rank of H by packed row elimination; once per code (row a1: k = n - rank)
+    const int m = h->m, n = h->n, W = (n + 63) / 64;
+    std::vector<uint64_t> a((size_t)m * W, 0);
+    for (int i = 0; i < m; i++)
+        for (int e = h->row_ptr[i]; e < h->row_ptr[i + 1]; e++)
+            a[(size_t)i * W + h->col_idx[e] / 64] ^= 1ull << (h->col_idx[e] % 64);
+    int r = 0;
+    for (int c = 0; c < n && r < m; c++) {
+        const int w = c / 64;
+        const uint64_t bit = 1ull << (c % 64);
+        int p = -1;
+        for (int i = r; i < m; i++)
+            if (a[(size_t)i * W + w] & bit) { p = i; break; }
+        if (p < 0) continue;
+        if (p != r) std::swap_ranges(a.begin() + (size_t)p * W, a.begin() + (size_t)(p + 1) * W, a.begin() + (size_t)r * W);
+        for (int i = r + 1; i < m; i++)
+            if (a[(size_t)i * W + w] & bit)
+                for (int x = w; x < W; x++) a[(size_t)i * W + x] ^= a[(size_t)r * W + x];
+        r++;
+    }
+    return r;
+}
+
+static int upload_probs(bposd_handle *h) {
+    const int n = h->n;
+    std::vector<double> prior(n), weight(n);
+    std::vector<float> prior32(n);
+    bool uni = n > 0;
+    for (int j = 0; j < n; j++) {
+        const double p = h->probs[j];
+        prior[j] = std::log((1.0 - p) / p); // row a3
+        weight[j] = std::log(1 / p);        // row a14
+        prior32[j] = (float)prior[j];
+        if (!(p == h->probs[0])) uni = false;
+    }
+    if (uni && !(h->probs[0] > 0.0 && h->probs[0] < 1.0)) uni = false;
+    h->uniform = uni ? 1 : 0;
+    CU_TRY(h, cudaMemcpy(h->d_prior64, prior.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_prior32, prior32.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_weight, weight.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    return BPOSD_OK;
+}
+
+static GraphDev graph_of(const bposd_handle *h) {
+    GraphDev g;
+    g.m = h->m; g.n = h->n; g.nnz = h->nnz;
+    g.row_ptr = h->d_row_ptr; g.col_idx = h->d_col_idx;
+    g.col_ptr = h->d_col_ptr; g.row_idx = h->d_row_idx; g.csc_slot = h->d_csc_slot;
+    return g;
+}
+
+template <typename real>
+static int plan_geometry_t(bposd_handle *h) {
+    const size_t rs = sizeof(real);
+    const int n = h->n, m = h->m, E = h->nnz;
+    int threads = h->force_threads > 0 ? h->force_threads : std::min(1024, std::max(32, ((n + 1) / 2 + 31) / 32 * 32));
+    threads = std::min(1024, (threads + 31) / 32 * 32);
+    // candidate kernels, best first
+    int kernel = -1;
+    size_t smem = 0;
+    const bool fast_ok = fast_supported(h->max_col_deg, h->max_row_deg, h->bp_method);
+    const size_t smem_fast = fast_ok ? fast_smem_bytes<real>(h->fast, n, m) : ((size_t)1 << 40);
+    const size_t smem_gen = (2 * (size_t)E + n) * rs + n + m + 16;
+    const int want = h->force_kernel - 1;
+    if ((want < 0 || want == 2) && fast_ok && smem_fast <= (size_t)h->smem_optin) {
+        kernel = 2; smem = smem_fast;
+        if (h->force_threads <= 0) threads = fast_default_threads(n, m);
+    } else if ((want < 0 || want == 1 || want == 2) && smem_gen <= (size_t)h->smem_optin) {
+        kernel = 1; smem = smem_gen;
+    } else {
+        kernel = 0; smem = (size_t)m + 16;
+    }
+    if (want == 0) { kernel = 0; smem = (size_t)m + 16; }
+    int occ = 0;
+    if (kernel == 2) {
+        if (threads * fast_vpt(n) < n) threads = fast_default_threads(n, m);
+        CU_TRY(h, fast_set_smem_t<real>(h->fast, n, smem));
+        CU_TRY(h, fast_occupancy_t<real>(h->fast, n, threads, smem, &occ));
+    } else if (kernel == 1) {
+        CU_TRY(h, cudaFuncSetAttribute(bp_generic_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bp_generic_kernel<real, true>, threads, smem));
+    } else {
+        CU_TRY(h, cudaFuncSetAttribute(bp_generic_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bp_generic_kernel<real, false>, threads, smem));
+    }
+    if (occ < 1) return fail(h, BPOSD_EUNSUP, "BP kernel does not fit on an SM");
+    h->bp_kernel = kernel;
+    h->bp_threads = threads;
+    h->bp_smem = (int)smem;
+    h->bp_ctas_per_sm = occ;
+    h->bp_grid = occ * h->sm_count;
+    if (kernel == 0) {
+        const size_t per_cta = (2 * (size_t)E + n) * rs;
+        const size_t need = per_cta * h->bp_grid;
+        if (need > h->scratch_bytes) {
+            cudaFree(h->d_scratch); cudaFree(h->d_scratch_dec);
+            h->d_scratch = nullptr; h->d_scratch_dec = nullptr;
+            CU_TRY(h, cudaMalloc(&h->d_scratch, need));
+            CU_TRY(h, cudaMalloc((void **)&h->d_scratch_dec, (size_t)n * h->bp_grid));
+            h->scratch_bytes = need;
+        }
+    }
+    // OSD kernel
+    h->osd_S = (m + 31) / 32;
+    h->osd_St = h->osd_S | 1;
+    h->osd_threads = std::min(1024, std::max(64, (m + 31) / 32 * 32));
+    const int nw = h->osd_threads / 32;
+    const size_t osd_smem = (size_t)n * 8 + 256 + ((size_t)m * h->osd_St + 3 * (size_t)h->osd_S + (size_t)nw * (h->osd_S + 64)) * 4 + 128 + 3 * (size_t)n * 2 + 16;
+    h->osd_smem = (int)osd_smem;
+    h->osd_supported = osd_smem <= (size_t)h->smem_optin && n < 65535 && m < 65535;
+    if (h->osd_supported) {
+        CU_TRY(h, cudaFuncSetAttribute(osd_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osd_smem));
+        int occ2 = 0;
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, osd_kernel<real>, h->osd_threads, osd_smem));
+        h->osd_ctas_per_sm = std::max(1, occ2);
+    }
+    // failed-shot LLR workspace capacity (shots per chunk)
+    const long long per_shot = (long long)n * (long long)rs;
+    h->fail_cap = std::max<long long>(1024, h->workspace_bytes / std::max<long long>(per_shot, 1));
+    h->geometry_ready = true;
+    return BPOSD_OK;
+}
+
+static int plan_geometry(bposd_handle *h) {
+    return h->precision == 64 ? plan_geometry_t<double>(h) : plan_geometry_t<float>(h);
+}
+
+extern "C" const char *bposd_version(void) { return "bposd_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *bposd_last_error(const bposd_t *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" void bposd_destroy(bposd_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_row_ptr); cudaFree(h->d_col_idx); cudaFree(h->d_col_ptr); cudaFree(h->d_row_idx); cudaFree(h->d_csc_slot);
+    cudaFree(h->d_prior64); cudaFree(h->d_prior32); cudaFree(h->d_weight);
+    fast_free(h->fast);
+    cudaFree(h->d_ctrl); cudaFree(h->d_fail_list); cudaFree(h->d_fail_llr);
+    cudaFree(h->d_scratch); cudaFree(h->d_scratch_dec);
+    cudaFree(h->d_t1); cudaFree(h->d_t2); cudaFree(h->d_t3); cudaFree(h->d_l_ptr); cudaFree(h->d_l_idx);
+    cudaFree(h->b_synd); cudaFree(h->b_err); cudaFree(h->b_osdw); cudaFree(h->b_osd0); cudaFree(h->b_bp);
+    cudaFree(h->b_conv); cudaFree(h->b_llr); cudaFree(h->b_iter); cudaFree(h->d_counters); cudaFree(h->d_minw);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    delete h;
+}
+
+extern "C" int bposd_create(const int32_t *indptr, const int32_t *indices, int32_t m, int32_t n,
+                            const double *probs, int32_t max_iter, int32_t bp_method, double alpha,
+                            int32_t osd_method, int32_t osd_order, int32_t precision, int32_t device,
+                            bposd_t **out) {
+    g_create_err.clear();
+    auto bad = [&](int code, const std::string &msg) { g_create_err = msg; return code; };
+    if (!out) return bad(BPOSD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!indptr || (!indices && m > 0 && indptr[m] > 0) || !probs) return bad(BPOSD_EINVAL, "NULL input pointer");
+    if (m < 0 || n <= 0) return bad(BPOSD_EINVAL, "parity-check matrix must have at least one column");
+    if (bp_method != BPOSD_BP_PRODUCT_SUM && bp_method != BPOSD_BP_MINIMUM_SUM) return bad(BPOSD_EINVAL, "unknown bp_method");
+    if (osd_method < BPOSD_OSD_0 || osd_method > BPOSD_OSD_OFF) return bad(BPOSD_EINVAL, "unknown osd_method");
+    if (precision != 64 && precision != 32) return bad(BPOSD_EINVAL, "precision must be 64 or 32");
+    if (max_iter < 0) return bad(BPOSD_EINVAL, "max_iter must be non-negative");
+    if (osd_order < 0) return bad(BPOSD_EINVAL, "osd_order must be non-negative");
+    for (int i = 0; i < m; i++) {
+        if (indptr[i + 1] < indptr[i]) return bad(BPOSD_EINVAL, "indptr must be non-decreasing");
+        for (int e = indptr[i]; e < indptr[i + 1]; e++) {
+            if (indices[e] < 0 || indices[e] >= n) return bad(BPOSD_EINVAL, "column index out of range");
+            if (e > indptr[i] && indices[e] <= indices[e - 1]) return bad(BPOSD_EINVAL, "column indices must be strictly ascending inside a row");
+        }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return bad(BPOSD_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return bad(BPOSD_EINVAL, "device index out of range");
+
+    bposd_handle *h = new (std::nothrow) bposd_handle();
+    if (!h) return bad(BPOSD_ENOMEM, "out of host memory");
+    h->device = device;
+    auto die = [&](int code) { g_create_err = h->err; bposd_destroy(h); return code; };
+#define CR_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e__); return die(BPOSD_ECUDA); } } while (0)
+    CR_TRY(cudaSetDevice(device));
+    CR_TRY(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CR_TRY(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    h->m = m; h->n = n; h->nnz = indptr[m];
+    h->row_ptr.assign(indptr, indptr + m + 1);
+    h->col_idx.assign(indices, indices + h->nnz);
+    h->col_ptr.assign(n + 1, 0);
+    for (int e = 0; e < h->nnz; e++) h->col_ptr[h->col_idx[e] + 1]++;
+    for (int j = 0; j < n; j++) { h->max_col_deg = std::max(h->max_col_deg, h->col_ptr[j + 1]); h->col_ptr[j + 1] += h->col_ptr[j]; }
+    h->row_idx.resize(h->nnz); h->csc_slot.resize(h->nnz);
+    {
+        std::vector<int> fill(n, 0);
+        for (int i = 0; i < m; i++) {
+            h->max_row_deg = std::max(h->max_row_deg, h->row_ptr[i + 1] - h->row_ptr[i]);
+            for (int e = h->row_ptr[i]; e < h->row_ptr[i + 1]; e++) {
+                const int j = h->col_idx[e], p = h->col_ptr[j] + fill[j]++;
+                h->row_idx[p] = i;
+                h->csc_slot[p] = e;
+            }
+        }
+    }
+    h->probs.assign(probs, probs + n);
+    h->max_iter = max_iter > 0 ? max_iter : n;
+    h->bp_method = bp_method;
+    h->alpha = alpha;
+    h->osd_method = osd_method;
+    h->osd_order = (osd_method == BPOSD_OSD_0 || osd_method == BPOSD_OSD_OFF) ? 0 : osd_order;
+    h->precision = precision;
+    h->rank = host_rank(h);
+    h->k = n - h->rank;
+    if (h->osd_order > h->k) { h->err = "osd_order must not exceed n - rank(H)"; return die(BPOSD_EINVAL); }
+    if (osd_method == BPOSD_OSD_E && h->osd_order > 30) { h->err = "osd_e order above 30 is not supported"; return die(BPOSD_EINVAL); }
+    if (h->osd_order > 63) { h->err = "osd_order above 63 is not supported"; return die(BPOSD_EINVAL); }
+
+    CR_TRY(upload(&h->d_row_ptr, h->row_ptr));
+    CR_TRY(upload(&h->d_col_idx, h->col_idx));
+    CR_TRY(upload(&h->d_col_ptr, h->col_ptr));
+    CR_TRY(upload(&h->d_row_idx, h->row_idx));
+    CR_TRY(upload(&h->d_csc_slot, h->csc_slot));
+    CR_TRY(cudaMalloc((void **)&h->d_prior64, n * sizeof(double)));
+    CR_TRY(cudaMalloc((void **)&h->d_prior32, n * sizeof(float)));
+    CR_TRY(cudaMalloc((void **)&h->d_weight, n * sizeof(double)));
+    if (upload_probs(h) != BPOSD_OK) return die(BPOSD_ECUDA);
+    CR_TRY(cudaMalloc((void **)&h->d_ctrl, 8 * sizeof(unsigned long long)));
+    CR_TRY(cudaMemset(h->d_ctrl, 0, 8 * sizeof(unsigned long long)));
+    h->d_fail_count = reinterpret_cast<int *>(h->d_ctrl + 4);
+    CR_TRY(cudaMalloc((void **)&h->d_counters, 8 * sizeof(unsigned long long)));
+    CR_TRY(cudaMalloc((void **)&h->d_minw, sizeof(int)));
+    for (auto &e : h->ev) CR_TRY(cudaEventCreate(&e));
+    if (fast_supported(h->max_col_deg, h->max_row_deg, bp_method)) {
+        cudaError_t e = fast_build(h->fast, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot);
+        if (e != cudaSuccess) { h->err = std::string("fast_build: ") + cudaGetErrorString(e); return die(BPOSD_ECUDA); }
+    }
+    int rc = plan_geometry(h);
+    if (rc != BPOSD_OK) return die(rc);
+#undef CR_TRY
+    *out = h;
+    return BPOSD_OK;
+}
+
+extern "C" int bposd_update_channel_probs(bposd_t *h, const double *probs) {
+    if (!h || !probs) return fail(h, BPOSD_EINVAL, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->probs.assign(probs, probs + h->n);
+    return upload_probs(h);
+}
+
+extern "C" int bposd_set_tuning(bposd_t *h, int32_t kernel_plus1, int32_t threads, int64_t workspace_bytes) {
+    if (!h) return BPOSD_EINVAL;
+    if (kernel_plus1 < 0 || kernel_plus1 > 3) return fail(h, BPOSD_EINVAL, "bp kernel selector out of range");
+    if (threads < 0 || threads > 1024 || (threads % 32)) return fail(h, BPOSD_EINVAL, "threads must be a multiple of 32 up to 1024");
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->force_kernel = kernel_plus1;
+    h->force_threads = threads;
+    if (workspace_bytes > 0) h->workspace_bytes = workspace_bytes;
+    return plan_geometry(h);
+}
+
+extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
+    if (!h || !info) return BPOSD_EINVAL;
+    info->m = h->m; info->n = h->n; info->nnz = h->nnz; info->rank = h->rank; info->k = h->k;
+    info->max_iter = h->max_iter; info->bp_method = h->bp_method; info->osd_method = h->osd_method;
+    info->osd_order = h->osd_order; info->precision = h->precision; info->device = h->device;
+    info->bp_kernel = h->bp_kernel; info->bp_threads = h->bp_threads; info->bp_ctas_per_sm = h->bp_ctas_per_sm;
+    info->bp_smem_bytes = h->bp_smem; info->osd_threads = h->osd_threads; info->osd_smem_bytes = h->osd_smem;
+    info->sm_count = h->sm_count; info->ms_scaling_factor = h->alpha;
+    return BPOSD_OK;
+}
+
+extern "C" int bposd_get_stats(const bposd_t *h, bposd_stats_t *stats) {
+    if (!h || !stats) return BPOSD_EINVAL;
+    *stats = h->stats;
+    return BPOSD_OK;
+}
+
+template <typename real>
+static int decode_batch_t(bposd_handle *h, const uint8_t *d_synd, long long B, const bposd_out_t *out,
+                          const void *d_priors, cudaStream_t st) {
+    const int n = h->n, m = h->m;
+    const bool osd_on = h->osd_method != BPOSD_OSD_OFF;
+    if (osd_on && !h->osd_supported)
+        return fail(h, BPOSD_EUNSUP, "OSD for this matrix size needs more shared memory than an SM has; use osd_method off");
+    real *llr_out = static_cast<real *>(out->d_llr);
+    const bool need_ws = osd_on && !llr_out;
+    long long chunk = B;
+    if (need_ws) {
+        chunk = std::min(B, h->fail_cap);
+        if (!h->d_fail_llr) CU_TRY(h, cudaMalloc(&h->d_fail_llr, (size_t)h->fail_cap * n * sizeof(real)));
+    }
+    chunk = std::min<long long>(chunk, 1ll << 30);
+    if (!h->d_fail_list || chunk > h->fail_list_cap) { // fail list holds one chunk
+        cudaFree(h->d_fail_list);
+        h->d_fail_list = nullptr;
+        CU_TRY(h, cudaMalloc((void **)&h->d_fail_list, (size_t)chunk * sizeof(int)));
+        h->fail_list_cap = chunk;
+    }
+    CU_TRY(h, cudaMemsetAsync(h->d_ctrl, 0, 8 * sizeof(unsigned long long), st));
+    h->stats = bposd_stats_t{};
+    float ms_bp = 0, ms_osd = 0;
+    int launches = 0, chunks = 0;
+    for (long long c0 = 0; c0 < B; c0 += chunk) {
+        const long long Bc = std::min(chunk, B - c0);
+        CU_TRY(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(unsigned long long), st));       // queue
+        CU_TRY(h, cudaMemsetAsync(h->d_fail_count, 0, sizeof(int), st));
+        BpArgs<real> a;
+        a.g = graph_of(h);
+        a.max_iter = h->max_iter;
+        a.method = h->bp_method;
+        a.alpha0 = (real)h->alpha;
+        if (d_priors) { a.prior = static_cast<const real *>(d_priors) + c0 * n; a.prior_stride = n; }
+        else { a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32; a.prior_stride = 0; }
+        a.synd = d_synd + c0 * m;
+        a.B = Bc;
+        a.bp = out->d_bp ? out->d_bp + c0 * n : nullptr;
+        a.osd0 = out->d_osd0 ? out->d_osd0 + c0 * n : nullptr;
+        a.osdw = out->d_osdw ? out->d_osdw + c0 * n : nullptr;
+        a.llr = llr_out ? llr_out + c0 * n : nullptr;
+        a.converge = out->d_converge ? out->d_converge + c0 : nullptr;
+        a.iter = out->d_iter ? out->d_iter + c0 : nullptr;
+        a.fail_count = h->d_fail_count;
+        a.fail_list = h->d_fail_list;
+        a.fail_llr = static_cast<real *>(h->d_fail_llr);
+        a.osd_off = osd_on ? 0 : 1;
+        a.queue = h->d_ctrl;
+        a.stat = h->d_ctrl + 1;
+        a.g_scratch = static_cast<real *>(h->d_scratch);
+        a.g_dec = h->d_scratch_dec;
+        const int grid = (int)std::min<long long>(Bc, h->bp_grid);
+        CU_TRY(h, cudaEventRecord(h->ev[0], st));
+        if (h->bp_kernel == 2) fast_launch<real>(h->fast, a, grid, h->bp_threads, h->bp_smem, st);
+        else if (h->bp_kernel == 1) bp_generic_kernel<real, true><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
+        else bp_generic_kernel<real, false><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
+        CU_TRY(h, cudaGetLastError());
+        launches++;
+        CU_TRY(h, cudaEventRecord(h->ev[1], st));
+        if (osd_on) {
+            OsdArgs<real> o;
+            o.g = a.g;
+            o.S = h->osd_S; o.St = h->osd_St;
+            o.method = h->osd_method; o.order = h->osd_order; o.uniform = d_priors ? 0 : h->uniform;
+            o.weight = h->d_weight;
+            o.synd = a.synd;
+            o.llr = llr_out ? a.llr : static_cast<const real *>(h->d_fail_llr);
+            o.llr_by_shot = llr_out ? 1 : 0;
+            o.fail_count = h->d_fail_count;
+            o.fail_list = h->d_fail_list;
+            o.osd0 = a.osd0; o.osdw = a.osdw;
+            o.stat = h->d_ctrl + 1;
+            const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
+            osd_kernel<real><<<ogrid, h->osd_threads, h->osd_smem, st>>>(o);
+            CU_TRY(h, cudaGetLastError());
+            launches++;
+        }
+        CU_TRY(h, cudaEventRecord(h->ev[2], st));
+        chunks++;
+        if (c0 + chunk < B || true) {
+            // events are re-used per chunk, so collect this chunk's times before the next one
+            CU_TRY(h, cudaEventSynchronize(h->ev[2]));
+            float t = 0;
+            CU_TRY(h, cudaEventElapsedTime(&t, h->ev[0], h->ev[1])); ms_bp += t;
+            CU_TRY(h, cudaEventElapsedTime(&t, h->ev[1], h->ev[2])); ms_osd += t;
+        }
+    }
+    unsigned long long ctrl[4];
+    CU_TRY(h, cudaMemcpyAsync(ctrl, h->d_ctrl, sizeof(ctrl), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    h->stats.shots = B;
+    h->stats.bp_converged = (int64_t)ctrl[1];
+    h->stats.bp_iterations = (int64_t)ctrl[2];
+    h->stats.osd_invocations = (int64_t)ctrl[3];
+    h->stats.ms_bp = ms_bp; h->stats.ms_osd = ms_osd;
+    h->stats.launches = launches; h->stats.chunks = chunks;
+    return BPOSD_OK;
+}
+
+extern "C" int bposd_decode_batch(bposd_t *h, const uint8_t *d_synd, int64_t B, const bposd_out_t *out,
+                                  const void *d_priors, void *stream) {
+    if (!h) return BPOSD_EINVAL;
+    if (!out || (!d_synd && B > 0 && h->m > 0)) return fail(h, BPOSD_EINVAL, "NULL argument");
+    if (B < 0) return fail(h, BPOSD_EINVAL, "negative batch size");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (B == 0) { h->stats = bposd_stats_t{}; return BPOSD_OK; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return h->precision == 64 ? decode_batch_t<double>(h, d_synd, B, out, d_priors, st)
+                              : decode_batch_t<float>(h, d_synd, B, out, d_priors, st);
+}
+
+static int ensure_buffers(bposd_handle *h, long long B, bool want_llr, bool want_err) {
+    const size_t rs = h->precision == 64 ? 8 : 4;
+    if (B > h->b_cap) {
+        cudaFree(h->b_synd); cudaFree(h->b_osdw); cudaFree(h->b_osd0); cudaFree(h->b_bp); cudaFree(h->b_conv);
+        cudaFree(h->b_iter); cudaFree(h->b_err); cudaFree(h->b_llr);
+        h->b_synd = h->b_osdw = h->b_osd0 = h->b_bp = h->b_conv = h->b_err = nullptr;
+        h->b_iter = nullptr; h->b_llr = nullptr;
+        h->b_cap = 0;
+        CU_TRY(h, cudaMalloc((void **)&h->b_synd, (size_t)B * std::max(h->m, 1)));
+        CU_TRY(h, cudaMalloc((void **)&h->b_osdw, (size_t)B * h->n));
+        CU_TRY(h, cudaMalloc((void **)&h->b_osd0, (size_t)B * h->n));
+        CU_TRY(h, cudaMalloc((void **)&h->b_bp, (size_t)B * h->n));
+        CU_TRY(h, cudaMalloc((void **)&h->b_conv, (size_t)B));
+        CU_TRY(h, cudaMalloc((void **)&h->b_iter, (size_t)B * 4));
+        h->b_cap = B;
+    }
+    if (want_llr && !h->b_llr) CU_TRY(h, cudaMalloc(&h->b_llr, (size_t)h->b_cap * h->n * rs));
+    if (want_err && !h->b_err) CU_TRY(h, cudaMalloc((void **)&h->b_err, (size_t)h->b_cap * h->n));
+    return BPOSD_OK;
+}
+
+extern "C" int bposd_decode_host(bposd_t *h, const uint8_t *h_synd, int64_t B, uint8_t *h_osdw, uint8_t *h_osd0,
+                                 uint8_t *h_bp, void *h_llr, uint8_t *h_conv, int32_t *h_iter) {
+    if (!h) return BPOSD_EINVAL;
+    if (B < 0 || (!h_synd && B > 0 && h->m > 0)) return fail(h, BPOSD_EINVAL, "bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (B == 0) return BPOSD_OK;
+    int rc = ensure_buffers(h, B, h_llr != nullptr, false);
+    if (rc) return rc;
+    const size_t rs = h->precision == 64 ? 8 : 4;
+    cudaStream_t st = nullptr;
+    CU_TRY(h, cudaMemcpyAsync(h->b_synd, h_synd, (size_t)B * h->m, cudaMemcpyHostToDevice, st));
+    bposd_out_t o{};
+    o.d_osdw = h_osdw ? h->b_osdw : nullptr;
+    o.d_osd0 = h_osd0 ? h->b_osd0 : nullptr;
+    o.d_bp = h_bp ? h->b_bp : nullptr;
+    o.d_llr = h_llr ? h->b_llr : nullptr;
+    o.d_converge = h_conv ? h->b_conv : nullptr;
+    o.d_iter = h_iter ? h->b_iter : nullptr;
+    rc = bposd_decode_batch(h, h->b_synd, B, &o, nullptr, st);
+    if (rc) return rc;
+    if (h_osdw) CU_TRY(h, cudaMemcpyAsync(h_osdw, h->b_osdw, (size_t)B * h->n, cudaMemcpyDeviceToHost, st));
+    if (h_osd0) CU_TRY(h, cudaMemcpyAsync(h_osd0, h->b_osd0, (size_t)B * h->n, cudaMemcpyDeviceToHost, st));
+    if (h_bp) CU_TRY(h, cudaMemcpyAsync(h_bp, h->b_bp, (size_t)B * h->n, cudaMemcpyDeviceToHost, st));
+    if (h_llr) CU_TRY(h, cudaMemcpyAsync(h_llr, h->b_llr, (size_t)B * h->n * rs, cudaMemcpyDeviceToHost, st));
+    if (h_conv) CU_TRY(h, cudaMemcpyAsync(h_conv, h->b_conv, (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (h_iter) CU_TRY(h, cudaMemcpyAsync(h_iter, h->b_iter, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    return BPOSD_OK;
+}
+
+extern "C" int bposd_set_channel_thresholds(bposd_t *h, const uint32_t *t1, const uint32_t *t2, const uint32_t *t3) {
+    if (!h || !t1 || !t2 || !t3) return fail(h, BPOSD_EINVAL, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->n * sizeof(uint32_t);
+    for (int j = 0; j < h->n; j++)
+        if (t1[j] > t2[j] || t2[j] > t3[j]) return fail(h, BPOSD_EINVAL, "thresholds must be cumulative (t1 <= t2 <= t3)");
+    if (!h->d_t1) {
+        CU_TRY(h, cudaMalloc((void **)&h->d_t1, bytes));
+        CU_TRY(h, cudaMalloc((void **)&h->d_t2, bytes));
+        CU_TRY(h, cudaMalloc((void **)&h->d_t3, bytes));
+    }
+    CU_TRY(h, cudaMemcpy(h->d_t1, t1, bytes, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_t2, t2, bytes, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_t3, t3, bytes, cudaMemcpyHostToDevice));
+    return BPOSD_OK;
+}
+
+extern "C" int bposd_sample_syndromes(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector,
+                                      uint8_t *d_errors, uint8_t *d_synd, void *stream) {
+    if (!h) return BPOSD_EINVAL;
+    if (!h->d_t1) return fail(h, BPOSD_EINVAL, "call bposd_set_channel_thresholds first");
+    if (B < 0 || (!d_synd && B > 0) || (sector != 0 && sector != 1)) return fail(h, BPOSD_EINVAL, "bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (B == 0) return BPOSD_OK;
+    SampleArgs a;
+    a.g = graph_of(h);
+    a.t1 = h->d_t1; a.t2 = h->d_t2; a.t3 = h->d_t3;
+    a.seed = seed; a.shot0 = shot0; a.B = B; a.sector = sector;
+    a.errors = d_errors; a.synd = d_synd;
+    const int threads = std::min(1024, std::max(32, ((h->n + 3) / 4 + 31) / 32 * 32));
+    const size_t smem = (size_t)h->n + 16;
+    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(sample_syndrome_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<long long>(B, (long long)h->sm_count * 8);
+    sample_syndrome_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    return BPOSD_OK;
+}
+
+extern "C" int bposd_set_logicals(bposd_t *h, const int32_t *indptr, const int32_t *indices, int32_t K) {
+    if (!h || !indptr || K < 0) return fail(h, BPOSD_EINVAL, "bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    for (int e = 0; e < indptr[K]; e++)
+        if (indices[e] < 0 || indices[e] >= h->n) return fail(h, BPOSD_EINVAL, "logical operator column out of range");
+    cudaFree(h->d_l_ptr); cudaFree(h->d_l_idx);
+    h->d_l_ptr = h->d_l_idx = nullptr;
+    std::vector<int> p(indptr, indptr + K + 1), x(indices, indices + indptr[K]);
+    CU_TRY(h, upload(&h->d_l_ptr, p));
+    CU_TRY(h, upload(&h->d_l_idx, x));
+    h->K = K;
+    return BPOSD_OK;
+}
+
+static int logical_launch(bposd_handle *h, const uint8_t *d_err, const uint8_t *d_dec, long long B, uint8_t *d_fail,
+                          unsigned long long *d_count, int *d_minw, cudaStream_t st) {
+    LogicalArgs a;
+    a.n = h->n; a.K = h->K; a.l_ptr = h->d_l_ptr; a.l_idx = h->d_l_idx;
+    a.errors = d_err; a.dec = d_dec; a.B = B; a.fail = d_fail; a.fail_count = d_count; a.min_weight = d_minw;
+    const int grid = (int)std::min<long long>((B + 7) / 8, (long long)h->sm_count * 8);
+    logical_check_kernel<<<std::max(grid, 1), 256, 0, st>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    return BPOSD_OK;
+}
+
+extern "C" int bposd_logical_check(bposd_t *h, const uint8_t *d_err, const uint8_t *d_dec, int64_t B, uint8_t *d_fail,
+                                   int64_t *d_fail_count, int32_t *d_min_weight, void *stream) {
+    if (!h) return BPOSD_EINVAL;
+    if (!h->d_l_ptr) return fail(h, BPOSD_EINVAL, "call bposd_set_logicals first");
+    if (B < 0 || ((!d_err || !d_dec) && B > 0)) return fail(h, BPOSD_EINVAL, "bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (B == 0) return BPOSD_OK;
+    return logical_launch(h, d_err, d_dec, B, d_fail, reinterpret_cast<unsigned long long *>(d_fail_count), d_min_weight,
+                          static_cast<cudaStream_t>(stream));
+}
+
+__global__ void bp_success_kernel(const uint8_t *fail, const uint8_t *conv, long long B, unsigned long long *count) {
+    // BP counts as a success only where it converged and the residual is trivial (css_decode_sim.py:336-349)
+    unsigned long long c = 0;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x)
+        c += (conv[b] && !fail[b]) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+extern "C" int bposd_sample_and_decode(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector,
+                                       int64_t *h_counters, void *stream) {
+    if (!h || !h_counters) return fail(h, BPOSD_EINVAL, "NULL argument");
+    if (!h->d_t1) return fail(h, BPOSD_EINVAL, "call bposd_set_channel_thresholds first");
+    if (!h->d_l_ptr) return fail(h, BPOSD_EINVAL, "call bposd_set_logicals first");
+    if (B < 0) return fail(h, BPOSD_EINVAL, "negative batch size");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (B == 0) return BPOSD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = ensure_buffers(h, B, false, true);
+    if (rc) return rc;
+    rc = bposd_sample_syndromes(h, seed, shot0, B, sector, h->b_err, h->b_synd, stream);
+    if (rc) return rc;
+    bposd_out_t o{};
+    o.d_osdw = h->b_osdw; o.d_osd0 = h->b_osd0; o.d_bp = h->b_bp; o.d_converge = h->b_conv;
+    rc = bposd_decode_batch(h, h->b_synd, B, &o, nullptr, stream);
+    if (rc) return rc;
+    // d_counters: [0] osdw failures, [1] osd0 failures, [2] bp successes; b_iter reused as fail flags for bp
+    CU_TRY(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    const int big = 0x7fffffff;
+    CU_TRY(h, cudaMemcpyAsync(h->d_minw, &big, sizeof(int), cudaMemcpyHostToDevice, st));
+    rc = logical_launch(h, h->b_err, h->b_osdw, B, nullptr, h->d_counters + 0, h->d_minw, st);
+    if (rc) return rc;
+    rc = logical_launch(h, h->b_err, h->b_osd0, B, nullptr, h->d_counters + 1, h->d_minw, st);
+    if (rc) return rc;
+    uint8_t *bpfail = reinterpret_cast<uint8_t *>(h->b_iter);
+    rc = logical_launch(h, h->b_err, h->b_bp, B, bpfail, nullptr, nullptr, st);
+    if (rc) return rc;
+    bp_success_kernel<<<std::max(1, std::min(h->sm_count * 4, (int)((B + 255) / 256))), 256, 0, st>>>(bpfail, h->b_conv, B, h->d_counters + 2);
+    CU_TRY(h, cudaGetLastError());
+    unsigned long long c[8];
+    int minw = 0;
+    CU_TRY(h, cudaMemcpyAsync(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(&minw, h->d_minw, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    h->stats.launches += 5;
+    h_counters[0] += B;
+    h_counters[1] += h->stats.bp_converged;
+    h_counters[2] += (int64_t)c[2];
+    h_counters[3] += B - (int64_t)c[1];
+    h_counters[4] += B - (int64_t)c[0];
+    h_counters[5] += h->stats.osd_invocations;
+    h_counters[6] += h->stats.bp_iterations;
+    if (minw != big && (h_counters[7] <= 0 || minw < h_counters[7])) h_counters[7] = minw;
+    return BPOSD_OK;
+}

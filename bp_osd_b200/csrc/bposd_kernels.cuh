@@ -1,0 +1,637 @@
+// bposd_kernels.cuh -- sm_100a device code of the BP+OSD decode path.
+//
+// Kernels (one per hot-path function of SURVEY.md section 8a):
+//   bp_generic_kernel   rows a3-a8   flooding min-sum / product-sum BP, any degrees, one shot per
+//                                    CTA at a time, persistent CTAs pulling shots from an atomic
+//                                    queue (iteration counts are heavy tailed), messages in
+//                                    shared memory when they fit, else in an L2-resident
+//                                    per-CTA scratch in HBM.
+//   osd_kernel          rows a9-a14  per failed shot: stable LLR rank sort, GF(2) elimination
+//                                    kept as the m x m row-operation matrix T in shared memory
+//                                    (column-major bit-packed), OSD-0 read-out, OSD-E / OSD-CS
+//                                    candidate search (popcount or ordered soft weights).
+//   sample_syndrome_kernel rows a17-a18  Philox4x32-10 error sampler + H e mod 2.
+//   logical_check_kernel   row a19   residual against the logical operators + counters.
+//
+// fp64 mode must reproduce the reference arithmetic bit for bit: this file is compiled with
+// -fmad=false and every floating-point accumulation follows the edge order documented in
+// oracle/bposd_oracle.c (ascending column inside a check, ascending row inside a bit).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace bposd {
+
+struct GraphDev {
+    int m, n, nnz;
+    const int *row_ptr, *col_idx;            // CSR: ascending column inside a row
+    const int *col_ptr, *row_idx, *csc_slot; // CSC: ascending row inside a column; CSR slot of each entry
+};
+
+template <typename real>
+struct BpArgs {
+    GraphDev g;
+    int max_iter;
+    int method;   // 0 product-sum, 1 min-sum
+    real alpha0;  // 0 => 1 - 2^-it
+    const real *prior;
+    long long prior_stride; // 0: one prior vector for all shots, n: per-shot rows
+    const uint8_t *synd;
+    long long B;
+    uint8_t *bp, *osd0, *osdw;
+    real *llr;
+    uint8_t *converge;
+    int *iter;
+    int *fail_count;
+    int *fail_list;
+    real *fail_llr; // [capacity, n], used when llr == nullptr
+    int osd_off;
+    unsigned long long *queue;
+    unsigned long long *stat; // [0] converged shots, [1] iterations
+    real *g_scratch;          // global mode: per-CTA [2*nnz + n] reals
+    uint8_t *g_dec;           // global mode: per-CTA [n]
+};
+
+template <typename real> __device__ __forceinline__ real real_max();
+template <> __device__ __forceinline__ double real_max<double>() { return DBL_MAX; }
+template <> __device__ __forceinline__ float real_max<float>() { return FLT_MAX; }
+
+__device__ __forceinline__ double ms_alpha(double alpha0, int it) {
+    return alpha0 == 0.0 ? 1.0 - ldexp(1.0, -it) : alpha0;
+}
+__device__ __forceinline__ float ms_alpha(float alpha0, int it) {
+    return alpha0 == 0.0f ? 1.0f - ldexpf(1.0f, -it) : alpha0;
+}
+__device__ __forceinline__ double r_tanh(double x) { return tanh(x); }
+__device__ __forceinline__ float r_tanh(float x) { return tanhf(x); }
+__device__ __forceinline__ double r_log(double x) { return log(x); }
+__device__ __forceinline__ float r_log(float x) { return logf(x); }
+__device__ __forceinline__ double r_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float r_abs(float x) { return fabsf(x); }
+
+// ---------------------------------------------------------------------------------------------
+// Shared epilogue: write one shot's results and queue it for OSD if BP failed.
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+__device__ __forceinline__ void bp_write_shot(const BpArgs<real> &a, long long shot, bool conv, int iters,
+                                              const real *llr_s, const uint8_t *dec_s, int *sh_slot) {
+    const int n = a.g.n;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const bool final_here = conv || a.osd_off;
+    if (!final_here) {
+        if (tid == 0) {
+            int slot = atomicAdd(a.fail_count, 1);
+            a.fail_list[slot] = (int)shot;
+            *sh_slot = slot;
+        }
+        __syncthreads();
+    }
+    const long long base = shot * (long long)n;
+    for (int j = tid; j < n; j += T) {
+        uint8_t d = dec_s[j];
+        if (a.bp) a.bp[base + j] = d;
+        if (final_here) {
+            if (a.osd0) a.osd0[base + j] = d;
+            if (a.osdw) a.osdw[base + j] = d;
+        }
+        if (a.llr) a.llr[base + j] = llr_s[j];
+        else if (!final_here) a.fail_llr[(long long)(*sh_slot) * n + j] = llr_s[j];
+    }
+    if (tid == 0) {
+        if (a.converge) a.converge[shot] = conv ? 1 : 0;
+        if (a.iter) a.iter[shot] = iters;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic BP kernel (rows a3-a8).  Literal flooding schedule with separate bit->check and
+// check->bit arrays, any row/column degree.  SMEM=true: state carved from dynamic shared
+// memory; SMEM=false: per-CTA scratch in global memory (stays in the 126 MB L2 for the
+// concurrently active shots when it can).
+// Convergence of iteration `it` is tested at the start of pass it+1, folded into the check
+// sweep (each check XORs the hard decisions of its neighbours), so an iteration costs two
+// block barriers; the vote rides on __syncthreads_and.
+// ---------------------------------------------------------------------------------------------
+template <typename real, bool SMEM>
+__global__ void __launch_bounds__(1024) bp_generic_kernel(BpArgs<real> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GraphDev &g = a.g;
+    const int m = g.m, n = g.n, E = g.nnz;
+    const int tid = threadIdx.x, T = blockDim.x;
+
+    real *b2c, *c2b, *llr_s;
+    uint8_t *dec_s, *synd_s;
+    __shared__ long long sh_shot;
+    __shared__ int sh_slot;
+    if (SMEM) {
+        b2c = reinterpret_cast<real *>(smem_raw);
+        c2b = b2c + E;
+        llr_s = c2b + E;
+        dec_s = reinterpret_cast<uint8_t *>(llr_s + n);
+        synd_s = dec_s + n;
+    } else {
+        real *base = a.g_scratch + (size_t)blockIdx.x * (2 * (size_t)E + n);
+        b2c = base;
+        c2b = base + E;
+        llr_s = base + 2 * (size_t)E;
+        dec_s = a.g_dec + (size_t)blockIdx.x * n;
+        synd_s = smem_raw;
+    }
+    unsigned long long n_conv = 0, n_iter = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh_shot = (long long)atomicAdd(a.queue, 1ull);
+        __syncthreads();
+        const long long shot = sh_shot;
+        if (shot >= a.B) break;
+        const real *prior = a.prior + shot * a.prior_stride;
+
+        for (int i = tid; i < m; i += T) synd_s[i] = a.synd[shot * m + i] & 1;
+        for (int j = tid; j < n; j += T) { // a3
+            real p = prior[j];
+            llr_s[j] = p;
+            dec_s[j] = 0;
+            for (int q = g.col_ptr[j]; q < g.col_ptr[j + 1]; q++) b2c[g.csc_slot[q]] = p;
+        }
+        __syncthreads();
+
+        bool conv = false;
+        int iters = 0;
+        for (int it = 1;; it++) {
+            // ---- check sweep of pass `it` (+ convergence vote for pass it-1) ----
+            bool ok = true;
+            const bool last = it > a.max_iter;
+            if (a.method == 1) {
+                const real alpha = ms_alpha(a.alpha0, it);
+                for (int i = tid; i < m; i += T) { // a4
+                    const int beg = g.row_ptr[i], end = g.row_ptr[i + 1];
+                    real min1 = real_max<real>(), min2 = real_max<real>();
+                    int arg = -1, tot = synd_s[i], par = 0;
+                    for (int e = beg; e < end; e++) {
+                        real v = b2c[e];
+                        tot += (v <= 0) ? 1 : 0;
+                        real av = r_abs(v);
+                        if (av < min1) { min2 = min1; min1 = av; arg = e; }
+                        else if (av < min2) min2 = av;
+                        par ^= dec_s[g.col_idx[e]];
+                    }
+                    if (it > 1 && par != synd_s[i]) ok = false;
+                    if (!last)
+                        for (int e = beg; e < end; e++) {
+                            real v = b2c[e];
+                            int sg = tot + ((v <= 0) ? 1 : 0);
+                            real mag = (e == arg) ? min2 : min1;
+                            c2b[e] = mag * ((sg & 1) ? -alpha : alpha);
+                        }
+                }
+            } else {
+                for (int i = tid; i < m; i += T) { // a5
+                    const int beg = g.row_ptr[i], end = g.row_ptr[i + 1];
+                    int par = 0;
+                    real t = 1;
+                    for (int e = beg; e < end; e++) {
+                        par ^= dec_s[g.col_idx[e]];
+                        if (!last) {
+                            c2b[e] = t;
+                            t *= r_tanh(b2c[e] / 2);
+                        }
+                    }
+                    if (it > 1 && par != synd_s[i]) ok = false;
+                    if (!last) {
+                        t = 1;
+                        const real sgn = synd_s[i] ? (real)-1 : (real)1;
+                        for (int e = end - 1; e >= beg; e--) {
+                            real x = c2b[e] * t;
+                            c2b[e] = sgn * r_log((1 + x) / (1 - x));
+                            t *= r_tanh(b2c[e] / 2);
+                        }
+                    }
+                }
+            }
+            const int all_ok = __syncthreads_and(ok ? 1 : 0);
+            if (it > 1 && all_ok) { conv = true; iters = it - 1; break; } // a7
+            if (last) { iters = a.max_iter; break; }
+            // ---- bit sweep of pass `it` (a6 then a8) ----
+            for (int j = tid; j < n; j += T) {
+                const int beg = g.col_ptr[j], end = g.col_ptr[j + 1];
+                real t = prior[j];
+                for (int q = beg; q < end; q++) {
+                    int e = g.csc_slot[q];
+                    b2c[e] = t;
+                    t += c2b[e];
+                }
+                llr_s[j] = t;
+                dec_s[j] = (t <= 0) ? 1 : 0;
+                real s = 0;
+                for (int q = end - 1; q >= beg; q--) {
+                    int e = g.csc_slot[q];
+                    b2c[e] += s;
+                    s += c2b[e];
+                }
+            }
+            __syncthreads();
+        }
+        if (a.max_iter <= 0) { conv = false; iters = 0; }
+        bp_write_shot<real>(a, shot, conv, iters, llr_s, dec_s, &sh_slot);
+        if (tid == 0) { n_conv += conv ? 1 : 0; n_iter += (unsigned long long)iters; }
+    }
+    if (tid == 0 && a.stat) {
+        atomicAdd(&a.stat[0], n_conv);
+        atomicAdd(&a.stat[1], n_iter);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// OSD kernel (rows a9-a14): one CTA per failed shot.
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+struct OsdArgs {
+    GraphDev g;
+    int S;        // 32-bit words per column of T (ceil(m/32))
+    int St;       // stride of a T column in words (S, padded to odd)
+    int method;   // 0 osd0, 1 osd_e, 2 osd_cs
+    int order;    // search depth w
+    int uniform;  // 1: all channel probabilities equal and in (0,1): weight = popcount
+    const double *weight; // [n] log(1/p_j)
+    const uint8_t *synd;
+    const real *llr;      // [B, n] if llr_by_shot else [capacity, n] indexed by fail slot
+    int llr_by_shot;
+    const int *fail_count;
+    const int *fail_list;
+    uint8_t *osd0, *osdw;
+    unsigned long long *stat; // [2] osd invocations
+};
+
+__device__ __forceinline__ unsigned long long sort_key(double x) {
+    if (x == 0.0) x = 0.0; // -0 and +0 compare equal in the reference's comparator
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ unsigned long long sort_key(float x) {
+    if (x == 0.0f) x = 0.0f;
+    unsigned int b = __float_as_uint(x);
+    return (unsigned long long)((b >> 31) ? ~b : (b | 0x80000000u));
+}
+
+#define OSD_NONE 0xFFFFu
+
+// XOR of the T columns selected by H column c, word w
+__device__ __forceinline__ uint32_t reduced_col_word(const GraphDev &g, const uint32_t *Tc, int St, int c, int w) {
+    uint32_t v = 0;
+    for (int q = g.col_ptr[c]; q < g.col_ptr[c + 1]; q++) v ^= Tc[g.row_idx[q] * St + w];
+    return v;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(1024) osd_kernel(OsdArgs<real> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GraphDev &g = a.g;
+    const int m = g.m, n = g.n, S = a.S, St = a.St;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int maxrank = m < n ? m : n;
+
+    // shared-memory carve-up
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);            // n
+    double *red_w = reinterpret_cast<double *>(keys + n);                                   // 32
+    uint32_t *Tc = reinterpret_cast<uint32_t *>(red_w + 32);                                // m*St
+    uint32_t *vmask = Tc + (size_t)m * St;                                                  // S
+    uint32_t *used = vmask + S;                                                             // S
+    uint32_t *sprime = used + S;                                                            // S
+    uint32_t *wscr = sprime + S;                                                            // nwarps*(S+64)
+    int *red_c = reinterpret_cast<int *>(wscr + (size_t)nwarps * (S + 64));                 // 32
+    uint16_t *order = reinterpret_cast<uint16_t *>(red_c + 32);                             // n
+    uint16_t *prow = order + n;                                                             // n
+    uint16_t *np = prow + n;                                                                // n
+    __shared__ int sh_found, sh_p, sh_t, sh_rank, sh_nnp, sh_best;
+
+    const int nfail = *a.fail_count;
+    for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
+        const long long shot = a.fail_list[f];
+        const real *llr = a.llr + (a.llr_by_shot ? shot : (long long)f) * n;
+        const uint8_t *synd = a.synd + shot * m;
+        __syncthreads();
+
+        // ---- a9: stable ascending rank sort on (llr, index) ----
+        for (int j = tid; j < n; j += T) { keys[j] = sort_key(llr[j]); prow[j] = OSD_NONE; }
+        for (int r = tid; r < m; r += T) {
+            for (int w = 0; w < St; w++) Tc[r * St + w] = 0;
+            Tc[r * St + (r >> 5)] = 1u << (r & 31);
+        }
+        for (int w = tid; w < S; w += T) used[w] = 0;
+        if (tid == 0) { sh_t = 0; sh_rank = 0; sh_nnp = 0; }
+        __syncthreads();
+        for (int j = tid; j < n; j += T) {
+            const unsigned long long kj = keys[j];
+            int rank = 0;
+            for (int i = 0; i < n; i++) {
+                const unsigned long long ki = keys[i];
+                rank += (ki < kj || (ki == kj && i < j)) ? 1 : 0;
+            }
+            order[rank] = (uint16_t)j;
+        }
+        __syncthreads();
+
+        // ---- a10: elimination, columns in sorted order.  T (m x m) is kept column-major:
+        // Tc[r] = column r of T as an m-bit vector.  The reduced image of H column c is the XOR
+        // of the T columns named by the rows of c; a pivot row p is the lowest unused row set in
+        // it; the row operation "rows i in v\{p} += row p" is, column by column of T,
+        // "if bit p of Tc[r] then Tc[r] ^= v\{p}".
+        for (;;) {
+            if (warp == 0) {
+                int t = sh_t, rank = sh_rank, nnp = sh_nnp, found = 0, p = 0;
+                while (t < n && rank < maxrank) {
+                    const int c = order[t];
+                    int best = 0x7fffffff;
+                    for (int w = lane; w < S; w += 32) {
+                        uint32_t v = reduced_col_word(g, Tc, St, c, w);
+                        vmask[w] = v;
+                        uint32_t cand = v & ~used[w];
+                        if (cand && best == 0x7fffffff) best = w * 32 + __ffs(cand) - 1;
+                    }
+                    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                    __syncwarp();
+                    if (best != 0x7fffffff) {
+                        p = best;
+                        if (lane == 0) {
+                            prow[c] = (uint16_t)p;
+                            used[p >> 5] |= 1u << (p & 31);
+                            vmask[p >> 5] &= ~(1u << (p & 31));
+                        }
+                        rank++; t++; found = 1;
+                        __syncwarp();
+                        break;
+                    }
+                    if (lane == 0) np[nnp] = (uint16_t)t;
+                    nnp++; t++;
+                }
+                if (lane == 0) { sh_found = found; sh_p = p; sh_t = t; sh_rank = rank; sh_nnp = nnp; }
+            }
+            __syncthreads();
+            if (!sh_found) break;
+            const int p = sh_p, pw = p >> 5, pb = p & 31;
+            for (int r = tid; r < m; r += T) {
+                uint32_t *col = Tc + (size_t)r * St;
+                if ((col[pw] >> pb) & 1u)
+                    for (int w = 0; w < S; w++) col[w] ^= vmask[w];
+            }
+            __syncthreads();
+        }
+        // positions never examined (rank reached min(m,n)) are non-pivots, in order
+        {
+            const int t0 = sh_t, nnp0 = sh_nnp;
+            for (int t = t0 + tid; t < n; t += T) np[nnp0 + (t - t0)] = (uint16_t)t;
+        }
+        const int nnp = sh_nnp + (n - sh_t);
+        __syncthreads();
+
+        // ---- a11: s' = T s, then OSD-0 read-out ----
+        {
+            uint32_t *mine = wscr + (size_t)warp * (S + 64);
+            for (int w = lane; w < S; w += 32) {
+                uint32_t acc = 0;
+                for (int r = warp; r < m; r += nwarps)
+                    if (synd[r] & 1) acc ^= Tc[(size_t)r * St + w];
+                mine[w] = acc;
+            }
+            __syncthreads();
+            for (int w = tid; w < S; w += T) {
+                uint32_t acc = 0;
+                for (int k = 0; k < nwarps; k++) acc ^= wscr[(size_t)k * (S + 64) + w];
+                sprime[w] = acc & used[w];
+            }
+            __syncthreads();
+        }
+        const long long base = shot * (long long)n;
+        for (int j = tid; j < n; j += T) {
+            const unsigned pr = prow[j];
+            uint8_t x = (pr != OSD_NONE) ? (uint8_t)((sprime[pr >> 5] >> (pr & 31)) & 1u) : 0;
+            if (a.osd0) a.osd0[base + j] = x;
+            if (a.osdw) a.osdw[base + j] = x; // overwritten below if a candidate wins
+        }
+        if (tid == 0 && a.stat) atomicAdd(&a.stat[2], 1ull);
+
+        const int wd = a.order;
+        if (a.method == 0 || wd <= 0 || !a.osdw) continue;
+
+        // ---- a12-a14: candidate search.  Candidate -1 is OSD-0 itself. ----
+        long long ncand = (a.method == 1) ? ((1ll << wd) - 1) : ((long long)nnp + (long long)wd * (wd - 1) / 2);
+        uint32_t *s2 = wscr + (size_t)warp * (S + 64);
+        int *selcol = reinterpret_cast<int *>(s2 + S);
+        double bestW = 0;
+        long long bestC = -2; // nothing yet
+        for (long long c = -1 + warp; c < ncand; c += nwarps) {
+            // decode the selection of non-pivot positions
+            int nsel = 0;
+            __syncwarp();
+            if (c >= 0) {
+                if (a.method == 1) {
+                    long long v = c + 1;
+                    for (int b = 0; b < wd; b++)
+                        if ((v >> b) & 1) { if (lane == 0) selcol[nsel] = order[np[b]]; nsel++; }
+                } else if (c < nnp) {
+                    if (lane == 0) selcol[0] = order[np[c]];
+                    nsel = 1;
+                } else {
+                    int idx = (int)(c - nnp), i = 0;
+                    while (idx >= wd - 1 - i) { idx -= wd - 1 - i; i++; }
+                    if (lane == 0) { selcol[0] = order[np[i]]; selcol[1] = order[np[i + 1 + idx]]; }
+                    nsel = 2;
+                }
+            }
+            __syncwarp();
+            // s'' = s' + reduced images of the selected columns
+            int pc = 0;
+            for (int w = lane; w < S; w += 32) {
+                uint32_t v = sprime[w];
+                for (int q = 0; q < nsel; q++) v ^= reduced_col_word(g, Tc, St, selcol[q], w);
+                v &= used[w];
+                s2[w] = v;
+                pc += __popc(v);
+            }
+            double W;
+            if (a.uniform) {
+                for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+                W = (double)(pc + nsel);
+            } else {
+                __syncwarp();
+                W = 0;
+                for (int j0 = 0; j0 < n; j0 += 32) {
+                    const int j = j0 + lane;
+                    int x = 0;
+                    if (j < n) {
+                        const unsigned pr = prow[j];
+                        if (pr != OSD_NONE) x = (s2[pr >> 5] >> (pr & 31)) & 1u;
+                        else
+                            for (int q = 0; q < nsel; q++) x |= (selcol[q] == j) ? 1 : 0;
+                    }
+                    unsigned mask = __ballot_sync(0xffffffffu, x);
+                    while (mask) { // ascending j, sequential fp64 accumulation (row a14)
+                        const int b = __ffs(mask) - 1;
+                        W += a.weight[j0 + b];
+                        mask &= mask - 1;
+                    }
+                }
+            }
+            if (bestC == -2 || W < bestW) { bestW = W; bestC = c; }
+        }
+        if (lane == 0) { red_w[warp] = bestW; red_c[warp] = (int)bestC; }
+        __syncthreads();
+        if (tid == 0) {
+            double bw = 0; int bc = -2;
+            for (int k = 0; k < nwarps; k++) {
+                if (red_c[k] == -2) continue;
+                if (bc == -2 || red_w[k] < bw || (red_w[k] == bw && red_c[k] < bc)) { bw = red_w[k]; bc = red_c[k]; }
+            }
+            sh_best = bc;
+        }
+        __syncthreads();
+        const int bc = sh_best;
+        if (bc < 0) continue; // OSD-0 stands (strict '<' in the reference: ties keep the earlier)
+        // rebuild the winner and write it
+        if (warp == 0) {
+            int nsel = 0;
+            if (a.method == 1) {
+                long long v = (long long)bc + 1;
+                for (int b = 0; b < wd; b++)
+                    if ((v >> b) & 1) { if (lane == 0) selcol[nsel] = order[np[b]]; nsel++; }
+            } else if (bc < nnp) {
+                if (lane == 0) selcol[0] = order[np[bc]];
+                nsel = 1;
+            } else {
+                int idx = bc - nnp, i = 0;
+                while (idx >= wd - 1 - i) { idx -= wd - 1 - i; i++; }
+                if (lane == 0) { selcol[0] = order[np[i]]; selcol[1] = order[np[i + 1 + idx]]; }
+                nsel = 2;
+            }
+            __syncwarp();
+            for (int w = lane; w < S; w += 32) {
+                uint32_t v = sprime[w];
+                for (int q = 0; q < nsel; q++) v ^= reduced_col_word(g, Tc, St, selcol[q], w);
+                s2[w] = v & used[w];
+            }
+            if (lane == 0) sh_found = nsel;
+        }
+        __syncthreads();
+        {
+            const int nsel = sh_found;
+            const uint32_t *w0 = wscr;
+            const int *sel0 = reinterpret_cast<const int *>(w0 + S);
+            for (int j = tid; j < n; j += T) {
+                const unsigned pr = prow[j];
+                int x = 0;
+                if (pr != OSD_NONE) x = (w0[pr >> 5] >> (pr & 31)) & 1u;
+                else
+                    for (int q = 0; q < nsel; q++) x |= (sel0[q] == j) ? 1 : 0;
+                a.osdw[base + j] = (uint8_t)x;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Harness step kernels (rows a17-a19)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+struct SampleArgs {
+    GraphDev g;
+    const uint32_t *t1, *t2, *t3;
+    unsigned long long seed, shot0;
+    long long B;
+    int sector; // 0: X component, 1: Z component
+    uint8_t *errors;
+    uint8_t *synd;
+};
+
+// one CTA per shot (grid-stride): errors staged in shared memory, one thread per check for H e
+__global__ void __launch_bounds__(1024) sample_syndrome_kernel(SampleArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t *e_s = smem_raw;
+    const int n = a.g.n, m = a.g.m, tid = threadIdx.x, T = blockDim.x;
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const unsigned long long gshot = a.shot0 + (unsigned long long)b;
+        __syncthreads();
+        for (int q = tid; q * 4 < n; q += T) {
+            uint32_t c[4] = {(uint32_t)q, 0u, (uint32_t)gshot, (uint32_t)(gshot >> 32)};
+            philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                const int j = q * 4 + l;
+                if (j < n) {
+                    const uint32_t r = c[l];
+                    const uint32_t u1 = a.t1[j], u2 = a.t2[j], u3 = a.t3[j];
+                    const int z = (r < u1) || (r >= u2 && r < u3);
+                    const int x = (r >= u1 && r < u3);
+                    const uint8_t e = (uint8_t)(a.sector ? z : x);
+                    e_s[j] = e;
+                    if (a.errors) a.errors[b * n + j] = e;
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += T) {
+            int acc = 0;
+            for (int p = a.g.row_ptr[i]; p < a.g.row_ptr[i + 1]; p++) acc ^= e_s[a.g.col_idx[p]];
+            a.synd[b * m + i] = (uint8_t)acc;
+        }
+    }
+}
+
+struct LogicalArgs {
+    int n, K;
+    const int *l_ptr, *l_idx;
+    const uint8_t *errors, *dec;
+    long long B;
+    uint8_t *fail;
+    unsigned long long *fail_count;
+    int *min_weight;
+};
+
+// one warp per shot: lanes split the logical rows; a shot fails if any row has odd overlap
+__global__ void __launch_bounds__(256) logical_check_kernel(LogicalArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long nfail = 0;
+    int minw = 0x7fffffff;
+    for (long long b = warp0; b < a.B; b += nw) {
+        const uint8_t *e = a.errors + b * a.n, *d = a.dec + b * a.n;
+        int any = 0;
+        for (int r = lane; r < a.K; r += 32) {
+            int acc = 0;
+            for (int p = a.l_ptr[r]; p < a.l_ptr[r + 1]; p++) {
+                const int j = a.l_idx[p];
+                acc ^= (e[j] ^ d[j]) & 1;
+            }
+            any |= acc;
+        }
+        any = __any_sync(0xffffffffu, any);
+        if (any && a.min_weight) {
+            int wsum = 0;
+            for (int j = lane; j < a.n; j += 32) wsum += (e[j] ^ d[j]) & 1;
+            for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+            minw = min(minw, wsum);
+        }
+        if (lane == 0) {
+            if (a.fail) a.fail[b] = (uint8_t)any;
+            nfail += any ? 1 : 0;
+        }
+    }
+    if (lane == 0) {
+        if (a.fail_count && nfail) atomicAdd(a.fail_count, nfail);
+        if (a.min_weight && minw != 0x7fffffff) atomicMin(a.min_weight, minw);
+    }
+}
+
+} // namespace bposd

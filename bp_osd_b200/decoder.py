@@ -1,0 +1,350 @@
+"""``bposd_decoder`` / ``BpOsdDecoder``: the reference's decoder class, backed by the sm_100a kernels.
+
+Drop-in surface.  Constructor keywords and their meaning follow the
+reference's two call styles -- README.md:178-187 (``error_rate`` + ``channel_probs=[None]``) and
+src/bposd/css_decode_sim.py:444-463 (``channel_probs`` only) of /root/reference -- and the result
+attributes are the ones the reference reads after ``decode``: ``osdw_decoding``,
+``osd0_decoding``, ``bp_decoding`` (css_decode_sim.py:257,294,338; README.md:202), ``converge``
+(css_decode_sim.py:331-336), plus ``log_prob_ratios`` and ``iter``.  ``update_channel_probs``
+is css_decode_sim.py:229,248.  New: ``decode_batch(syndromes[B, m])`` for CUDA tensors (or numpy
+arrays), and the device-side Monte-Carlo step ``sample_and_decode``.
+
+All arithmetic runs in libbposd_b200.so through the C ABI (include/bposd_b200.h); this class
+only validates arguments, owns buffers and converts types.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _capi
+
+__all__ = ["BpOsdDecoder", "bposd_decoder", "BatchResult", "prob_thresholds"]
+
+_BP_NAMES = {
+    "ps": _capi.BP_PRODUCT_SUM, "product_sum": _capi.BP_PRODUCT_SUM, "prod_sum": _capi.BP_PRODUCT_SUM,
+    "0": _capi.BP_PRODUCT_SUM, 0: _capi.BP_PRODUCT_SUM,
+    "ms": _capi.BP_MINIMUM_SUM, "minimum_sum": _capi.BP_MINIMUM_SUM, "min_sum": _capi.BP_MINIMUM_SUM,
+    "1": _capi.BP_MINIMUM_SUM, 1: _capi.BP_MINIMUM_SUM,
+}
+_OSD_NAMES = {
+    "osd0": _capi.OSD_0, "osd_0": _capi.OSD_0, "0": _capi.OSD_0, "zero": _capi.OSD_0,
+    "osd_e": _capi.OSD_E, "osde": _capi.OSD_E, "e": _capi.OSD_E, "exhaustive": _capi.OSD_E,
+    "osd_cs": _capi.OSD_CS, "osdcs": _capi.OSD_CS, "cs": _capi.OSD_CS, "combination_sweep": _capi.OSD_CS,
+    "off": _capi.OSD_OFF, "osd_off": _capi.OSD_OFF, "none": _capi.OSD_OFF,
+}
+
+
+def prob_thresholds(p) -> np.ndarray:
+    """uint32 threshold T such that a 32-bit uniform r satisfies r < T with probability floor(p 2^32)/2^32."""
+    t = np.floor(np.asarray(p, dtype=np.float64) * 4294967296.0)
+    return np.clip(t, 0, 4294967295).astype(np.uint32)
+
+
+@dataclass
+class BatchResult:
+    """Outputs of ``decode_batch``; tensors live where the syndromes lived (CUDA or host)."""
+    osdw_decoding: object
+    osd0_decoding: object
+    bp_decoding: object
+    log_prob_ratios: object
+    converge: object
+    iter: object
+
+
+def _ptr(arr) -> Optional[int]:
+    return None if arr is None else arr.ctypes.data
+
+
+class BpOsdDecoder:
+    def __init__(self, parity_check_matrix, error_rate=None, channel_probs=None, max_iter=0,
+                 bp_method="minimum_sum", ms_scaling_factor=1.0, osd_method="osd_0", osd_order=0,
+                 error_channel=None, schedule="parallel", input_vector_type="syndrome",
+                 precision=64, device=None, **unused):
+        if schedule not in ("parallel", 0, "0"):
+            raise ValueError("only the parallel (flooding) BP schedule is implemented")
+        if input_vector_type not in ("syndrome", 0, "0"):
+            raise ValueError("only input_vector_type='syndrome' is implemented")
+        h = parity_check_matrix
+        if not sp.issparse(h):
+            h = np.asarray(h)
+            if h.ndim != 2:
+                raise TypeError("parity_check_matrix must be a 2-D array or a scipy sparse matrix")
+        h = sp.csr_matrix(h)
+        h.data = (np.asarray(h.data).astype(np.int64) % 2).astype(np.uint8)
+        h.eliminate_zeros()
+        h.sum_duplicates()
+        h.data %= 2
+        h.eliminate_zeros()
+        h.sort_indices()
+        self.m, self.n = (int(x) for x in h.shape)
+        self._pcm = h.astype(np.uint8)
+
+        probs = error_channel if error_channel is not None else channel_probs
+        if probs is not None and len(probs) and probs[0] is not None:
+            probs = np.array(probs, dtype=np.float64)  # copy: the caller's array may be read-only
+            if probs.shape != (self.n,):
+                raise ValueError(f"channel probability vector must have length {self.n}")
+        elif error_rate is not None:
+            probs = np.full(self.n, float(error_rate), dtype=np.float64)
+        else:
+            raise ValueError("specify either error_rate or channel_probs")
+        if np.any(probs < 0) or np.any(probs > 1) or np.any(np.isnan(probs)):
+            raise ValueError("channel probabilities must lie in [0, 1]")
+        self._probs = probs
+
+        key = bp_method.lower() if isinstance(bp_method, str) else bp_method
+        if key not in _BP_NAMES:
+            raise ValueError(f"bp_method '{bp_method}' is invalid; use 'ms'/'minimum_sum' or 'ps'/'product_sum'")
+        okey = str(osd_method).lower()
+        if okey not in _OSD_NAMES:
+            raise ValueError(f"osd_method '{osd_method}' is invalid; use 'osd0', 'osd_e' or 'osd_cs'")
+        if precision not in (64, 32):
+            raise ValueError("precision must be 64 (bit-exact mode) or 32 (fast mode)")
+        if int(max_iter) < 0:
+            raise ValueError("max_iter must be non-negative")
+        if int(osd_order) < 0:
+            raise ValueError("osd_order must be non-negative")
+        self.precision = int(precision)
+        self._real = np.float64 if self.precision == 64 else np.float32
+
+        if device is None:
+            device = 0
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    device = torch.cuda.current_device()
+            except Exception:
+                pass
+        self.device = int(device)
+
+        lib = _capi.load()
+        ip = np.ascontiguousarray(h.indptr, dtype=np.int32)
+        ix = np.ascontiguousarray(h.indices, dtype=np.int32)
+        handle = C.c_void_p()
+        rc = lib.bposd_create(_ptr(ip), _ptr(ix), self.m, self.n, _ptr(self._probs), int(max_iter),
+                              _BP_NAMES[key], float(ms_scaling_factor), _OSD_NAMES[okey], int(osd_order),
+                              self.precision, self.device, C.byref(handle))
+        _capi.check(None, rc)
+        self._h = handle
+        info = self.info()
+        self.rank, self.k = info["rank"], info["k"]
+        self.max_iter = info["max_iter"]
+        self.bp_method = "minimum_sum" if info["bp_method"] == 1 else "product_sum"
+        self.osd_method = {0: "osd_0", 1: "osd_e", 2: "osd_cs", 3: "off"}[info["osd_method"]]
+        self.osd_order = info["osd_order"]
+        self.ms_scaling_factor = float(ms_scaling_factor)
+        # result attributes, overwritten by every decode (reference semantics)
+        self.osdw_decoding = np.zeros(self.n, dtype=int)
+        self.osd0_decoding = np.zeros(self.n, dtype=int)
+        self.bp_decoding = np.zeros(self.n, dtype=int)
+        self.log_prob_ratios = np.zeros(self.n, dtype=np.float64)
+        self.converge = False
+        self.iter = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _capi.load().bposd_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _check(self, rc):
+        _capi.check(self._h, rc)
+
+    def info(self) -> dict:
+        inf = _capi.Info()
+        self._check(_capi.load().bposd_get_info(self._h, C.byref(inf)))
+        return {k: getattr(inf, k) for k, _ in _capi.Info._fields_}
+
+    def stats(self) -> dict:
+        st = _capi.Stats()
+        self._check(_capi.load().bposd_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _capi.Stats._fields_}
+
+    def set_tuning(self, bp_kernel=None, bp_threads=0, workspace_bytes=0):
+        """bp_kernel: None (auto), 0 generic/global, 1 generic/smem, 2 in-place smem."""
+        sel = 0 if bp_kernel is None else int(bp_kernel) + 1
+        self._check(_capi.load().bposd_set_tuning(self._h, sel, int(bp_threads), int(workspace_bytes)))
+
+    @property
+    def channel_probs(self):
+        return self._probs.copy()
+
+    @property
+    def decoding(self):
+        return self.osdw_decoding
+
+    def update_channel_probs(self, channel_probs):
+        p = np.array(channel_probs, dtype=np.float64)
+        if p.shape != (self.n,):
+            raise ValueError(f"channel probability vector must have length {self.n}")
+        if np.any(p < 0) or np.any(p > 1) or np.any(np.isnan(p)):
+            raise ValueError("channel probabilities must lie in [0, 1]")
+        self._probs = p
+        self._check(_capi.load().bposd_update_channel_probs(self._h, _ptr(p)))
+
+    # ------------------------------------------------------------------ decode
+    def decode(self, syndrome):
+        """Decode one syndrome; returns ``osdw_decoding`` and refreshes the result attributes."""
+        s = np.asarray(syndrome)
+        if s.ndim != 1 or s.shape[0] != self.m:
+            raise ValueError(f"syndrome must have length {self.m}")
+        dtype = s.dtype if np.issubdtype(s.dtype, np.integer) else int
+        res = self._decode_host(np.ascontiguousarray((s.astype(np.int64) & 1).astype(np.uint8)).reshape(1, self.m))
+        self.osdw_decoding = res.osdw_decoding[0].astype(dtype)
+        self.osd0_decoding = res.osd0_decoding[0].astype(dtype)
+        self.bp_decoding = res.bp_decoding[0].astype(dtype)
+        self.log_prob_ratios = res.log_prob_ratios[0].astype(np.float64)
+        self.converge = bool(res.converge[0])
+        self.iter = int(res.iter[0])
+        return self.osdw_decoding
+
+    def _decode_host(self, synd_u8: np.ndarray, want_llr: bool = True, want_all: bool = True,
+                     out: Optional[dict] = None) -> BatchResult:
+        B = synd_u8.shape[0]
+        out = out or {}
+        osdw = out.get("osdw") if "osdw" in out else np.empty((B, self.n), np.uint8)
+        osd0 = out.get("osd0") if "osd0" in out else (np.empty((B, self.n), np.uint8) if want_all else None)
+        bp = out.get("bp") if "bp" in out else (np.empty((B, self.n), np.uint8) if want_all else None)
+        llr = out.get("llr") if "llr" in out else (np.empty((B, self.n), self._real) if want_llr else None)
+        conv = out.get("converge") if "converge" in out else np.empty(B, np.uint8)
+        it = out.get("iter") if "iter" in out else np.empty(B, np.int32)
+        self._check(_capi.load().bposd_decode_host(self._h, _ptr(synd_u8), B, _ptr(osdw), _ptr(osd0), _ptr(bp),
+                                                   _ptr(llr), _ptr(conv), _ptr(it)))
+        return BatchResult(osdw, osd0, bp, llr, None if conv is None else conv.astype(bool), it)
+
+    def decode_batch(self, syndromes, return_llr: bool = True, return_all: bool = True, priors=None):
+        """Decode ``syndromes[B, m]``.
+
+        A CUDA ``torch.Tensor`` (uint8/bool/int, 0/1) is decoded in place on its device and the
+        result holds CUDA tensors; a numpy array goes through pinned-staging copies
+        (``bposd_decode_host``) and the result holds numpy arrays.  ``priors`` (CUDA tensor
+        [B, n] of prior LLRs in the handle's precision) selects per-shot channel priors.
+        """
+        try:
+            import torch
+        except Exception:  # pragma: no cover
+            torch = None
+        if torch is not None and isinstance(syndromes, torch.Tensor):
+            if not syndromes.is_cuda:
+                return self.decode_batch(syndromes.numpy(), return_llr, return_all)
+            if syndromes.dim() != 2 or syndromes.shape[1] != self.m:
+                raise ValueError(f"syndromes must have shape [B, {self.m}]")
+            if syndromes.device.index != self.device:
+                raise ValueError(f"syndromes live on cuda:{syndromes.device.index}, decoder on cuda:{self.device}")
+            s = syndromes
+            if s.dtype != torch.uint8:
+                s = (s != 0).to(torch.uint8)
+            s = s.contiguous()
+            B = s.shape[0]
+            dev = s.device
+            tdt = torch.float64 if self.precision == 64 else torch.float32
+            osdw = torch.empty((B, self.n), dtype=torch.uint8, device=dev)
+            osd0 = torch.empty((B, self.n), dtype=torch.uint8, device=dev) if return_all else None
+            bp = torch.empty((B, self.n), dtype=torch.uint8, device=dev) if return_all else None
+            llr = torch.empty((B, self.n), dtype=tdt, device=dev) if return_llr else None
+            conv = torch.empty(B, dtype=torch.uint8, device=dev)
+            it = torch.empty(B, dtype=torch.int32, device=dev)
+            pri = None
+            if priors is not None:
+                if not (isinstance(priors, torch.Tensor) and priors.is_cuda and priors.shape == (B, self.n)
+                        and priors.dtype == tdt):
+                    raise ValueError("priors must be a CUDA tensor [B, n] in the decoder's precision")
+                pri = priors.contiguous()
+            o = _capi.Out(osdw.data_ptr(), osd0.data_ptr() if osd0 is not None else None,
+                          bp.data_ptr() if bp is not None else None,
+                          llr.data_ptr() if llr is not None else None, conv.data_ptr(), it.data_ptr())
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            self._check(_capi.load().bposd_decode_batch(self._h, s.data_ptr(), B, C.byref(o),
+                                                        pri.data_ptr() if pri is not None else None, stream))
+            return BatchResult(osdw, osd0, bp, llr, conv.bool(), it)
+        s = np.asarray(syndromes)
+        if s.ndim != 2 or s.shape[1] != self.m:
+            raise ValueError(f"syndromes must have shape [B, {self.m}]")
+        s = np.ascontiguousarray((s.astype(np.int64) & 1).astype(np.uint8)) if s.dtype != np.uint8 else np.ascontiguousarray(s)
+        return self._decode_host(s, want_llr=return_llr, want_all=return_all)
+
+    # ------------------------------------------------------------------ harness step on the device
+    def set_error_channel(self, pz=None, px=None, py=None):
+        """Per-qubit Pauli probabilities for the device sampler (css_decode_sim.py:471-496 split)."""
+        z = np.zeros(self.n) if pz is None else np.broadcast_to(np.asarray(pz, np.float64), (self.n,))
+        x = np.zeros(self.n) if px is None else np.broadcast_to(np.asarray(px, np.float64), (self.n,))
+        y = np.zeros(self.n) if py is None else np.broadcast_to(np.asarray(py, np.float64), (self.n,))
+        t1, t2, t3 = (np.ascontiguousarray(prob_thresholds(v)) for v in (z, z + x, z + x + y))
+        self._check(_capi.load().bposd_set_channel_thresholds(self._h, _ptr(t1), _ptr(t2), _ptr(t3)))
+
+    def set_logicals(self, logicals):
+        l = sp.csr_matrix(logicals).astype(np.uint8)
+        l.data %= 2
+        l.eliminate_zeros()
+        l.sort_indices()
+        if l.shape[1] != self.n:
+            raise ValueError(f"logical operators must have {self.n} columns")
+        ip = np.ascontiguousarray(l.indptr, dtype=np.int32)
+        ix = np.ascontiguousarray(l.indices, dtype=np.int32)
+        self._check(_capi.load().bposd_set_logicals(self._h, _ptr(ip), _ptr(ix), int(l.shape[0])))
+
+    def sample_syndromes(self, seed: int, shot0: int, B: int, sector: int = 0, return_errors: bool = True):
+        """Device sampler + syndrome kernel; returns CUDA tensors (errors[B, n] or None, syndromes[B, m])."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        err = torch.empty((B, self.n), dtype=torch.uint8, device=dev) if return_errors else None
+        syn = torch.empty((B, self.m), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(_capi.load().bposd_sample_syndromes(self._h, int(seed), int(shot0), int(B), int(sector),
+                                                        err.data_ptr() if err is not None else None,
+                                                        syn.data_ptr(), stream))
+        return err, syn
+
+    def logical_check(self, errors, decodings):
+        """fail[b] = ((L @ (e ^ d)) % 2).any() on the device for CUDA uint8 tensors [B, n]."""
+        import torch
+        B = errors.shape[0]
+        fail = torch.empty(B, dtype=torch.uint8, device=errors.device)
+        stream = torch.cuda.current_stream(errors.device).cuda_stream
+        self._check(_capi.load().bposd_logical_check(self._h, errors.contiguous().data_ptr(),
+                                                     decodings.contiguous().data_ptr(), B, fail.data_ptr(),
+                                                     None, None, stream))
+        return fail.bool()
+
+    def sample_and_decode(self, seed: int, shot0: int, B: int, sector: int = 0, counters=None) -> np.ndarray:
+        """One Monte-Carlo step of B shots on the device; returns / accumulates int64 counters[8]:
+        shots, bp_converged, bp_success, osd0_success, osdw_success, osd_invocations, bp_iterations,
+        min_logical_weight."""
+        if counters is None:
+            counters = np.zeros(8, dtype=np.int64)
+        stream = None
+        try:
+            import torch
+            stream = torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream
+        except Exception:
+            pass
+        self._check(_capi.load().bposd_sample_and_decode(self._h, int(seed), int(shot0), int(B), int(sector),
+                                                         _ptr(counters), stream))
+        return counters
+
+
+class bposd_decoder(BpOsdDecoder):
+    """Legacy-signature class the reference re-exports (src/bposd/__init__.py:1; README.md:176-187)."""
+
+    def __init__(self, parity_check_matrix, error_rate=None, max_iter=0, bp_method="ms",
+                 ms_scaling_factor=1.0, channel_probs=(None,), osd_order=-1, osd_method="osd0",
+                 input_vector_type="syndrome", **kw):
+        okey = str(osd_method).lower()
+        if osd_order == -1:
+            osd_order = 0
+        if okey in ("osd0", "osd_0", "0", "zero"):
+            osd_order = 0
+        super().__init__(parity_check_matrix, error_rate=error_rate, channel_probs=list(channel_probs)
+                         if channel_probs is not None and len(channel_probs) == 1 and channel_probs[0] is None
+                         else channel_probs, max_iter=max_iter, bp_method=bp_method,
+                         ms_scaling_factor=ms_scaling_factor, osd_method=osd_method, osd_order=osd_order,
+                         input_vector_type=input_vector_type, **kw)

@@ -1,0 +1,152 @@
+/*
+ * bposd_b200.h -- C ABI of the B200-native BP+OSD decoder (libbposd_b200.so).
+ *
+ * This is the drop-in boundary for the decode hot path of quantumgizmos/bp_osd.  In the
+ * reference the boundary is a Python class, `bposd.bposd_decoder` == `ldpc.bposd_decoder`
+ * (/root/reference/src/bposd/__init__.py:1), also used as `ldpc.BpOsdDecoder`
+ * (src/bposd/css_decode_sim.py:6).  Each entry point below names the reference call site it
+ * replaces.  Plain pointers and sizes only; no torch or Python types.  INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions: every function returns 0 on success or a negative BPOSD_E* code; the message
+ * is available from bposd_last_error().  A handle is bound to one CUDA device, is not
+ * thread-safe, and owns copies of everything passed to bposd_create (the reference's
+ * harness keeps and re-uses its matrices and marks its probability arrays read-only,
+ * css_decode_sim.py:141-142,432-434).  Pointers named d_* are device pointers on the
+ * handle's device, h_* are host pointers.  `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef BPOSD_B200_H
+#define BPOSD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bposd_handle bposd_t;
+
+/* bp_method: README.md:183, css_decode_sim.py:35,70,448 ("ms"/"minimum_sum", "ps"/"product_sum") */
+#define BPOSD_BP_PRODUCT_SUM 0
+#define BPOSD_BP_MINIMUM_SUM 1
+/* osd_method: README.md:185, css_decode_sim.py:41,450.  OFF = BP only (no reference analogue) */
+#define BPOSD_OSD_0 0
+#define BPOSD_OSD_E 1
+#define BPOSD_OSD_CS 2
+#define BPOSD_OSD_OFF 3
+/* precision: 64 = bit-exact mode (IEEE double, reference accumulation order), 32 = fast mode */
+#define BPOSD_FP64 64
+#define BPOSD_FP32 32
+
+#define BPOSD_OK 0
+#define BPOSD_EINVAL (-1)  /* bad argument (maps to ValueError in the Python layer)          */
+#define BPOSD_ECUDA (-2)   /* CUDA runtime error; bposd_last_error() holds the CUDA message   */
+#define BPOSD_ENOMEM (-3)  /* host or device allocation failed                                */
+#define BPOSD_EUNSUP (-4)  /* configuration not supported by the kernels built into this lib  */
+
+/* Device output block of bposd_decode_batch.  Any pointer may be NULL (that output is not
+ * produced).  Layout row-major [B, n].  Mirrors the result attributes the reference reads
+ * after decode(): osdw_decoding / osd0_decoding / bp_decoding (css_decode_sim.py:257,294,338;
+ * README.md:202), converge (css_decode_sim.py:331-336), log_prob_ratios and iter (ldpc
+ * attributes required by BASELINE.json's north_star). */
+typedef struct {
+    uint8_t *d_osdw;    /* [B, n] 0/1                                                  */
+    uint8_t *d_osd0;    /* [B, n] 0/1                                                  */
+    uint8_t *d_bp;      /* [B, n] 0/1, hard decision of the last BP iteration          */
+    void *d_llr;        /* [B, n] double (precision 64) or float (precision 32)        */
+    uint8_t *d_converge;/* [B] 1 if BP reproduced the syndrome                         */
+    int32_t *d_iter;    /* [B] BP iterations executed                                  */
+} bposd_out_t;
+
+typedef struct {
+    int32_t m, n, nnz, rank, k;     /* k = n - rank                                      */
+    int32_t max_iter, bp_method, osd_method, osd_order, precision, device;
+    int32_t bp_kernel;              /* 0 generic/global, 1 generic/smem, 2 in-place smem  */
+    int32_t bp_threads, bp_ctas_per_sm, bp_smem_bytes;
+    int32_t osd_threads, osd_smem_bytes, sm_count;
+    double ms_scaling_factor;
+} bposd_info_t;
+
+/* Per-launch statistics of the most recent bposd_decode_batch / bposd_decode_host call
+ * (read back with a stream synchronise). */
+typedef struct {
+    int64_t shots;
+    int64_t bp_converged;
+    int64_t osd_invocations;
+    int64_t bp_iterations;   /* sum over shots of iterations executed */
+    float ms_bp;             /* CUDA-event time of the BP kernels, summed over chunks  */
+    float ms_osd;            /* CUDA-event time of the OSD kernels, summed over chunks */
+    int32_t launches;        /* kernels launched */
+    int32_t chunks;
+} bposd_stats_t;
+
+/* Constructor.  Replaces `bposd_decoder(H, error_rate=..., channel_probs=..., max_iter=...,
+ * bp_method=..., ms_scaling_factor=..., osd_method=..., osd_order=...)`
+ * (README.md:178-187; css_decode_sim.py:444-463).  H is CSR over GF(2) with ascending
+ * column indices inside each row.  max_iter == 0 means n (css_decode_sim.py:72).
+ * ms_scaling_factor == 0 selects the variable factor 1 - 2^-iteration (README.md:184). */
+int bposd_create(const int32_t *h_indptr, const int32_t *h_indices, int32_t m, int32_t n,
+                 const double *h_channel_probs, int32_t max_iter, int32_t bp_method,
+                 double ms_scaling_factor, int32_t osd_method, int32_t osd_order,
+                 int32_t precision, int32_t device, bposd_t **out);
+
+/* Replaces `decoder.update_channel_probs(probs)` (css_decode_sim.py:229,248). */
+int bposd_update_channel_probs(bposd_t *h, const double *h_channel_probs);
+
+/* Batched form of `decoder.decode(syndrome)` (README.md:197; css_decode_sim.py:174-202):
+ * d_syndromes is [B, m] uint8 (0/1) on the device.  Asynchronous on `stream` except for a
+ * final stream synchronise that collects bposd_stats_t.
+ * d_priors_per_shot: NULL, or [B, n] prior LLRs log((1-p)/p) in the handle's precision, one
+ * row per shot (the per-shot channel update of css_decode_sim.py:207-248). */
+int bposd_decode_batch(bposd_t *h, const uint8_t *d_syndromes, int64_t B, const bposd_out_t *out,
+                       const void *d_priors_per_shot, void *stream);
+
+/* Same, with host buffers: copies h_syndromes [B, m] to the device, decodes, copies the
+ * requested outputs back (NULL = not wanted).  This is what the reference-facing
+ * `decode()` / `decode_batch(numpy)` call goes through; pinned staging is internal. */
+int bposd_decode_host(bposd_t *h, const uint8_t *h_syndromes, int64_t B, uint8_t *h_osdw,
+                      uint8_t *h_osd0, uint8_t *h_bp, void *h_llr, uint8_t *h_converge,
+                      int32_t *h_iter);
+
+/* Device-side restatement of the harness step `_generate_error` + `H @ e % 2`
+ * (css_decode_sim.py:465-498,173-201): Philox4x32-10, counter (j/4, 0, shot_lo, shot_hi),
+ * key = seed, one 32-bit uniform r per qubit; r < t1 -> Z, t1 <= r < t2 -> X, t2 <= r < t3 -> Y
+ * (h_t1..h_t3 are per-qubit cumulative uint32 thresholds).  Writes the sector error this
+ * decoder corrects (`sector` 0: X component, 1: Z component) to d_errors [B, n] (may be
+ * NULL) and its syndrome H e mod 2 to d_syndromes [B, m]. */
+int bposd_set_channel_thresholds(bposd_t *h, const uint32_t *h_t1, const uint32_t *h_t2,
+                                 const uint32_t *h_t3);
+int bposd_sample_syndromes(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector,
+                           uint8_t *d_errors, uint8_t *d_syndromes, void *stream);
+
+/* Logical operators for the failure check (css_decode_sim.py:257-272): CSR, K rows. */
+int bposd_set_logicals(bposd_t *h, const int32_t *h_indptr, const int32_t *h_indices, int32_t K);
+
+/* fail[b] = ((L @ (e ^ d)) % 2).any() for B shots; also accumulates *d_fail_count (int64,
+ * may be NULL) and the minimum weight of a failing residual into *d_min_weight (int32, may
+ * be NULL; css_decode_sim.py:261-264). */
+int bposd_logical_check(bposd_t *h, const uint8_t *d_errors, const uint8_t *d_decodings,
+                        int64_t B, uint8_t *d_fail, int64_t *d_fail_count, int32_t *d_min_weight,
+                        void *stream);
+
+/* One Monte-Carlo step of one sector, all on the device (css_decode_sim.py:163-205 for a
+ * single sector): sample B errors starting at global shot index shot0, syndromes, decode,
+ * residual check against the logicals, accumulate into h_counters[8] (int64):
+ * [0] shots, [1] bp_converged, [2] bp_success, [3] osd0_success, [4] osdw_success,
+ * [5] osd_invocations, [6] bp_iterations, [7] min_logical_weight (min-combined). */
+int bposd_sample_and_decode(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector,
+                            int64_t *h_counters, void *stream);
+
+int bposd_get_info(const bposd_t *h, bposd_info_t *info);
+int bposd_get_stats(const bposd_t *h, bposd_stats_t *stats);
+/* Tuning knobs (0 = keep automatic): BP kernel variant (+1 of bposd_info_t.bp_kernel),
+ * threads per CTA, workspace bytes for the failed-shot LLR buffer. */
+int bposd_set_tuning(bposd_t *h, int32_t bp_kernel_plus1, int32_t bp_threads, int64_t workspace_bytes);
+const char *bposd_last_error(const bposd_t *h);
+const char *bposd_version(void);
+void bposd_destroy(bposd_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPOSD_B200_H */
