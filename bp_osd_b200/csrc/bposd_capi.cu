@@ -57,7 +57,7 @@ struct bposd_handle {
     uint8_t *b_synd = nullptr, *b_err = nullptr, *b_osdw = nullptr, *b_osd0 = nullptr, *b_bp = nullptr, *b_conv = nullptr;
     void *b_llr = nullptr;
     int32_t *b_iter = nullptr;
-    long long b_cap = 0, fail_list_cap = 0;
+    long long b_cap = 0, fail_list_cap = 0, fail_llr_cap = 0;
     unsigned long long *d_counters = nullptr; // 8 words
     int *d_minw = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -375,7 +375,12 @@ static int decode_batch_t(bposd_handle *h, const uint8_t *d_synd, long long B, c
     long long chunk = B;
     if (need_ws) {
         chunk = std::min(B, h->fail_cap);
-        if (!h->d_fail_llr) CU_TRY(h, cudaMalloc(&h->d_fail_llr, (size_t)h->fail_cap * n * sizeof(real)));
+        if (!h->d_fail_llr || chunk > h->fail_llr_cap) {
+            cudaFree(h->d_fail_llr);
+            h->d_fail_llr = nullptr;
+            CU_TRY(h, cudaMalloc(&h->d_fail_llr, (size_t)chunk * n * sizeof(real)));
+            h->fail_llr_cap = chunk;
+        }
     }
     chunk = std::min<long long>(chunk, 1ll << 30);
     if (!h->d_fail_list || chunk > h->fail_list_cap) { // fail list holds one chunk

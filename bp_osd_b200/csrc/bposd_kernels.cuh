@@ -15,7 +15,7 @@
 //
 // fp64 mode must reproduce the reference arithmetic bit for bit: this file is compiled with
 // -fmad=false and every floating-point accumulation follows the edge order documented in
-// oracle/bposd_oracle.c (ascending column inside a check, ascending row inside a bit).
+// SURVEY.md section 8a (ascending column inside a check, ascending row inside a bit).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -211,31 +211,43 @@ class BpOsdDecoder:
                      out: Optional[dict] = None) -> BatchResult:
         B = synd_u8.shape[0]
         out = out or {}
-        osdw = out.get("osdw") if "osdw" in out else np.empty((B, self.n), np.uint8)
-        osd0 = out.get("osd0") if "osd0" in out else (np.empty((B, self.n), np.uint8) if want_all else None)
-        bp = out.get("bp") if "bp" in out else (np.empty((B, self.n), np.uint8) if want_all else None)
-        llr = out.get("llr") if "llr" in out else (np.empty((B, self.n), self._real) if want_llr else None)
-        conv = out.get("converge") if "converge" in out else np.empty(B, np.uint8)
-        it = out.get("iter") if "iter" in out else np.empty(B, np.int32)
+
+        def buf(key, shape, dtype, want=True):
+            a = out.get(key)
+            if a is None:
+                return np.empty(shape, dtype) if want else None
+            if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.shape == tuple(shape) and a.flags.c_contiguous):
+                raise ValueError(f"out['{key}'] must be a C-contiguous {np.dtype(dtype)} array of shape {tuple(shape)}")
+            return a
+
+        osdw = buf("osdw", (B, self.n), np.uint8)
+        osd0 = buf("osd0", (B, self.n), np.uint8, want_all)
+        bp = buf("bp", (B, self.n), np.uint8, want_all)
+        llr = buf("llr", (B, self.n), self._real, want_llr)
+        conv = buf("converge", (B,), np.uint8)
+        it = buf("iter", (B,), np.int32)
         self._check(_capi.load().bposd_decode_host(self._h, _ptr(synd_u8), B, _ptr(osdw), _ptr(osd0), _ptr(bp),
                                                    _ptr(llr), _ptr(conv), _ptr(it)))
         return BatchResult(osdw, osd0, bp, llr, None if conv is None else conv.astype(bool), it)
 
-    def decode_batch(self, syndromes, return_llr: bool = True, return_all: bool = True, priors=None):
+    def decode_batch(self, syndromes, return_llr: bool = True, return_all: bool = True, priors=None, out=None):
         """Decode ``syndromes[B, m]``.
 
         A CUDA ``torch.Tensor`` (uint8/bool/int, 0/1) is decoded in place on its device and the
         result holds CUDA tensors; a numpy array goes through pinned-staging copies
         (``bposd_decode_host``) and the result holds numpy arrays.  ``priors`` (CUDA tensor
         [B, n] of prior LLRs in the handle's precision) selects per-shot channel priors.
+        ``out`` may hold preallocated result buffers (keys ``osdw osd0 bp llr converge iter``; CUDA
+        tensors for CUDA input, numpy arrays -- ideally pinned -- for host input).
         """
+        out = out or {}
         try:
             import torch
         except Exception:  # pragma: no cover
             torch = None
         if torch is not None and isinstance(syndromes, torch.Tensor):
             if not syndromes.is_cuda:
-                return self.decode_batch(syndromes.numpy(), return_llr, return_all)
+                return self.decode_batch(syndromes.numpy(), return_llr, return_all, out=out)
             if syndromes.dim() != 2 or syndromes.shape[1] != self.m:
                 raise ValueError(f"syndromes must have shape [B, {self.m}]")
             if syndromes.device.index != self.device:
@@ -247,12 +259,21 @@ class BpOsdDecoder:
             B = s.shape[0]
             dev = s.device
             tdt = torch.float64 if self.precision == 64 else torch.float32
-            osdw = torch.empty((B, self.n), dtype=torch.uint8, device=dev)
-            osd0 = torch.empty((B, self.n), dtype=torch.uint8, device=dev) if return_all else None
-            bp = torch.empty((B, self.n), dtype=torch.uint8, device=dev) if return_all else None
-            llr = torch.empty((B, self.n), dtype=tdt, device=dev) if return_llr else None
-            conv = torch.empty(B, dtype=torch.uint8, device=dev)
-            it = torch.empty(B, dtype=torch.int32, device=dev)
+            def buf(key, shape, dtype, want=True):
+                t = out.get(key)
+                if t is None:
+                    return torch.empty(shape, dtype=dtype, device=dev) if want else None
+                if not (t.is_cuda and t.device == dev and t.dtype == dtype and tuple(t.shape) == tuple(shape)
+                        and t.is_contiguous()):
+                    raise ValueError(f"out['{key}'] must be a contiguous {dtype} CUDA tensor of shape {tuple(shape)}")
+                return t
+
+            osdw = buf("osdw", (B, self.n), torch.uint8)
+            osd0 = buf("osd0", (B, self.n), torch.uint8, return_all)
+            bp = buf("bp", (B, self.n), torch.uint8, return_all)
+            llr = buf("llr", (B, self.n), tdt, return_llr)
+            conv = buf("converge", (B,), torch.uint8)
+            it = buf("iter", (B,), torch.int32)
             pri = None
             if priors is not None:
                 if not (isinstance(priors, torch.Tensor) and priors.is_cuda and priors.shape == (B, self.n)
@@ -270,7 +291,7 @@ class BpOsdDecoder:
         if s.ndim != 2 or s.shape[1] != self.m:
             raise ValueError(f"syndromes must have shape [B, {self.m}]")
         s = np.ascontiguousarray((s.astype(np.int64) & 1).astype(np.uint8)) if s.dtype != np.uint8 else np.ascontiguousarray(s)
-        return self._decode_host(s, want_llr=return_llr, want_all=return_all)
+        return self._decode_host(s, want_llr=return_llr, want_all=return_all, out=out)
 
     # ------------------------------------------------------------------ harness step on the device
     def set_error_channel(self, pz=None, px=None, py=None):

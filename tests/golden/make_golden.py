@@ -1,0 +1,60 @@
+"""Regenerates tests/golden/*.npz.
+
+The reference's decoder lives in the third-party package `ldpc`, which cannot be installed offline,
+so these are NOT outputs of the reference: they are outputs of the CPU oracle
+(oracle/bposd_oracle.c) on seeded inputs, kept only where the independently written second
+restatement (oracle/slow_ref.py) agrees bit for bit.  They pin the oracle against regressions and
+give the GPU parity tests fixed vectors.  The one vector that does come from the reference's
+documentation (README.md:194-216, "G1") is hard-coded in tests/test_oracle.py.
+
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from bp_osd_b200 import codes  # noqa: E402
+from oracle.oracle import OracleDecoder  # noqa: E402
+from oracle.slow_ref import SlowDecoder  # noqa: E402
+
+CASES = {
+    "d5_ms_cs7": dict(cfg=1, p=0.08, shots=200, kw=dict(max_iter=0, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=7)),
+    "d5_ms625_e8": dict(cfg=1, p=0.10, shots=200, kw=dict(max_iter=5, bp_method="ms", ms_scaling_factor=0.625, osd_method="osd_e", osd_order=8)),
+    "hgp400_ms_cs7": dict(cfg=2, p=0.06, shots=40, kw=dict(max_iter=40, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=7)),
+    "hgp400_ms_osd0": dict(cfg=2, p=0.07, shots=40, kw=dict(max_iter=25, bp_method="ms", ms_scaling_factor=0.9, osd_method="osd0", osd_order=0)),
+}
+
+
+def main():
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    for name, c in CASES.items():
+        H = codes.config_code(c["cfg"]).hz
+        n = H.shape[1]
+        rng = np.random.default_rng(20251018)
+        e = (rng.random((c["shots"], n)) < c["p"]).astype(np.uint8)
+        s = np.asarray((H @ e.T) % 2, dtype=np.uint8).T.copy()
+        kw = c["kw"]
+        o = OracleDecoder(H, error_rate=c["p"], **kw)
+        ref = o.decode_batch(s)
+        slow = SlowDecoder(H, [c["p"]] * n, kw["max_iter"], kw["bp_method"], kw["ms_scaling_factor"],
+                           "osd0" if kw["osd_method"] == "osd0" else kw["osd_method"], kw["osd_order"])
+        for b in range(c["shots"]):
+            x = slow.decode(s[b])
+            assert (np.array(x) == ref["osdw"][b]).all(), (name, b)
+            assert (np.array(slow.osd0_decoding) == ref["osd0"][b]).all(), (name, b)
+            assert (np.array(slow.bp_decoding) == ref["bp"][b]).all(), (name, b)
+            assert (np.array(slow.llr) == ref["llr"][b]).all(), (name, b)
+            assert slow.converge == bool(ref["converge"][b]) and slow.iter == ref["iter"][b], (name, b)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), cfg=c["cfg"], p=c["p"],
+                            kw=np.array(repr(kw)), syndromes=np.packbits(s, axis=1), m=H.shape[0],
+                            osdw=np.packbits(ref["osdw"], axis=1), osd0=np.packbits(ref["osd0"], axis=1),
+                            bp=np.packbits(ref["bp"], axis=1), llr=ref["llr"], converge=ref["converge"],
+                            iter=ref["iter"], n=n)
+        print(name, "ok:", c["shots"], "shots,", int((1 - ref["converge"]).sum()), "went to OSD")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,341 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+fp64 mode: bit-exact osdw/osd0/bp decodings, converge flags, iteration counts and LLRs for min-sum;
+product-sum LLRs within the stated tolerance (CUDA libm != glibc libm bit for bit).
+fp32 mode: statistical (logical error rate inside the 95% CI of the oracle's).
+Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+
+from bp_osd_b200 import codes
+from bp_osd_b200.hgp import hgp
+from tests._util import golden_names, load_golden, random_syndromes
+
+pytestmark = pytest.mark.gpu
+
+MS_CS7 = dict(max_iter=0, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=7)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda(cuda_lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def gpu_decode(torch, H, syn, kernel=None, threads=0, precision=64, probs=None, error_rate=None, **kw):
+    from bp_osd_b200 import BpOsdDecoder
+    d = BpOsdDecoder(H, error_rate=error_rate, channel_probs=probs, precision=precision, **kw)
+    if kernel is not None or threads:
+        d.set_tuning(bp_kernel=kernel, bp_threads=threads)
+    r = d.decode_batch(torch.tensor(syn, device="cuda"))
+    torch.cuda.synchronize()
+    out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
+               llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
+    return d, out
+
+
+def assert_exact(out, ref, llr_exact=True):
+    for k in ("osdw", "osd0", "bp"):
+        bad = np.flatnonzero((out[k] != ref[k]).any(1))
+        assert bad.size == 0, f"{k} differs for shots {bad[:10]}"
+    assert (out["converge"] == ref["converge"].astype(bool)).all()
+    assert (out["iter"] == ref["iter"]).all()
+    if llr_exact:
+        assert (out["llr"] == ref["llr"]).all(), "log_prob_ratios not bit-exact"
+
+
+def test_g1_readme_known_answer_on_gpu(torch_cuda):
+    # /root/reference/README.md:145-216 through the drop-in class, legacy signature
+    from bp_osd_b200 import bposd_decoder
+    sc = hgp(codes.rep_code(3))
+    bpd = bposd_decoder(sc.hz, error_rate=0.05, channel_probs=[None], max_iter=sc.N, bp_method="ms",
+                        ms_scaling_factor=0, osd_method="osd_cs", osd_order=7)
+    error = np.zeros(sc.N).astype(int)
+    error[[5, 12]] = 1
+    syndrome = sc.hz @ error % 2
+    bpd.decode(syndrome)
+    assert (bpd.osdw_decoding == [0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0]).all()
+    residual = (bpd.osdw_decoding + error) % 2
+    assert not (sc.lz @ residual % 2).any()
+    assert bpd.converge and bpd.iter == 2
+    assert (bpd.osd0_decoding == bpd.bp_decoding).all()
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_golden_fixtures(torch_cuda, cfg_codes, name, kernel):
+    g = load_golden(name)
+    H = cfg_codes(g["cfg"]).hz
+    d, out = gpu_decode(torch_cuda, H, g["syndromes"], kernel=kernel, error_rate=g["p"], **g["kw"])
+    assert_exact(out, g)
+
+
+@pytest.mark.parametrize("cfg,p,B,kw", [
+    (1, 0.05, 3000, MS_CS7),
+    (1, 0.10, 1500, dict(max_iter=7, bp_method="ms", ms_scaling_factor=0.625, osd_method="osd_e", osd_order=9)),
+    (2, 0.05, 1500, MS_CS7),
+    (2, 0.08, 400, dict(MS_CS7, osd_method="osd0", osd_order=0)),
+    (3, 0.05, 600, MS_CS7),
+    (3, 0.06, 200, dict(MS_CS7, max_iter=30)),
+    (4, 0.05, 300, dict(max_iter=20, bp_method="ms", ms_scaling_factor=0.9, osd_method="osd_e", osd_order=10)),
+], ids=["d5", "d5-osd_e9", "hgp400", "hgp400-osd0", "hgp1922", "hgp1922-it30", "lp882-ms-e10"])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_min_sum_bit_exact(torch_cuda, oracle_mod, cfg_codes, cfg, p, B, kw, kernel):
+    H = cfg_codes(cfg).hz
+    _, syn = random_syndromes(H, p, B, seed=12345)
+    ref = oracle_mod.OracleDecoder(H, error_rate=p, **kw).decode_batch(syn)
+    d, out = gpu_decode(torch_cuda, H, syn, kernel=kernel, error_rate=p, **kw)
+    assert d.info()["bp_kernel"] == kernel
+    assert_exact(out, ref)
+    st = d.stats()
+    assert st["bp_converged"] == int(ref["converge"].sum())
+    assert st["bp_iterations"] == int(ref["iter"].sum())
+    assert st["osd_invocations"] == B - st["bp_converged"]
+
+
+@pytest.mark.parametrize("threads", [32, 64, 256, 1024])
+def test_thread_counts_do_not_change_results(torch_cuda, oracle_mod, cfg_codes, threads):
+    H = cfg_codes(2).hz
+    _, syn = random_syndromes(H, 0.06, 300, seed=8)
+    ref = oracle_mod.OracleDecoder(H, error_rate=0.06, **MS_CS7).decode_batch(syn)
+    for kernel in (1, 2):
+        _, out = gpu_decode(torch_cuda, H, syn, kernel=kernel, threads=threads, error_rate=0.06, **MS_CS7)
+        assert_exact(out, ref)
+
+
+def test_product_sum_lifted_product(torch_cuda, oracle_mod, cfg_codes):
+    """Config 4: product-sum BP + OSD-E 10.  tanh/log come from CUDA's libm, so LLRs carry a tolerance:
+    1e-9 relative for shots that stop within 20 iterations (error grows with the iteration count)."""
+    H = cfg_codes(4).hz
+    kw = dict(max_iter=0, bp_method="ps", ms_scaling_factor=0, osd_method="osd_e", osd_order=10)
+    _, syn = random_syndromes(H, 0.05, 300, seed=12345)
+    ref = oracle_mod.OracleDecoder(H, error_rate=0.05, **kw).decode_batch(syn)
+    for kernel in (0, 1):
+        _, out = gpu_decode(torch_cuda, H, syn, kernel=kernel, error_rate=0.05, **kw)
+        same = (out["converge"] == ref["converge"].astype(bool)) & (out["iter"] == ref["iter"])
+        assert same.mean() > 0.97
+        assert ((out["bp"] == ref["bp"]).all(1) | ~same).mean() > 0.97
+        assert (out["osdw"] == ref["osdw"]).all(1).mean() > 0.95
+        quick = same & (ref["iter"] <= 20)
+        assert quick.sum() > 50
+        rel = np.abs(out["llr"][quick] - ref["llr"][quick]) / np.abs(ref["llr"][quick])
+        assert rel.max() < 1e-9
+        Hd = H.toarray()
+        assert ((out["osdw"] @ Hd.T % 2) == syn).all()
+
+
+def test_nonuniform_and_zero_probabilities(torch_cuda, oracle_mod, cfg_codes):
+    """Soft OSD weights in ascending-index fp64 order, and p = 0 entries (prior +inf, weight inf) without NaN."""
+    H = cfg_codes(2).hz
+    n = H.shape[1]
+    rng = np.random.default_rng(21)
+    probs = rng.uniform(0.01, 0.15, size=n)
+    probs[::17] = 0.0
+    kw = dict(max_iter=12, bp_method="ms", ms_scaling_factor=0.8, osd_method="osd_cs", osd_order=6)
+    e = (rng.random((400, n)) < probs).astype(np.uint8)
+    syn = np.asarray((H @ e.T) % 2, dtype=np.uint8).T.copy()
+    with np.errstate(divide="ignore"):
+        ref = oracle_mod.OracleDecoder(H, channel_probs=probs, **kw).decode_batch(syn)
+    for kernel in (1, 2):
+        d, out = gpu_decode(torch_cuda, H, syn, kernel=kernel, probs=probs, **kw)
+        assert_exact(out, ref)
+        assert not np.isnan(out["llr"]).any()
+    assert (ref["converge"] == 0).sum() > 50  # the soft-weight OSD path was exercised
+
+
+def test_update_channel_probs(torch_cuda, oracle_mod, cfg_codes):
+    # css_decode_sim.py:229,248: new probabilities change priors and OSD weights of the next decode
+    from bp_osd_b200 import BpOsdDecoder
+    H = cfg_codes(1).hz
+    n = H.shape[1]
+    kw = dict(max_iter=3, bp_method="ms", ms_scaling_factor=0.7, osd_method="osd_cs", osd_order=5)
+    d = BpOsdDecoder(H, error_rate=0.1, **kw)
+    o = oracle_mod.OracleDecoder(H, error_rate=0.1, **kw)
+    _, syn = random_syndromes(H, 0.12, 200, seed=4)
+    newp = np.random.default_rng(2).uniform(0.02, 0.3, size=n)
+    newp.setflags(write=False)  # the harness hands over read-only arrays (css_decode_sim.py:432-434)
+    d.update_channel_probs(newp)
+    o.update_channel_probs(newp)
+    for b in range(40):
+        assert (d.decode(syn[b]) == o.decode(syn[b])).all()
+        assert (d.osd0_decoding == o.osd0_decoding).all() and (d.bp_decoding == o.bp_decoding).all()
+        assert d.converge == o.converge and d.iter == o.iter
+        assert (d.log_prob_ratios == o.log_prob_ratios).all()
+
+
+def test_per_shot_priors(torch_cuda, oracle_mod, cfg_codes):
+    """decode_batch(priors=[B,n]) == update_channel_probs before every shot (the x->z channel update)."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(1).hz
+    n = H.shape[1]
+    kw = dict(max_iter=4, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)
+    rng = np.random.default_rng(3)
+    B = 64
+    probs = rng.uniform(0.02, 0.3, size=(B, n))
+    _, syn = random_syndromes(H, 0.1, B, seed=6)
+    d = BpOsdDecoder(H, error_rate=0.1, **kw)
+    pri = torch.tensor(np.log((1 - probs) / probs), device="cuda", dtype=torch.float64)
+    r = d.decode_batch(torch.tensor(syn, device="cuda"), priors=pri)
+    o = oracle_mod.OracleDecoder(H, error_rate=0.1, **kw)
+    for b in range(B):
+        o.update_channel_probs(probs[b])
+        o.decode(syn[b])
+        assert (r.bp_decoding[b].cpu().numpy() == o.bp_decoding).all()
+        assert (r.log_prob_ratios[b].cpu().numpy() == o.log_prob_ratios).all()
+        assert bool(r.converge[b]) == o.converge and int(r.iter[b]) == o.iter
+
+
+def test_edge_cases(torch_cuda, oracle_mod, cfg_codes):
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(1).hz
+    m, n = H.shape
+    d = BpOsdDecoder(H, error_rate=0.05, **MS_CS7)
+    # empty batch
+    r = d.decode_batch(torch.zeros((0, m), dtype=torch.uint8, device="cuda"))
+    assert r.osdw_decoding.shape == (0, n)
+    # zero syndrome: BP converges in one pass to the zero vector
+    r = d.decode_batch(torch.zeros((3, m), dtype=torch.uint8, device="cuda"))
+    assert not r.osdw_decoding.any() and r.converge.all() and (r.iter == 1).all()
+    # single shot through decode(), int and bool syndromes, wrong length
+    _, syn = random_syndromes(H, 0.1, 5, seed=1)
+    a = d.decode(syn[0].astype(int))
+    b = d.decode(syn[0].astype(bool))
+    assert (a == b).all()
+    with pytest.raises(ValueError):
+        d.decode(np.zeros(m + 1, dtype=int))
+    with pytest.raises(ValueError):
+        d.decode_batch(torch.zeros((2, m + 1), dtype=torch.uint8, device="cuda"))
+    # numpy input goes through the host-buffer entry point and returns numpy
+    rn = d.decode_batch(syn)
+    rg = d.decode_batch(torch.tensor(syn, device="cuda"))
+    assert isinstance(rn.osdw_decoding, np.ndarray)
+    assert (rn.osdw_decoding == rg.osdw_decoding.cpu().numpy()).all()
+    assert (rn.log_prob_ratios == rg.log_prob_ratios.cpu().numpy()).all()
+    # osd_order larger than n - rank is rejected (k = 21 for this code)
+    with pytest.raises(ValueError):
+        BpOsdDecoder(H, error_rate=0.05, osd_method="osd_cs", osd_order=22)
+    # repetition code: rows of weight 2, columns of weight 1-2, rank-deficient-free; ring code is rank deficient
+    for Hs in (codes.rep_code(9), codes.ring_code(8), codes.hamming_code(4)):
+        kw = dict(max_iter=3, bp_method="ms", ms_scaling_factor=0.5, osd_method="osd_e", osd_order=1)
+        _, s2 = random_syndromes(Hs, 0.2, 200, seed=5)
+        ref = oracle_mod.OracleDecoder(Hs, error_rate=0.2, **kw).decode_batch(s2)
+        for kernel in (0, 1, 2):
+            dd, out = gpu_decode(torch, Hs, s2, kernel=kernel, error_rate=0.2, **kw)
+            assert_exact(out, ref)
+
+
+def test_small_workspace_chunks(torch_cuda, oracle_mod, cfg_codes):
+    """When LLRs are not requested the failed-shot LLR workspace bounds the chunk size; results must not change."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(2).hz
+    _, syn = random_syndromes(H, 0.07, 3000, seed=10)
+    ref = oracle_mod.OracleDecoder(H, error_rate=0.07, **MS_CS7).decode_batch(syn, want_llr=False)
+    d = BpOsdDecoder(H, error_rate=0.07, **MS_CS7)
+    d.set_tuning(workspace_bytes=1 << 20)  # forces fail_cap = 1024 shots per chunk
+    r = d.decode_batch(torch.tensor(syn, device="cuda"), return_llr=False)
+    assert d.stats()["chunks"] == 3
+    assert (r.osdw_decoding.cpu().numpy() == ref["osdw"]).all()
+    assert (r.osd0_decoding.cpu().numpy() == ref["osd0"]).all()
+    assert (r.converge.cpu().numpy() == ref["converge"].astype(bool)).all()
+
+
+def test_sampler_syndrome_and_logical_kernels(torch_cuda, oracle_mod, cfg_codes):
+    from bp_osd_b200 import BpOsdDecoder
+    code = cfg_codes(2)
+    n = code.N
+    d = BpOsdDecoder(code.hz, error_rate=0.05, **MS_CS7)
+    rng = np.random.default_rng(0)
+    pz, px, py = rng.uniform(0, 0.05, n), rng.uniform(0, 0.05, n), rng.uniform(0, 0.03, n)
+    d.set_error_channel(pz=pz, px=px, py=py)
+    d.set_logicals(code.lz)
+    ex_ref, ez_ref = oracle_mod.sample_errors(77, 5000, 500, pz, px, py)
+    ex, sx = d.sample_syndromes(77, 5000, 500, sector=0)
+    ez, _ = d.sample_syndromes(77, 5000, 500, sector=1)
+    assert (ex.cpu().numpy() == ex_ref).all() and (ez.cpu().numpy() == ez_ref).all()
+    assert (sx.cpu().numpy() == np.asarray((code.hz @ ex_ref.T) % 2).T).all()
+    dec = d.decode_batch(sx).osdw_decoding
+    fail = d.logical_check(ex, dec).cpu().numpy()
+    want = oracle_mod.logical_fail(code.lz, ex_ref, dec.cpu().numpy()).astype(bool)
+    assert (fail == want).all()
+
+
+def test_sample_and_decode_counters(torch_cuda, oracle_mod, cfg_codes):
+    """The device Monte-Carlo step against the same step done with the oracle (css_decode_sim.py:163-205,250-349)."""
+    from bp_osd_b200 import BpOsdDecoder
+    code = cfg_codes(1)
+    n, p, B = code.N, 0.09, 2000
+    d = BpOsdDecoder(code.hz, error_rate=p, **MS_CS7)
+    d.set_error_channel(px=p)
+    d.set_logicals(code.lz)
+    c = d.sample_and_decode(seed=99, shot0=0, B=B // 2)
+    c = d.sample_and_decode(seed=99, shot0=B // 2, B=B // 2, counters=c)
+    z = np.zeros(n)
+    ex, _ = oracle_mod.sample_errors(99, 0, B, z, np.full(n, p), z)
+    o = oracle_mod.OracleDecoder(code.hz, error_rate=p, **MS_CS7)
+    out = o.decode_batch(o.syndrome(ex), want_llr=False)
+    fw = oracle_mod.logical_fail(code.lz, ex, out["osdw"]).astype(bool)
+    f0 = oracle_mod.logical_fail(code.lz, ex, out["osd0"]).astype(bool)
+    fb = oracle_mod.logical_fail(code.lz, ex, out["bp"]).astype(bool)
+    cv = out["converge"].astype(bool)
+    assert c[0] == B and c[1] == cv.sum() and c[2] == (cv & ~fb).sum()
+    assert c[3] == (~f0).sum() and c[4] == (~fw).sum()
+    assert c[5] == (~cv).sum() and c[6] == out["iter"].sum()
+    wts = np.concatenate([(ex ^ out["osdw"])[fw].sum(1), (ex ^ out["osd0"])[f0].sum(1)])
+    assert c[7] == (wts.min() if wts.size else 0)
+
+
+def test_full_size_round_trip_property(torch_cuda, cfg_codes):
+    """At BASELINE size the oracle is too slow; check size-independent properties instead:
+    H * osdw == syndrome for every shot, converged shots have osd0 == osdw == bp, weights ordered."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    code = cfg_codes(3)
+    d = BpOsdDecoder(code.hz, error_rate=0.05, **MS_CS7)
+    d.set_error_channel(px=0.05)
+    d.set_logicals(code.lz)
+    B = 100_000
+    err, syn = d.sample_syndromes(1, 0, B, sector=0)
+    r = d.decode_batch(syn, return_llr=False)
+    Hd = torch.tensor(code.hz.toarray(), dtype=torch.float16, device="cuda")
+    for name in ("osdw_decoding", "osd0_decoding"):
+        x = getattr(r, name)
+        for s in range(0, B, 20000):
+            chk = (x[s:s + 20000].to(torch.float16) @ Hd.T) % 2
+            assert (chk.to(torch.uint8) == syn[s:s + 20000]).all(), name
+    c = r.converge
+    assert (r.osd0_decoding[c] == r.bp_decoding[c]).all() and (r.osdw_decoding[c] == r.bp_decoding[c]).all()
+    assert (r.osdw_decoding.sum(1) <= r.osd0_decoding.sum(1)).all()
+    st = d.stats()
+    assert st["bp_converged"] == int(c.sum()) and st["osd_invocations"] == B - st["bp_converged"]
+    fail = d.logical_check(err, r.osdw_decoding)
+    assert fail.float().mean().item() < 0.01
+
+
+def test_fp32_fast_mode_is_statistically_equivalent(torch_cuda, oracle_mod, cfg_codes):
+    """fp32 mode: decoding-mismatch rate is reported, the logical error rate must sit inside the 95% CI
+    of the fp64 oracle's on the same shots."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    code = cfg_codes(2)
+    p, B = 0.06, 6000
+    n = code.N
+    z = np.zeros(n)
+    ex, _ = oracle_mod.sample_errors(4242, 0, B, z, np.full(n, p), z)
+    o = oracle_mod.OracleDecoder(code.hz, error_rate=p, **MS_CS7)
+    syn = o.syndrome(ex)
+    ref = o.decode_batch(syn, want_llr=False)
+    ler_ref = oracle_mod.logical_fail(code.lz, ex, ref["osdw"]).mean()
+    d = BpOsdDecoder(code.hz, error_rate=p, precision=32, **MS_CS7)
+    r = d.decode_batch(torch.tensor(syn, device="cuda"), return_llr=False)
+    out = r.osdw_decoding.cpu().numpy()
+    assert ((out @ code.hz.toarray().T % 2) == syn).all()
+    ler = oracle_mod.logical_fail(code.lz, ex, out).mean()
+    ci = 1.96 * np.sqrt(max(ler_ref * (1 - ler_ref), 1e-6) / B)
+    mismatch = (out != ref["osdw"]).any(1).mean()
+    print(f"fp32: LER {ler:.4f} vs fp64 {ler_ref:.4f} +- {ci:.4f}; decoding mismatch rate {mismatch:.3f}")
+    assert abs(ler - ler_ref) <= ci + 2.0 / B

@@ -1,0 +1,100 @@
+"""Host GF(2) toolkit and code builders against the reference's doc/test known answers."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from bp_osd_b200 import codes, mod2
+from bp_osd_b200.css import css_code
+from bp_osd_b200.hgp import hgp, compute_exact_code_distance
+
+
+def test_hamming_matrix_matches_readme():
+    # /root/reference/README.md:66-68
+    want = np.array([[0, 0, 0, 1, 1, 1, 1], [0, 1, 1, 0, 0, 1, 1], [1, 0, 1, 0, 1, 0, 1]])
+    assert (codes.hamming_code(3).toarray() == want).all()
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_steane_code(dense):
+    # /root/reference/tests/test_css.py:8-27 and README.md:85-88
+    h = codes.hamming_code(3)
+    if dense:
+        h = h.toarray()
+    q = css_code(hx=h, hz=h, code_distance=3, name="Steane code")
+    assert (q.N, q.K, q.D) == (7, 1, 3)
+    assert q.test(show_tests=False)
+    assert (q.lx.toarray() == [[1, 1, 1, 0, 0, 0, 0]]).all()
+    assert (q.lz.toarray() == [[1, 1, 1, 0, 0, 0, 0]]).all()
+
+
+def test_invalid_css_code():
+    # /root/reference/README.md:120-136: rep-code hx = hz gives K = -5 and test() False
+    q = css_code(codes.rep_code(7), codes.rep_code(7))
+    assert q.K == -5
+    assert not q.test(show_tests=False)
+
+
+def test_hgp_surface_code():
+    # /root/reference/tests/test_hgp.py:9-18, README.md:153
+    q = hgp(codes.rep_code(3), codes.rep_code(3), compute_distance=True)
+    assert q.test(show_tests=False)
+    assert (q.N, q.K, q.D) == (13, 1, 3)
+    assert q.code_params == "(2,4)-[[13,1,3]]"
+
+
+def test_hgp_seed_code_builds():
+    # /root/reference/tests/test_hgp.py:21-39 (the 12x16 seed is mkmn_16_4_6)
+    q = hgp(codes.mkmn_16_4_6(), codes.mkmn_16_4_6(), compute_distance=True)
+    assert (q.N, q.K, q.D) == (400, 16, 6)
+    assert q.test(show_tests=False)
+
+
+def test_mismatched_columns_raise():
+    with pytest.raises(Exception):
+        css_code(np.ones((2, 3)), np.ones((2, 4)))
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_rank_nullspace_pivots_random(seed):
+    rng = np.random.default_rng(seed)
+    m, n = rng.integers(3, 40, size=2)
+    a = (rng.random((m, n)) < 0.3).astype(np.uint8)
+    r = mod2.rank(a)
+    assert r == mod2.rank(a.T)
+    ker = mod2.nullspace(a).toarray()
+    assert ker.shape == (n - r, n)
+    assert not ((a.astype(int) @ ker.T.astype(int)) % 2).any()
+    assert mod2.rank(ker) == n - r
+    pr = mod2.pivot_rows(a)
+    assert len(pr) == r and mod2.rank(a[pr]) == r
+    assert (np.diff(pr) > 0).all()
+    red, rk, tr, pc = mod2.reduced_row_echelon(a)
+    assert rk == r
+    assert ((tr.astype(int) @ a.astype(int)) % 2 == red).all()
+    assert (red[np.arange(r), pc] == 1).all() and (red[:, pc].sum(0) == 1).all()
+
+
+def test_row_span_and_distance():
+    h = codes.hamming_code(3)
+    span = mod2.row_span(h).toarray()
+    assert span.shape == (8, 7) and len({tuple(r) for r in span}) == 8
+    assert compute_exact_code_distance(h) == 3
+    assert compute_exact_code_distance(codes.rep_code(5)) == 5
+
+
+@pytest.mark.parametrize("cfg,N,K,m,E,rank", [(1, 41, 1, 20, 72, 20), (2, 400, 16, 192, 1344, 192),
+                                              (3, 1922, 50, 961, 5766, 936), (4, 882, 24, 441, 2646, 429)])
+def test_config_codes(cfg_codes, cfg, N, K, m, E, rank):
+    # sizes of SURVEY.md section 8 table
+    q = cfg_codes(cfg)
+    assert (q.N, q.K) == (N, K)
+    assert q.hz.shape == (m, N) and q.hz.nnz == E
+    assert mod2.rank(q.hz) == rank
+    assert q.lz.shape == (K, N) and q.lx.shape == (K, N)
+    assert q.test(show_tests=False)
+
+
+def test_config5_shape():
+    q = codes.config_code(5)
+    assert q.hz.shape == (19200, 40000) and q.hz.nnz == 134400
+    assert not ((q.hx @ q.hz.T).data % 2).any()

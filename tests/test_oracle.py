@@ -1,0 +1,154 @@
+"""Pins the CPU oracle: the reference's documented known answer (G1), known-answer vectors of the
+building blocks, a second independent restatement, brute force on small codes, and invariants."""
+import itertools
+
+import numpy as np
+import pytest
+
+from bp_osd_b200 import codes
+from bp_osd_b200.hgp import hgp
+from tests._util import golden_names, load_golden, random_syndromes
+
+
+def test_g1_readme_known_answer(oracle_mod):
+    # /root/reference/README.md:145-216: d=3 surface code, error on qubits {5,12}
+    sc = hgp(codes.rep_code(3))
+    d = oracle_mod.OracleDecoder(sc.hz, error_rate=0.05, channel_probs=[None], max_iter=sc.N, bp_method="ms",
+                                 ms_scaling_factor=0, osd_method="osd_cs", osd_order=7)
+    err = np.zeros(sc.N, dtype=int)
+    err[[5, 12]] = 1
+    syn = sc.hz @ err % 2
+    assert (syn == [0, 0, 0, 0, 0, 1]).all()
+    out = d.decode(syn)
+    assert (out == [0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0]).all()
+    residual = (out + err) % 2
+    assert not (sc.lz @ residual % 2).any()  # "Logical Error: No"
+    assert d.converge and d.iter == 2
+    want = [6.2569, 7.3611, 6.2569, 6.2569, 6.2569, 4.0486, 4.0486, 2.9444, -0.3681, 7.3611, 6.2569, 6.2569, 2.9444]
+    assert np.allclose(d.log_prob_ratios, want, atol=5e-5)
+
+
+def test_philox_known_answers(oracle_mod):
+    # Random123 kat_vectors for philox4x32-10
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        assert list(oracle_mod.philox4x32_10(ctr, key)) == want
+
+
+def test_sampler_statistics_and_split(oracle_mod):
+    n, B = 64, 4000
+    pz, px, py = np.full(n, 0.02), np.full(n, 0.03), np.full(n, 0.01)
+    ex, ez = oracle_mod.sample_errors(5, 0, B, pz, px, py)
+    # Z-only 0.02, X-only 0.03, Y (both) 0.01
+    assert abs(((ez == 1) & (ex == 0)).mean() - 0.02) < 0.002
+    assert abs(((ex == 1) & (ez == 0)).mean() - 0.03) < 0.003
+    assert abs(((ex == 1) & (ez == 1)).mean() - 0.01) < 0.002
+    # subsequence = global shot index: a shifted window reproduces the overlap
+    ex2, _ = oracle_mod.sample_errors(5, 1000, 100, pz, px, py)
+    assert (ex2 == ex[1000:1100]).all()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_golden(oracle_mod, cfg_codes, name):
+    g = load_golden(name)
+    H = cfg_codes(g["cfg"]).hz
+    out = oracle_mod.OracleDecoder(H, error_rate=g["p"], **g["kw"]).decode_batch(g["syndromes"])
+    for k in ("osdw", "osd0", "bp", "converge", "iter"):
+        assert (out[k] == g[k]).all(), k
+    assert (out["llr"] == g["llr"]).all()
+
+
+CASES = [
+    dict(cfg=1, p=0.08, kw=dict(max_iter=0, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=7), shots=60),
+    dict(cfg=1, p=0.12, kw=dict(max_iter=4, bp_method="ms", ms_scaling_factor=0.75, osd_method="osd_e", osd_order=7), shots=60),
+    dict(cfg=1, p=0.10, kw=dict(max_iter=9, bp_method="ps", ms_scaling_factor=0, osd_method="osd_cs", osd_order=5), shots=60),
+    dict(cfg=2, p=0.06, kw=dict(max_iter=15, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=4), shots=8),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"cfg{c['cfg']}-{c['kw']['bp_method']}-{c['kw']['osd_method']}")
+def test_oracle_vs_second_restatement(oracle_mod, cfg_codes, case):
+    from oracle.slow_ref import SlowDecoder
+    H = cfg_codes(case["cfg"]).hz
+    n = H.shape[1]
+    kw = case["kw"]
+    o = oracle_mod.OracleDecoder(H, error_rate=case["p"], **kw)
+    s = SlowDecoder(H, [case["p"]] * n, kw["max_iter"], kw["bp_method"], kw["ms_scaling_factor"], kw["osd_method"], kw["osd_order"])
+    _, syn = random_syndromes(H, case["p"], case["shots"], seed=3)
+    for b in range(case["shots"]):
+        a = o.decode(syn[b])
+        x = s.decode(syn[b])
+        assert (a == np.array(x)).all()
+        assert (o.osd0_decoding == np.array(s.osd0_decoding)).all()
+        assert (o.bp_decoding == np.array(s.bp_decoding)).all()
+        assert o.converge == s.converge and o.iter == s.iter
+        if kw["bp_method"] == "ms":
+            assert (o.log_prob_ratios == np.array(s.llr)).all()
+        else:
+            assert np.allclose(o.log_prob_ratios, np.array(s.llr), rtol=1e-12, atol=0)
+
+
+def test_nonuniform_probs_second_restatement(oracle_mod, cfg_codes):
+    from oracle.slow_ref import SlowDecoder
+    H = cfg_codes(1).hz
+    n = H.shape[1]
+    rng = np.random.default_rng(11)
+    probs = rng.uniform(0.02, 0.2, size=n)
+    kw = dict(max_iter=3, bp_method="ms", ms_scaling_factor=0.8, osd_method="osd_cs", osd_order=6)
+    o = oracle_mod.OracleDecoder(H, channel_probs=probs, **kw)
+    s = SlowDecoder(H, probs, 3, "ms", 0.8, "osd_cs", 6)
+    _, syn = random_syndromes(H, 0.12, 80, seed=5)
+    for b in range(80):
+        assert (o.decode(syn[b]) == np.array(s.decode(syn[b]))).all()
+
+
+def test_osd_e_full_order_is_exhaustive_minimum(oracle_mod, cfg_codes):
+    """OSD-E with osd_order = k enumerates every solution of H x = s: osdw must have minimum weight."""
+    H = hgp(codes.rep_code(3)).hz  # 6 x 13, k = 7
+    Hd = H.toarray()
+    n = Hd.shape[1]
+    o = oracle_mod.OracleDecoder(H, error_rate=0.1, max_iter=1, bp_method="ms", ms_scaling_factor=0.5,
+                                 osd_method="osd_e", osd_order=7)
+    assert o.k == 7
+    allx = np.array(list(itertools.product([0, 1], repeat=n)), dtype=np.uint8)
+    allsyn = allx @ Hd.T % 2
+    _, syn = random_syndromes(H, 0.2, 40, seed=9)
+    for b in range(40):
+        x = o.decode(syn[b])
+        assert (Hd @ x % 2 == syn[b]).all()
+        if not o.converge:
+            sols = allx[(allsyn == syn[b]).all(1)]
+            assert x.sum() == sols.sum(1).min()
+
+
+@pytest.mark.parametrize("cfg,p", [(1, 0.1), (2, 0.07)])
+def test_invariants(oracle_mod, cfg_codes, cfg, p):
+    H = cfg_codes(cfg).hz
+    o = oracle_mod.OracleDecoder(H, error_rate=p, max_iter=10, bp_method="ms", ms_scaling_factor=0,
+                                 osd_method="osd_cs", osd_order=5)
+    _, syn = random_syndromes(H, p, 50, seed=2)
+    out = o.decode_batch(syn)
+    Hd = H.toarray()
+    assert ((out["osdw"] @ Hd.T % 2) == syn).all()
+    assert ((out["osd0"] @ Hd.T % 2) == syn).all()
+    assert (out["osdw"].sum(1) <= out["osd0"].sum(1)).all()
+    c = out["converge"].astype(bool)
+    assert (out["osd0"][c] == out["bp"][c]).all() and (out["osdw"][c] == out["bp"][c]).all()
+    assert (out["iter"][~c] == 10).all()
+
+
+def test_zero_probability_entries_do_not_nan(oracle_mod, cfg_codes):
+    # the reference's example builds an X decoder with all-zero probabilities
+    # (examples/qldpc_decode_example.py:11 with css_decode_sim.py:457)
+    H = cfg_codes(1).hz
+    probs = np.full(H.shape[1], 0.05)
+    probs[::3] = 0.0
+    with np.errstate(divide="ignore"):
+        o = oracle_mod.OracleDecoder(H, channel_probs=probs, max_iter=0, bp_method="ms", ms_scaling_factor=0,
+                                     osd_method="osd_cs", osd_order=3)
+        _, syn = random_syndromes(H, 0.05, 30, seed=4)
+        out = o.decode_batch(syn)
+    assert not np.isnan(out["llr"]).any()
