@@ -120,8 +120,10 @@ def test_product_sum_lifted_product(torch_cuda, oracle_mod, cfg_codes):
         assert (out["osdw"] == ref["osdw"]).all(1).mean() > 0.95
         quick = same & (ref["iter"] <= 20)
         assert quick.sum() > 50
-        rel = np.abs(out["llr"][quick] - ref["llr"][quick]) / np.abs(ref["llr"][quick])
-        assert rel.max() < 1e-9
+        a, b = out["llr"][quick], ref["llr"][quick]
+        fin = np.isfinite(b)  # product-sum is unclipped upstream: tanh saturates to +-1 and the LLR to +-inf
+        assert (a[~fin] == b[~fin]).all()
+        assert (np.abs(a[fin] - b[fin]) / np.abs(b[fin])).max() < 1e-9
         Hd = H.toarray()
         assert ((out["osdw"] @ Hd.T % 2) == syn).all()
 
