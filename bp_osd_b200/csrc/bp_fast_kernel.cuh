@@ -1,28 +1,41 @@
 // bp_fast_kernel.cuh -- in-place shared-memory min-sum BP for sm_100a (rows a3-a8, bit-exact in fp64).
 //
-// One message array, check-major with a fixed row stride DC (slot = check*DC + k, k-th edge of
-// the check in ascending column order).  A pass is two sweeps over it:
-//   check sweep: the thread that owns a check pulls its whole row with 16-byte LDS, reduces
-//                min1/min2/argmin/sign parity in registers, and overwrites the row with the
-//                check->bit messages (16-byte STS);
-//   bit sweep:   the thread that owns a bit gathers its <= DV messages, forms the prefix/suffix
-//                sums in the reference's order (prior + c_1 + ... left to right; suffix from the
-//                last edge backwards), overwrites them with the new bit->check messages and drops
-//                its hard decision next to each edge (one byte per edge, row stride DS) so the next
-//                check sweep can test H*decoding == syndrome while it reads the row anyway.
-// Per-bit state that must survive to the end of the shot (the LLR of the last executed pass and
-// the edge slots) lives in registers; nothing but the syndrome and the results touches HBM.
-// Shots are pulled from an atomic queue by persistent CTAs, one shot per CTA at a time.
+// One message array in shared memory, check-major with a fixed row stride DC: slot = prow*DC + kappa,
+// where prow is the *physical* row the host layout pass assigned to a check and kappa its edge's
+// physical position in that row (min is order independent, so both are free; the host pass picks
+// them to make the bit-side gathers/scatters bank-conflict free, see fast_build).  A pass is two
+// sweeps over the array:
+//   check sweep: the thread that owns a physical row pulls it with 16-byte LDS, forms for every
+//                edge the minimum over the *other* edges with prefix/suffix running minima (the
+//                reference's own formulation: 3d-4 compare-selects, no argmin bookkeeping), applies
+//                sign and scaling with integer sign-bit arithmetic (exact slow path when a message
+//                is +-0, where "<= 0" and the sign bit disagree), and overwrites the row in place;
+//   bit sweep:   the thread that owns a bit gathers its <= DV messages, forms prefix/suffix sums in
+//                the reference's order (prior + c_1 + ... left to right; suffix from the last edge
+//                backwards) and overwrites them with the new bit->check messages.
+// Convergence (H*decoding == syndrome) is tracked incrementally: every check keeps one parity-mismatch
+// bit, initialised to its syndrome bit; a bit whose hard decision flips toggles the mismatch bits of
+// its checks with a shared-memory atomicXor (rare), and the next check sweep only votes on that bit.
+// Per-bit state that must survive to the end of the shot (LLR of the last executed pass, edge
+// offsets, last hard decisions) lives in registers; nothing but the syndrome and the results
+// touches HBM.  Persistent CTAs pull shots from an atomic queue (iteration counts are heavy tailed).
 #pragma once
 #include "bposd_kernels.cuh"
+#include <algorithm>
+#include <cmath>
+#include <random>
 #include <vector>
 
 namespace bposd {
 
 struct FastTables {
     int DC = 0, DV = 0;            // degree class (upper bounds, compile-time in the kernel)
+    int regular = 0;               // every row has exactly DC entries and every column exactly DV
+    int elem_bytes = 8;
     uint16_t *d_vslot = nullptr;   // [n, DV] message slot of the k-th edge of bit j (ascending row), 0xFFFF = none
-    uint8_t *d_cdeg = nullptr;     // [m] row degrees
+    uint8_t *d_cdeg = nullptr;     // [m] degree of the check stored in physical row p
+    uint16_t *d_row_of = nullptr;  // [m] original check index of physical row p
+    long long conflicts_before = 0, conflicts_after = 0, wavefronts_ideal = 0;
 };
 
 static inline bool fast_supported(int max_col_deg, int max_row_deg, int method) {
@@ -36,35 +49,164 @@ static inline void fast_class(int max_col_deg, int max_row_deg, int *DC, int *DV
     else { *DC = 16; *DV = 8; }
 }
 
-static inline int fast_dstride(int DC) { return (DC + 7) / 8 * 8; }
-
 static inline void fast_free(FastTables &t) {
-    cudaFree(t.d_vslot); cudaFree(t.d_cdeg);
-    t.d_vslot = nullptr; t.d_cdeg = nullptr;
+    cudaFree(t.d_vslot); cudaFree(t.d_cdeg); cudaFree(t.d_row_of);
+    t.d_vslot = nullptr; t.d_cdeg = nullptr; t.d_row_of = nullptr;
 }
+
+static inline int fast_vpt(int n) { return n <= 2048 ? 4 : 8; }
+static inline int fast_maxt(int n) { return n <= 4096 ? 512 : 1024; }
+
+static inline int fast_default_threads(int n, int m) {
+    (void)m;
+    const int vpt = fast_vpt(n);
+    int t = ((n + vpt - 1) / vpt + 31) / 32 * 32;
+    return std::min(fast_maxt(n), std::max(32, t));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host layout pass ("the Tanner graph compiled once per parity-check matrix").
+// The bit sweep's k-th access of a warp touches slot[j][k] for its 32 bits j; shared memory serves
+// one 128-byte wavefront per cycle, so 8-byte accesses go out as two half-warps of 16 lanes over
+// 16 eight-byte banks and 4-byte accesses as 32 lanes over 32 banks.  Local search over the row
+// permutation and the in-row edge positions minimises the total number of wavefronts.
+// ---------------------------------------------------------------------------------------------
+struct LayoutOpt {
+    int m, n, DC, DV, nbanks;
+    std::vector<int> prow;             // check -> physical row
+    std::vector<int> kappa;            // CSR edge -> position inside its physical row
+    std::vector<int> edge_group;       // CSR edge -> access group id
+    std::vector<int> edge_row;         // CSR edge -> check
+    std::vector<int> hist;             // [group][bank] number of lanes of the group that hit the bank
+    int bank_of(int e) const { return (prow[edge_row[e]] * DC + kappa[e]) % nbanks; }
+    // pair cost: sum over groups and banks of C(count, 2); moving one edge changes it by count differences
+    long long remove(int e) { int &c = hist[(size_t)edge_group[e] * nbanks + bank_of(e)]; c--; return -(long long)c; }
+    long long add(int e) { int &c = hist[(size_t)edge_group[e] * nbanks + bank_of(e)]; long long d = c; c++; return d; }
+    long long wavefronts() const { // what the hardware pays: max bank multiplicity per group
+        long long w = 0;
+        for (size_t g = 0; g * nbanks < hist.size(); g++) {
+            int mx = 0;
+            for (int b = 0; b < nbanks; b++) mx = std::max(mx, hist[g * nbanks + b]);
+            w += mx;
+        }
+        return w;
+    }
+};
 
 static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vector<int> &row_ptr,
                                      const std::vector<int> &col_idx, const std::vector<int> &col_ptr,
-                                     const std::vector<int> &row_idx, const std::vector<int> &csc_slot) {
-    int mr = 0, mc = 0;
-    for (int i = 0; i < m; i++) mr = std::max(mr, row_ptr[i + 1] - row_ptr[i]);
-    for (int j = 0; j < n; j++) mc = std::max(mc, col_ptr[j + 1] - col_ptr[j]);
+                                     const std::vector<int> &row_idx, const std::vector<int> &csc_slot,
+                                     int elem_bytes) {
+    int mr = 0, mc = 0, minr = 1 << 30, minc = 1 << 30;
+    for (int i = 0; i < m; i++) { int d = row_ptr[i + 1] - row_ptr[i]; mr = std::max(mr, d); minr = std::min(minr, d); }
+    for (int j = 0; j < n; j++) { int d = col_ptr[j + 1] - col_ptr[j]; mc = std::max(mc, d); minc = std::min(minc, d); }
     fast_class(mc, mr, &t.DC, &t.DV);
-    if ((long long)m * t.DC >= 0xFFFF) { t.DC = 0; return cudaSuccess; } // slots must fit in 16 bits
-    std::vector<uint16_t> vs((size_t)n * t.DV, 0xFFFF);
-    std::vector<uint8_t> cd(std::max(m, 1), 0);
-    for (int i = 0; i < m; i++) cd[i] = (uint8_t)(row_ptr[i + 1] - row_ptr[i]);
+    t.elem_bytes = elem_bytes;
+    t.regular = (m > 0 && minr == t.DC && mr == t.DC && minc == t.DV && mc == t.DV) ? 1 : 0;
+    if ((long long)m * t.DC >= 0xFFFF || m == 0) { t.DC = 0; return cudaSuccess; } // slots must fit in 16 bits
+    const int E = row_ptr[m];
+    LayoutOpt L;
+    L.m = m; L.n = n; L.DC = t.DC; L.DV = t.DV;
+    const int group = elem_bytes == 8 ? 16 : 32; // lanes served together by one wavefront
+    L.nbanks = elem_bytes == 8 ? 16 : 32;        // banks in units of the element size
+    L.prow.resize(m); L.kappa.resize(E); L.edge_row.resize(E); L.edge_group.assign(E, 0);
+    for (int i = 0; i < m; i++) {
+        L.prow[i] = i;
+        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) { L.kappa[e] = e - row_ptr[i]; L.edge_row[e] = i; }
+    }
+    // access groups: bits are dealt to threads as j = tid + r*T with T a multiple of 32, so the lanes
+    // served together are `group` consecutive j; group id = (j / group, k)
+    const int ngroups = ((n + group - 1) / group) * t.DV;
+    for (int j = 0; j < n; j++)
+        for (int q = col_ptr[j]; q < col_ptr[j + 1]; q++) L.edge_group[csc_slot[q]] = (j / group) * t.DV + (q - col_ptr[j]);
+    L.hist.assign((size_t)ngroups * L.nbanks, 0);
+    long long pairs = 0, ideal = 0;
+    for (int e = 0; e < E; e++) pairs += L.add(e);
+    {
+        std::vector<char> used(ngroups, 0);
+        for (int e = 0; e < E; e++) used[L.edge_group[e]] = 1;
+        for (char u : used) ideal += u;
+    }
+    t.wavefronts_ideal = ideal;
+    t.conflicts_before = L.wavefronts() - ideal;
+    // local search on the pair cost: swap two physical rows, or two positions inside one row
+    std::mt19937 rng(12345u);
+    const long long budget = std::min<long long>(3000000, 600ll * E);
+    long long cur = pairs;
+    // simulated annealing: uphill moves of size d are accepted with probability exp(-d/temp)
+    auto accept = [&](long long d, long long iter) {
+        if (d <= 0) return true;
+        // a short, cool annealing tail helps tiny graphs; large ones do best with plain descent
+        if (E > 2000 || iter > budget / 2) return false;
+        const double temp = 0.3 * (1.0 - 2.0 * (double)iter / (double)budget) + 1e-3;
+        return (rng() & 0xFFFFFF) < (unsigned)(16777216.0 * std::exp(-(double)d / temp));
+    };
+    for (long long iter = 0; iter < budget && cur > 0; iter++) {
+        if (rng() & 1) {
+            const int i1 = rng() % m, i2 = rng() % m;
+            if (i1 == i2) continue;
+            long long d = 0;
+            for (int e = row_ptr[i1]; e < row_ptr[i1 + 1]; e++) d += L.remove(e);
+            for (int e = row_ptr[i2]; e < row_ptr[i2 + 1]; e++) d += L.remove(e);
+            std::swap(L.prow[i1], L.prow[i2]);
+            for (int e = row_ptr[i1]; e < row_ptr[i1 + 1]; e++) d += L.add(e);
+            for (int e = row_ptr[i2]; e < row_ptr[i2 + 1]; e++) d += L.add(e);
+            if (accept(d, iter)) { cur += d; continue; }
+            for (int e = row_ptr[i1]; e < row_ptr[i1 + 1]; e++) L.remove(e);
+            for (int e = row_ptr[i2]; e < row_ptr[i2 + 1]; e++) L.remove(e);
+            std::swap(L.prow[i1], L.prow[i2]);
+            for (int e = row_ptr[i1]; e < row_ptr[i1 + 1]; e++) L.add(e);
+            for (int e = row_ptr[i2]; e < row_ptr[i2 + 1]; e++) L.add(e);
+        } else {
+            const int i = rng() % m, dg = row_ptr[i + 1] - row_ptr[i];
+            // exchange two occupied positions of this row (pad positions of short rows stay at the end:
+            // the kernel keeps +max in positions >= degree)
+            if (dg < 2) continue;
+            const int p1 = rng() % dg, p2 = rng() % dg;
+            if (p1 == p2) continue;
+            int e1 = -1, e2 = -1;
+            for (int e = row_ptr[i]; e < row_ptr[i] + dg; e++) { if (L.kappa[e] == p1) e1 = e; if (L.kappa[e] == p2) e2 = e; }
+            if (e1 < 0 && e2 < 0) continue;
+            long long d = 0;
+            if (e1 >= 0) d += L.remove(e1);
+            if (e2 >= 0) d += L.remove(e2);
+            if (e1 >= 0) L.kappa[e1] = p2;
+            if (e2 >= 0) L.kappa[e2] = p1;
+            if (e1 >= 0) d += L.add(e1);
+            if (e2 >= 0) d += L.add(e2);
+            if (accept(d, iter)) { cur += d; continue; }
+            if (e1 >= 0) L.remove(e1);
+            if (e2 >= 0) L.remove(e2);
+            if (e1 >= 0) L.kappa[e1] = p1;
+            if (e2 >= 0) L.kappa[e2] = p2;
+            if (e1 >= 0) L.add(e1);
+            if (e2 >= 0) L.add(e2);
+        }
+    }
+    t.conflicts_after = L.wavefronts() - ideal;
+    std::vector<int> row_at(m);
+    for (int i = 0; i < m; i++) row_at[L.prow[i]] = i;
+
+
+    std::vector<uint16_t> vs((size_t)n * t.DV, 0xFFFF), rowof(m);
+    std::vector<uint8_t> cd(m, 0);
+    for (int p = 0; p < m; p++) { rowof[p] = (uint16_t)row_at[p]; cd[p] = (uint8_t)(row_ptr[row_at[p] + 1] - row_ptr[row_at[p]]); }
     for (int j = 0; j < n; j++)
         for (int q = col_ptr[j]; q < col_ptr[j + 1]; q++) {
-            const int i = row_idx[q], k = csc_slot[q] - row_ptr[i];
-            vs[(size_t)j * t.DV + (q - col_ptr[j])] = (uint16_t)(i * t.DC + k);
+            const int i = row_idx[q], e = csc_slot[q];
+            vs[(size_t)j * t.DV + (q - col_ptr[j])] = (uint16_t)(L.prow[i] * t.DC + L.kappa[e]);
         }
     (void)col_idx;
+    fast_free(t);
     cudaError_t e = cudaMalloc((void **)&t.d_vslot, vs.size() * sizeof(uint16_t));
     if (e != cudaSuccess) return e;
     e = cudaMalloc((void **)&t.d_cdeg, cd.size());
     if (e != cudaSuccess) return e;
+    e = cudaMalloc((void **)&t.d_row_of, rowof.size() * sizeof(uint16_t));
+    if (e != cudaSuccess) return e;
     e = cudaMemcpy(t.d_vslot, vs.data(), vs.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(t.d_row_of, rowof.data(), rowof.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
     return cudaMemcpy(t.d_cdeg, cd.data(), cd.size(), cudaMemcpyHostToDevice);
 }
@@ -74,18 +216,8 @@ static inline size_t fast_smem_bytes(const FastTables &t, int n, int m) {
     (void)n;
     if (t.DC == 0) return (size_t)1 << 40;
     size_t msgs = ((size_t)m * t.DC * sizeof(real) + 15) / 16 * 16;
-    size_t dbits = ((size_t)m * fast_dstride(t.DC) + 15) / 16 * 16;
     size_t meta = ((size_t)m + 15) / 16 * 16;
-    return msgs + dbits + meta + 16;
-}
-
-static inline int fast_vpt(int n) { return n <= 4096 ? 4 : 8; }
-
-static inline int fast_default_threads(int n, int m) {
-    (void)m;
-    const int vpt = fast_vpt(n);
-    int t = ((n + vpt - 1) / vpt + 31) / 32 * 32;
-    return std::min(1024, std::max(32, t));
+    return msgs + meta + 16;
 }
 
 // ---- vector row load/store helpers -----------------------------------------------------------
@@ -123,21 +255,30 @@ template <int DC> struct RowIO<float, DC> {
     }
 };
 
-template <typename real, int DC, int DV, int VPT>
-__global__ void __launch_bounds__(1024) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
-                                                       const uint8_t *__restrict__ cdeg_tab) {
-    constexpr int DS = (DC + 7) / 8 * 8; // hard-decision bytes per check row
+// word that carries the IEEE sign bit in bit 31, and "flip the sign where bit 31 of s is set"
+__device__ __forceinline__ uint32_t sign_word(double x) { return (uint32_t)__double2hiint(x); }
+__device__ __forceinline__ uint32_t sign_word(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ double xor_sign(double x, uint32_t s) {
+    return __hiloint2double(__double2hiint(x) ^ (int)(s & 0x80000000u), __double2loint(x));
+}
+__device__ __forceinline__ float xor_sign(float x, uint32_t s) { return __uint_as_float(__float_as_uint(x) ^ (s & 0x80000000u)); }
+template <typename real> __device__ __forceinline__ real lt_min(real a, real b) { return (a < b) ? a : b; } // `if (a < t) t = a`
+
+template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
+                                                       const uint8_t *__restrict__ cdeg_tab,
+                                                       const uint16_t *__restrict__ row_of_tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = a.g.m, n = a.g.n;
     const int tid = threadIdx.x, T = blockDim.x;
     real *msg = reinterpret_cast<real *>(smem_raw);
-    uint8_t *dbit = smem_raw + ((size_t)m * DC * sizeof(real) + 15) / 16 * 16;
-    uint8_t *meta = dbit + ((size_t)m * DS + 15) / 16 * 16;
+    uint8_t *meta = smem_raw + ((size_t)m * DC * sizeof(real) + 15) / 16 * 16; // bit0 mismatch, bits1-5 degree, bit7 syndrome
+    unsigned *meta32 = reinterpret_cast<unsigned *>(meta);
     __shared__ long long sh_shot;
     __shared__ int sh_slot;
 
-    // per-bit registers: edge slots and degree (shot independent), LLR (per shot)
-    uint16_t sl[VPT][DV];
+    // per-bit registers: byte offsets of the edges' slots (shot independent)
+    unsigned off[VPT][DV];
     int dj[VPT];
 #pragma unroll
     for (int r = 0; r < VPT; r++) {
@@ -145,17 +286,16 @@ __global__ void __launch_bounds__(1024) bp_fast_kernel(BpArgs<real> a, const uin
         dj[r] = 0;
 #pragma unroll
         for (int k = 0; k < DV; k++) {
-            sl[r][k] = (j < n) ? vslot_tab[(size_t)j * DV + k] : (uint16_t)0xFFFF;
-            dj[r] += (sl[r][k] != 0xFFFF) ? 1 : 0;
+            const unsigned s = (j < n) ? vslot_tab[(size_t)j * DV + k] : 0xFFFFu;
+            off[r][k] = s * (unsigned)sizeof(real);
+            dj[r] += (s != 0xFFFFu) ? 1 : 0;
         }
     }
-    // absent slots of short rows hold +max forever: neutral for min and sign
-    for (int i = tid; i < m; i += T) {
-        const int d = cdeg_tab[i];
-        for (int k = d; k < DC; k++) msg[i * DC + k] = real_max<real>();
-        for (int k = 0; k < DS; k++) dbit[i * DS + k] = 0;
-    }
+    if (!REG) // absent slots of short rows hold +max forever: neutral for min and sign
+        for (int p = tid; p < m; p += T)
+            for (int k = cdeg_tab[p]; k < DC; k++) msg[p * DC + k] = real_max<real>();
     unsigned long long n_conv = 0, n_iter = 0;
+    const bool shared_prior = a.prior_stride == 0;
 
     for (;;) {
         __syncthreads();
@@ -164,19 +304,23 @@ __global__ void __launch_bounds__(1024) bp_fast_kernel(BpArgs<real> a, const uin
         const long long shot = sh_shot;
         if (shot >= a.B) break;
         const real *prior = a.prior + shot * a.prior_stride;
+        (void)shared_prior;
 
-        for (int i = tid; i < m; i += T) meta[i] = (uint8_t)(cdeg_tab[i] | ((a.synd[shot * m + i] & 1) << 7));
-        real llr[VPT];
+        for (int p = tid; p < m; p += T) {
+            const unsigned s = a.synd[shot * m + row_of_tab[p]] & 1u;
+            meta[p] = (uint8_t)(s | ((unsigned)cdeg_tab[p] << 1) | (s << 7));
+        }
+        real llr[VPT], pri[VPT];
+        unsigned dprev = 0;
 #pragma unroll
         for (int r = 0; r < VPT; r++) {
             const int j = tid + r * T;
-            llr[r] = 0;
+            pri[r] = (j < n) ? prior[j] : (real)0;
+            llr[r] = pri[r];
             if (j < n) {
-                const real p = prior[j];
-                llr[r] = p;
 #pragma unroll
                 for (int k = 0; k < DV; k++)
-                    if (k < dj[r]) msg[sl[r][k]] = p;
+                    if (REG || k < dj[r]) *reinterpret_cast<real *>(smem_raw + off[r][k]) = pri[r];
             }
         }
         __syncthreads();
@@ -188,38 +332,46 @@ __global__ void __launch_bounds__(1024) bp_fast_kernel(BpArgs<real> a, const uin
             const real alpha = ms_alpha(a.alpha0, it);
             bool ok = true;
             // ---- check sweep (a4) + convergence vote for the previous pass (a7) ----
-            for (int i = tid; i < m; i += T) {
-                real v[DC];
-                RowIO<real, DC>::load(msg + (size_t)i * DC, v);
-                unsigned par = 0;
+            for (int p = tid; p < m; p += T) {
+                const unsigned mt = meta[p];
+                if (mt & 1u) ok = false;
+                if (last) continue;
+                real v[DC], av[DC], pre[DC], suf[DC];
+                RowIO<real, DC>::load(msg + (size_t)p * DC, v);
+                uint32_t X = (mt & 0x80u) << 24;
 #pragma unroll
-                for (int k = 0; k < DS; k += 8) {
-                    const uint2 d = *reinterpret_cast<const uint2 *>(dbit + (size_t)i * DS + k);
-                    par ^= d.x ^ d.y;
-                }
-                par ^= par >> 16; par ^= par >> 8;
-                const unsigned mt = meta[i];
-                const int deg = mt & 0x7f, s = mt >> 7;
-                if (it > 1 && (int)(par & 1u) != s) ok = false;
-                if (!last) {
-                    real min1 = real_max<real>(), min2 = real_max<real>();
-                    int arg = -1, tot = s;
+                for (int k = 0; k < DC; k++) { av[k] = r_abs(v[k]); X ^= sign_word(v[k]); }
+                pre[0] = av[0];
 #pragma unroll
-                    for (int k = 0; k < DC; k++) {
-                        const real av = r_abs(v[k]);
-                        tot += (v[k] <= 0) ? 1 : 0;
-                        if (av < min1) { min2 = min1; min1 = av; arg = k; }
-                        else if (av < min2) min2 = av;
-                    }
+                for (int k = 1; k < DC; k++) pre[k] = lt_min(av[k], pre[k - 1]);
+                suf[DC - 1] = av[DC - 1];
+#pragma unroll
+                for (int k = DC - 2; k >= 0; k--) suf[k] = lt_min(av[k], suf[k + 1]);
+                real out[DC];
+                out[0] = (DC > 1) ? suf[DC > 1 ? 1 : 0] : real_max<real>();
+                out[DC - 1] = (DC > 1) ? pre[DC > 1 ? DC - 2 : 0] : real_max<real>();
+#pragma unroll
+                for (int k = 1; k < DC - 1; k++) out[k] = lt_min(suf[k + 1], pre[k - 1]);
+                if (pre[DC - 1] == (real)0) {
+                    // some message is +-0: "<= 0" counts +0 as negative, the sign bit does not -> exact path
+                    int tot = (int)(mt >> 7);
+#pragma unroll
+                    for (int k = 0; k < DC; k++) tot += (v[k] <= 0) ? 1 : 0;
 #pragma unroll
                     for (int k = 0; k < DC; k++) {
                         const int sg = tot + ((v[k] <= 0) ? 1 : 0);
-                        const real mag = (k == arg) ? min2 : min1;
-                        const real out = mag * ((sg & 1) ? -alpha : alpha);
-                        v[k] = (k < deg) ? out : real_max<real>();
+                        out[k] = out[k] * ((sg & 1) ? -alpha : alpha);
                     }
-                    RowIO<real, DC>::store(msg + (size_t)i * DC, v);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < DC; k++) out[k] = xor_sign(out[k] * alpha, X ^ sign_word(v[k]));
                 }
+                if (!REG) {
+                    const int deg = (mt >> 1) & 0x1f;
+#pragma unroll
+                    for (int k = 0; k < DC; k++) out[k] = (k < deg) ? out[k] : real_max<real>();
+                }
+                RowIO<real, DC>::store(msg + (size_t)p * DC, out);
             }
             const int all_ok = __syncthreads_and(ok ? 1 : 0);
             if (it > 1 && all_ok) { conv = true; iters = it - 1; break; }
@@ -231,21 +383,30 @@ __global__ void __launch_bounds__(1024) bp_fast_kernel(BpArgs<real> a, const uin
                 if (j < n) {
                     real c[DV], pre[DV];
 #pragma unroll
-                    for (int k = 0; k < DV; k++) c[k] = (k < dj[r]) ? msg[sl[r][k]] : (real)0;
-                    real t = prior[j];
+                    for (int k = 0; k < DV; k++) c[k] = (REG || k < dj[r]) ? *reinterpret_cast<const real *>(smem_raw + off[r][k]) : (real)0;
+                    real t = pri[r];
 #pragma unroll
                     for (int k = 0; k < DV; k++)
-                        if (k < dj[r]) { pre[k] = t; t += c[k]; }
+                        if (REG || k < dj[r]) { pre[k] = t; t += c[k]; }
                     llr[r] = t;
-                    const uint8_t d = (t <= 0) ? 1 : 0;
+                    const unsigned d = (t <= 0) ? 1u : 0u;
+                    if (d != ((dprev >> r) & 1u)) {
+                        // hard decision flipped: toggle the parity-mismatch bit of every neighbouring check
+                        dprev ^= 1u << r;
+#pragma unroll
+                        for (int k = 0; k < DV; k++)
+                            if (REG || k < dj[r]) {
+                                const unsigned p = off[r][k] / (unsigned)(DC * sizeof(real));
+                                atomicXor(&meta32[p >> 2], 1u << ((p & 3u) * 8u));
+                            }
+                    }
                     real sfx = 0;
 #pragma unroll
                     for (int k = DV - 1; k >= 0; k--)
-                        if (k < dj[r]) {
-                            const unsigned s16 = sl[r][k];
-                            msg[s16] = pre[k] + sfx;
+                        if (REG || k < dj[r]) {
+                            // the last edge gets pre + 0, which is pre itself (sign of zero is immaterial downstream)
+                            *reinterpret_cast<real *>(smem_raw + off[r][k]) = (REG && k == DV - 1) ? pre[k] : pre[k] + sfx;
                             sfx += c[k];
-                            dbit[s16 + (s16 / DC) * (DS - DC)] = d;
                         }
                 }
             }
@@ -291,34 +452,39 @@ __global__ void __launch_bounds__(1024) bp_fast_kernel(BpArgs<real> a, const uin
 }
 
 // ---- dispatch over the degree classes ---------------------------------------------------------
-#define BPOSD_FAST_DISPATCH(real, t, n, EXPR)                                                    \
+#define BPOSD_FAST_GEOM(DCv, DVv, EXPR)                                                          \
     do {                                                                                         \
-        const int vpt__ = fast_vpt(n);                                                           \
-        if (t.DC == 4 && vpt__ == 4) { constexpr int DC = 4, DV = 2, VPT = 4; EXPR; }            \
-        else if (t.DC == 4) { constexpr int DC = 4, DV = 2, VPT = 8; EXPR; }                     \
-        else if (t.DC == 6 && vpt__ == 4) { constexpr int DC = 6, DV = 3, VPT = 4; EXPR; }       \
-        else if (t.DC == 6) { constexpr int DC = 6, DV = 3, VPT = 8; EXPR; }                     \
-        else if (t.DC == 8 && vpt__ == 4) { constexpr int DC = 8, DV = 4, VPT = 4; EXPR; }       \
-        else if (t.DC == 8) { constexpr int DC = 8, DV = 4, VPT = 8; EXPR; }                     \
-        else if (vpt__ == 4) { constexpr int DC = 16, DV = 8, VPT = 4; EXPR; }                   \
-        else { constexpr int DC = 16, DV = 8, VPT = 8; EXPR; }                                   \
+        constexpr int DC = DCv, DV = DVv;                                                        \
+        if (vpt__ == 4) { constexpr int VPT = 4, MAXT = 512; if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } \
+        else if (maxt__ == 512) { constexpr int VPT = 8, MAXT = 512; if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } \
+        else { constexpr int VPT = 8, MAXT = 1024; if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } \
+    } while (0)
+
+#define BPOSD_FAST_DISPATCH(t, n, EXPR)                                                          \
+    do {                                                                                         \
+        const int vpt__ = fast_vpt(n), maxt__ = fast_maxt(n);                                    \
+        const bool reg__ = t.regular != 0;                                                       \
+        if (t.DC == 4) BPOSD_FAST_GEOM(4, 2, EXPR);                                              \
+        else if (t.DC == 6) BPOSD_FAST_GEOM(6, 3, EXPR);                                         \
+        else if (t.DC == 8) BPOSD_FAST_GEOM(8, 4, EXPR);                                         \
+        else BPOSD_FAST_GEOM(16, 8, EXPR);                                                       \
     } while (0)
 
 template <typename real>
 static inline cudaError_t fast_set_smem_t(const FastTables &t, int n, size_t smem) {
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_DISPATCH(real, t, n, e = cudaFuncSetAttribute(bp_fast_kernel<real, DC, DV, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BPOSD_FAST_DISPATCH(t, n, e = cudaFuncSetAttribute(bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return e;
 }
 template <typename real>
 static inline cudaError_t fast_occupancy_t(const FastTables &t, int n, int threads, size_t smem, int *occ) {
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_DISPATCH(real, t, n, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bp_fast_kernel<real, DC, DV, VPT>, threads, smem));
+    BPOSD_FAST_DISPATCH(t, n, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, threads, smem));
     return e;
 }
 template <typename real>
 static inline void fast_launch(const FastTables &t, const BpArgs<real> &a, int grid, int threads, int smem, cudaStream_t st) {
-    BPOSD_FAST_DISPATCH(real, t, a.g.n, (bp_fast_kernel<real, DC, DV, VPT><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg)));
+    BPOSD_FAST_DISPATCH(t, a.g.n, (bp_fast_kernel<real, DC, DV, VPT, MAXT, REG><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg, t.d_row_of)));
 }
 
 } // namespace bposd

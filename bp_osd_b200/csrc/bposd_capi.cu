@@ -151,7 +151,7 @@ static int plan_geometry_t(bposd_handle *h) {
     // candidate kernels, best first
     int kernel = -1;
     size_t smem = 0;
-    const bool fast_ok = fast_supported(h->max_col_deg, h->max_row_deg, h->bp_method);
+    const bool fast_ok = fast_supported(h->max_col_deg, h->max_row_deg, h->bp_method) && h->fast.DC > 0 && n <= 8192;
     const size_t smem_fast = fast_ok ? fast_smem_bytes<real>(h->fast, n, m) : ((size_t)1 << 40);
     const size_t smem_gen = (2 * (size_t)E + n) * rs + n + m + 16;
     const int want = h->force_kernel - 1;
@@ -166,6 +166,7 @@ static int plan_geometry_t(bposd_handle *h) {
     if (want == 0) { kernel = 0; smem = (size_t)m + 16; }
     int occ = 0;
     if (kernel == 2) {
+        threads = std::min(threads, fast_maxt(n));
         if (threads * fast_vpt(n) < n) threads = fast_default_threads(n, m);
         CU_TRY(h, fast_set_smem_t<real>(h->fast, n, smem));
         CU_TRY(h, fast_occupancy_t<real>(h->fast, n, threads, smem, &occ));
@@ -318,7 +319,7 @@ extern "C" int bposd_create(const int32_t *indptr, const int32_t *indices, int32
     CR_TRY(cudaMalloc((void **)&h->d_minw, sizeof(int)));
     for (auto &e : h->ev) CR_TRY(cudaEventCreate(&e));
     if (fast_supported(h->max_col_deg, h->max_row_deg, bp_method)) {
-        cudaError_t e = fast_build(h->fast, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot);
+        cudaError_t e = fast_build(h->fast, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot, precision / 8);
         if (e != cudaSuccess) { h->err = std::string("fast_build: ") + cudaGetErrorString(e); return die(BPOSD_ECUDA); }
     }
     int rc = plan_geometry(h);
