@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbposd_b200.so")
+LIB_PATH = os.environ.get("BPOSD_LIB") or os.path.join(_HERE, "libbposd_b200.so")  # BPOSD_LIB: A/B builds
 
 BP_PRODUCT_SUM, BP_MINIMUM_SUM = 0, 1
 OSD_0, OSD_E, OSD_CS, OSD_OFF = 0, 1, 2, 3

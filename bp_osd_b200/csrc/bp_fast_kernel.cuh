@@ -23,6 +23,7 @@
 #include "bposd_kernels.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <random>
 #include <vector>
 
@@ -54,8 +55,26 @@ static inline void fast_free(FastTables &t) {
     t.d_vslot = nullptr; t.d_cdeg = nullptr; t.d_row_of = nullptr;
 }
 
-static inline int fast_vpt(int n) { return n <= 2048 ? 4 : 8; }
-static inline int fast_maxt(int n) { return n <= 4096 ? 512 : 1024; }
+// bits per thread and the CTA size cap: (2, 1024) | (4, 512) | (8, 512) | (8, 1024)
+// Geometry: bits per thread (VPT) and CTA size cap (MAXT) by code size.  Measured on B200 (profiles/):
+// fp64 wants no spills (register cap 128, few big-ILP warps), fp32 wants occupancy (cap 64).
+//   n <= 256: (2, 128)   n <= 2048: (8, 256)   n <= 4096: (8, 512)   n <= 8192: (8, 1024)
+#ifndef BPOSD_CHECK_UNROLL
+#define BPOSD_CHECK_UNROLL 1
+#endif
+constexpr int kCheckUnroll = BPOSD_CHECK_UNROLL; // rows of the check sweep interleaved per thread
+#ifndef BPOSD_REGCAP64
+#define BPOSD_REGCAP64 128
+#endif
+#ifndef BPOSD_REGCAP32
+#define BPOSD_REGCAP32 64
+#endif
+static inline int fast_vpt(int n) { return n <= 256 ? 2 : 8; }
+static inline int fast_maxt(int n) { return n <= 256 ? 128 : (n <= 2048 ? 256 : (n <= 4096 ? 512 : 1024)); }
+template <typename real, int MAXT> constexpr int fast_minb() {
+    constexpr int cap = sizeof(real) == 8 ? BPOSD_REGCAP64 : BPOSD_REGCAP32;
+    return (65536 / (MAXT * cap)) < 1 ? 1 : (65536 / (MAXT * cap));
+}
 
 static inline int fast_default_threads(int n, int m) {
     (void)m;
@@ -213,11 +232,11 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
 
 template <typename real>
 static inline size_t fast_smem_bytes(const FastTables &t, int n, int m) {
-    (void)n;
     if (t.DC == 0) return (size_t)1 << 40;
     size_t msgs = ((size_t)m * t.DC * sizeof(real) + 15) / 16 * 16;
     size_t meta = ((size_t)m + 15) / 16 * 16;
-    return msgs + meta + 16;
+    size_t prior = ((size_t)n * sizeof(real) + 15) / 16 * 16; // copy of the priors when they are not uniform
+    return msgs + meta + prior + 16;
 }
 
 // ---- vector row load/store helpers -----------------------------------------------------------
@@ -255,17 +274,18 @@ template <int DC> struct RowIO<float, DC> {
     }
 };
 
-// word that carries the IEEE sign bit in bit 31, and "flip the sign where bit 31 of s is set"
+// bit-level helpers: word that carries the IEEE sign bit in bit 31, |x| on the integer pipe, and
+// "x with the high word replaced" (used to build +-alpha without a select)
 __device__ __forceinline__ uint32_t sign_word(double x) { return (uint32_t)__double2hiint(x); }
 __device__ __forceinline__ uint32_t sign_word(float x) { return __float_as_uint(x); }
-__device__ __forceinline__ double xor_sign(double x, uint32_t s) {
-    return __hiloint2double(__double2hiint(x) ^ (int)(s & 0x80000000u), __double2loint(x));
-}
-__device__ __forceinline__ float xor_sign(float x, uint32_t s) { return __uint_as_float(__float_as_uint(x) ^ (s & 0x80000000u)); }
+__device__ __forceinline__ double abs_bits(double x) { return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x)); }
+__device__ __forceinline__ float abs_bits(float x) { return __uint_as_float(__float_as_uint(x) & 0x7fffffffu); }
+__device__ __forceinline__ double with_sign_word(double x, uint32_t w) { return __hiloint2double((int)w, __double2loint(x)); }
+__device__ __forceinline__ float with_sign_word(float, uint32_t w) { return __uint_as_float(w); }
 template <typename real> __device__ __forceinline__ real lt_min(real a, real b) { return (a < b) ? a : b; } // `if (a < t) t = a`
 
 template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
+__global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
                                                        const uint8_t *__restrict__ cdeg_tab,
                                                        const uint16_t *__restrict__ row_of_tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -274,6 +294,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) bp_fast_kernel(Bp
     real *msg = reinterpret_cast<real *>(smem_raw);
     uint8_t *meta = smem_raw + ((size_t)m * DC * sizeof(real) + 15) / 16 * 16; // bit0 mismatch, bits1-5 degree, bit7 syndrome
     unsigned *meta32 = reinterpret_cast<unsigned *>(meta);
+    real *prior_s = reinterpret_cast<real *>(meta + ((size_t)m + 15) / 16 * 16); // [n] priors when they are not uniform
     __shared__ long long sh_shot;
     __shared__ int sh_slot;
 
@@ -295,7 +316,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) bp_fast_kernel(Bp
         for (int p = tid; p < m; p += T)
             for (int k = cdeg_tab[p]; k < DC; k++) msg[p * DC + k] = real_max<real>();
     unsigned long long n_conv = 0, n_iter = 0;
-    const bool shared_prior = a.prior_stride == 0;
+    const bool uniform = a.uniform_prior != 0;
+    const real prior_u = a.prior[0];
 
     for (;;) {
         __syncthreads();
@@ -304,67 +326,76 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) bp_fast_kernel(Bp
         const long long shot = sh_shot;
         if (shot >= a.B) break;
         const real *prior = a.prior + shot * a.prior_stride;
-        (void)shared_prior;
 
         for (int p = tid; p < m; p += T) {
             const unsigned s = a.synd[shot * m + row_of_tab[p]] & 1u;
             meta[p] = (uint8_t)(s | ((unsigned)cdeg_tab[p] << 1) | (s << 7));
         }
-        real llr[VPT], pri[VPT];
+        real llr[VPT];
         unsigned dprev = 0;
 #pragma unroll
         for (int r = 0; r < VPT; r++) {
             const int j = tid + r * T;
-            pri[r] = (j < n) ? prior[j] : (real)0;
-            llr[r] = pri[r];
+            llr[r] = 0;
             if (j < n) {
+                const real pj = uniform ? prior_u : prior[j];
+                if (!uniform) prior_s[j] = pj;
+                llr[r] = pj;
 #pragma unroll
                 for (int k = 0; k < DV; k++)
-                    if (REG || k < dj[r]) *reinterpret_cast<real *>(smem_raw + off[r][k]) = pri[r];
+                    if (REG || k < dj[r]) *reinterpret_cast<real *>(smem_raw + off[r][k]) = pj;
             }
         }
         __syncthreads();
 
         bool conv = false;
         int iters = 0;
+        real pow2 = 1; // 2^-it, exact
         for (int it = 1;; it++) {
             const bool last = it > a.max_iter;
-            const real alpha = ms_alpha(a.alpha0, it);
+            pow2 *= (real)0.5;
+            const real alpha = (a.alpha0 == (real)0) ? (real)1 - pow2 : a.alpha0;
+            const uint32_t alpha_w = sign_word(alpha);
             bool ok = true;
             // ---- check sweep (a4) + convergence vote for the previous pass (a7) ----
+#pragma unroll kCheckUnroll
             for (int p = tid; p < m; p += T) {
                 const unsigned mt = meta[p];
                 if (mt & 1u) ok = false;
                 if (last) continue;
-                real v[DC], av[DC], pre[DC], suf[DC];
+                real v[DC], suf[DC];
+                uint32_t sw[DC];
                 RowIO<real, DC>::load(msg + (size_t)p * DC, v);
                 uint32_t X = (mt & 0x80u) << 24;
 #pragma unroll
-                for (int k = 0; k < DC; k++) { av[k] = r_abs(v[k]); X ^= sign_word(v[k]); }
-                pre[0] = av[0];
+                for (int k = 0; k < DC; k++) { sw[k] = sign_word(v[k]); X ^= sw[k]; v[k] = abs_bits(v[k]); }
+                // suffix minima first, then one running prefix minimum: out[k] = min(prefix before k, suffix after k)
+                suf[DC - 1] = v[DC - 1];
 #pragma unroll
-                for (int k = 1; k < DC; k++) pre[k] = lt_min(av[k], pre[k - 1]);
-                suf[DC - 1] = av[DC - 1];
-#pragma unroll
-                for (int k = DC - 2; k >= 0; k--) suf[k] = lt_min(av[k], suf[k + 1]);
+                for (int k = DC - 2; k >= 1; k--) suf[k] = lt_min(v[k], suf[k + 1]);
                 real out[DC];
+                real run = v[0];
                 out[0] = (DC > 1) ? suf[DC > 1 ? 1 : 0] : real_max<real>();
-                out[DC - 1] = (DC > 1) ? pre[DC > 1 ? DC - 2 : 0] : real_max<real>();
 #pragma unroll
-                for (int k = 1; k < DC - 1; k++) out[k] = lt_min(suf[k + 1], pre[k - 1]);
-                if (pre[DC - 1] == (real)0) {
+                for (int k = 1; k < DC - 1; k++) { out[k] = lt_min(suf[k + 1], run); run = lt_min(v[k], run); }
+                if (DC > 1) out[DC - 1] = run;
+                const real all_min = (DC > 1) ? lt_min(v[DC - 1], run) : v[0];
+                if (all_min == (real)0) {
                     // some message is +-0: "<= 0" counts +0 as negative, the sign bit does not -> exact path
+                    // (the magnitudes are already in v; a zero magnitude with a clear sign bit is the +0 case)
                     int tot = (int)(mt >> 7);
 #pragma unroll
-                    for (int k = 0; k < DC; k++) tot += (v[k] <= 0) ? 1 : 0;
+                    for (int k = 0; k < DC; k++) tot += ((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0;
 #pragma unroll
                     for (int k = 0; k < DC; k++) {
-                        const int sg = tot + ((v[k] <= 0) ? 1 : 0);
+                        const int sg = tot + (((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0);
                         out[k] = out[k] * ((sg & 1) ? -alpha : alpha);
                     }
                 } else {
+                    // sign of edge k = syndrome ^ (parity of all sign bits) ^ own sign bit; fold it into alpha
+                    const uint32_t XA = (X & 0x80000000u) ^ alpha_w;
 #pragma unroll
-                    for (int k = 0; k < DC; k++) out[k] = xor_sign(out[k] * alpha, X ^ sign_word(v[k]));
+                    for (int k = 0; k < DC; k++) out[k] = out[k] * with_sign_word(alpha, XA ^ (sw[k] & 0x80000000u));
                 }
                 if (!REG) {
                     const int deg = (mt >> 1) & 0x1f;
@@ -377,6 +408,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) bp_fast_kernel(Bp
             if (it > 1 && all_ok) { conv = true; iters = it - 1; break; }
             if (last) { iters = a.max_iter; break; }
             // ---- bit sweep (a6 + a8) ----
+            unsigned dnow = 0;
 #pragma unroll
             for (int r = 0; r < VPT; r++) {
                 const int j = tid + r * T;
@@ -384,15 +416,29 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) bp_fast_kernel(Bp
                     real c[DV], pre[DV];
 #pragma unroll
                     for (int k = 0; k < DV; k++) c[k] = (REG || k < dj[r]) ? *reinterpret_cast<const real *>(smem_raw + off[r][k]) : (real)0;
-                    real t = pri[r];
+                    real t = uniform ? prior_u : prior_s[j];
 #pragma unroll
                     for (int k = 0; k < DV; k++)
                         if (REG || k < dj[r]) { pre[k] = t; t += c[k]; }
                     llr[r] = t;
-                    const unsigned d = (t <= 0) ? 1u : 0u;
-                    if (d != ((dprev >> r) & 1u)) {
-                        // hard decision flipped: toggle the parity-mismatch bit of every neighbouring check
-                        dprev ^= 1u << r;
+                    dnow |= ((t <= 0) ? 1u : 0u) << r;
+                    real sfx = 0;
+#pragma unroll
+                    for (int k = DV - 1; k >= 0; k--)
+                        if (REG || k < dj[r]) {
+                            // the last edge gets pre + 0, which is pre itself (sign of zero is immaterial downstream)
+                            *reinterpret_cast<real *>(smem_raw + off[r][k]) = (REG && k == DV - 1) ? pre[k] : pre[k] + sfx;
+                            sfx = (REG && k == DV - 1) ? c[k] : sfx + c[k];
+                        }
+                }
+            }
+            if (dnow != dprev) {
+                // a hard decision flipped (rare): toggle the parity-mismatch bit of every neighbouring check
+                unsigned flip = dnow ^ dprev;
+                dprev = dnow;
+#pragma unroll
+                for (int r = 0; r < VPT; r++)
+                    if ((flip >> r) & 1u) {
 #pragma unroll
                         for (int k = 0; k < DV; k++)
                             if (REG || k < dj[r]) {
@@ -400,15 +446,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) bp_fast_kernel(Bp
                                 atomicXor(&meta32[p >> 2], 1u << ((p & 3u) * 8u));
                             }
                     }
-                    real sfx = 0;
-#pragma unroll
-                    for (int k = DV - 1; k >= 0; k--)
-                        if (REG || k < dj[r]) {
-                            // the last edge gets pre + 0, which is pre itself (sign of zero is immaterial downstream)
-                            *reinterpret_cast<real *>(smem_raw + off[r][k]) = (REG && k == DV - 1) ? pre[k] : pre[k] + sfx;
-                            sfx += c[k];
-                        }
-                }
             }
             __syncthreads();
         }
@@ -452,17 +489,19 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 512 ? 2 : 1)) bp_fast_kernel(Bp
 }
 
 // ---- dispatch over the degree classes ---------------------------------------------------------
+#define BPOSD_FAST_REG(EXPR) do { if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } while (0)
 #define BPOSD_FAST_GEOM(DCv, DVv, EXPR)                                                          \
     do {                                                                                         \
         constexpr int DC = DCv, DV = DVv;                                                        \
-        if (vpt__ == 4) { constexpr int VPT = 4, MAXT = 512; if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } \
-        else if (maxt__ == 512) { constexpr int VPT = 8, MAXT = 512; if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } \
-        else { constexpr int VPT = 8, MAXT = 1024; if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } \
+        if (maxt__ == 128) { constexpr int VPT = 2, MAXT = 128; BPOSD_FAST_REG(EXPR); }          \
+        else if (maxt__ == 256) { constexpr int VPT = 8, MAXT = 256; BPOSD_FAST_REG(EXPR); }     \
+        else if (maxt__ == 512) { constexpr int VPT = 8, MAXT = 512; BPOSD_FAST_REG(EXPR); }     \
+        else { constexpr int VPT = 8, MAXT = 1024; BPOSD_FAST_REG(EXPR); }                       \
     } while (0)
 
 #define BPOSD_FAST_DISPATCH(t, n, EXPR)                                                          \
     do {                                                                                         \
-        const int vpt__ = fast_vpt(n), maxt__ = fast_maxt(n);                                    \
+        const int maxt__ = fast_maxt(n);                                                         \
         const bool reg__ = t.regular != 0;                                                       \
         if (t.DC == 4) BPOSD_FAST_GEOM(4, 2, EXPR);                                              \
         else if (t.DC == 6) BPOSD_FAST_GEOM(6, 3, EXPR);                                         \

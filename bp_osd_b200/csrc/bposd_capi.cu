@@ -30,7 +30,7 @@ struct bposd_handle {
     int *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_col_ptr = nullptr, *d_row_idx = nullptr, *d_csc_slot = nullptr;
     double *d_prior64 = nullptr, *d_weight = nullptr;
     float *d_prior32 = nullptr;
-    int uniform = 0;
+    int uniform = 0, uniform_prior = 0;
     // fast-kernel tables
     FastTables fast;
     // control words: [0] queue, [1] converged, [2] iterations, [3] osd invocations, then int fail_count
@@ -126,8 +126,9 @@ static int upload_probs(bposd_handle *h) {
         prior32[j] = (float)prior[j];
         if (!(p == h->probs[0])) uni = false;
     }
+    h->uniform_prior = uni ? 1 : 0; // all priors bit-identical (any value, including +-inf)
     if (uni && !(h->probs[0] > 0.0 && h->probs[0] < 1.0)) uni = false;
-    h->uniform = uni ? 1 : 0;
+    h->uniform = uni ? 1 : 0;       // OSD weights: popcount ordering is exact only for 0 < p < 1
     CU_TRY(h, cudaMemcpy(h->d_prior64, prior.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(h->d_prior32, prior32.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(h->d_weight, weight.data(), n * sizeof(double), cudaMemcpyHostToDevice));
@@ -403,6 +404,7 @@ static int decode_batch_t(bposd_handle *h, const uint8_t *d_synd, long long B, c
         a.max_iter = h->max_iter;
         a.method = h->bp_method;
         a.alpha0 = (real)h->alpha;
+        a.uniform_prior = d_priors ? 0 : h->uniform_prior;
         if (d_priors) { a.prior = static_cast<const real *>(d_priors) + c0 * n; a.prior_stride = n; }
         else { a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32; a.prior_stride = 0; }
         a.synd = d_synd + c0 * m;

@@ -37,6 +37,7 @@ struct BpArgs {
     real alpha0;  // 0 => 1 - 2^-it
     const real *prior;
     long long prior_stride; // 0: one prior vector for all shots, n: per-shot rows
+    int uniform_prior;      // 1: every bit has the same prior (a scalar in registers)
     const uint8_t *synd;
     long long B;
     uint8_t *bp, *osd0, *osdw;
