@@ -278,7 +278,8 @@ def run_gpu(args):
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             tj = json.load(f)
-        traffic = tj.get(f"bp_fp{prec}_dram_bytes_per_launch")
+        per_shot = tj.get(f"bp_fp{prec}_dram_bytes_per_shot")
+        traffic = per_shot * S if per_shot else None  # ncu --set full capture, scaled to this launch's shots
     except Exception:
         pass
     roofline = {
@@ -287,9 +288,16 @@ def run_gpu(args):
         "algorithmic_bytes_per_launch": alg_bytes_rank / max(args.steps, 1),
         "note": "algorithmic bytes = it*(4E+2n)*w + in/out per SURVEY 8(d); messages are kept in shared memory, so "
                 "frac can exceed 1: HBM is not the binding resource, shared-memory bandwidth is (see DESIGN.md)",
+        "smem": {"bound": "shared-memory pipe", "achieved": (iters * 4 * E * w) / (ms_bp * 1e-3) / 1e9 if ms_bp > 0 else None,
+                 "peak": info["sm_count"] * 128 * (clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9, "unit": "GB/s",
+                 "note": "4*E*w bytes per shot-iteration (each message read and written once per sweep) against "
+                         "SMs x 128 B/clk x max SM clock"},
         "bp_ms_per_step": ms_bp / args.steps, "osd_ms_per_step": ms_osd / args.steps,
         "mean_iterations": iters / (S * args.steps), "bp_shot_iterations_per_s": iters / (ms_bp * 1e-3) if ms_bp else None,
     }
+
+    if roofline["smem"]["achieved"]:
+        roofline["smem"]["frac"] = roofline["smem"]["achieved"] / roofline["smem"]["peak"]
 
     # ---- end to end through the public API with pinned host buffers ----
     Se = min(S, args.e2e_shots_per_gpu)
