@@ -22,9 +22,13 @@
 #pragma once
 #include "bposd_kernels.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <random>
+#include <string>
 #include <vector>
 
 namespace bposd {
@@ -33,9 +37,10 @@ struct FastTables {
     int DC = 0, DV = 0;            // degree class (upper bounds, compile-time in the kernel)
     int regular = 0;               // every row has exactly DC entries and every column exactly DV
     int elem_bytes = 8;
-    uint16_t *d_vslot = nullptr;   // [n, DV] message slot of the k-th edge of bit j (ascending row), 0xFFFF = none
+    uint16_t *d_vslot = nullptr;   // [n, DV] message slot of the k-th edge (ascending row) of the bit at position q, 0xFFFF = none
     uint8_t *d_cdeg = nullptr;     // [m] degree of the check stored in physical row p
     uint16_t *d_row_of = nullptr;  // [m] original check index of physical row p
+    uint16_t *d_bit_of = nullptr;  // [n] bit handled at thread position q (the layout pass permutes bits too)
     long long conflicts_before = 0, conflicts_after = 0, wavefronts_ideal = 0;
 };
 
@@ -51,8 +56,8 @@ static inline void fast_class(int max_col_deg, int max_row_deg, int *DC, int *DV
 }
 
 static inline void fast_free(FastTables &t) {
-    cudaFree(t.d_vslot); cudaFree(t.d_cdeg); cudaFree(t.d_row_of);
-    t.d_vslot = nullptr; t.d_cdeg = nullptr; t.d_row_of = nullptr;
+    cudaFree(t.d_vslot); cudaFree(t.d_cdeg); cudaFree(t.d_row_of); cudaFree(t.d_bit_of);
+    t.d_vslot = nullptr; t.d_cdeg = nullptr; t.d_row_of = nullptr; t.d_bit_of = nullptr;
 }
 
 // bits per thread and the CTA size cap: (2, 1024) | (4, 512) | (8, 512) | (8, 1024)
@@ -91,16 +96,20 @@ static inline int fast_default_threads(int n, int m) {
 // permutation and the in-row edge positions minimises the total number of wavefronts.
 // ---------------------------------------------------------------------------------------------
 struct LayoutOpt {
-    int m, n, DC, DV, nbanks;
+    int m, n, DC, DV, nbanks, group;
     std::vector<int> prow;             // check -> physical row
     std::vector<int> kappa;            // CSR edge -> position inside its physical row
-    std::vector<int> edge_group;       // CSR edge -> access group id
+    std::vector<int> pos;              // bit -> position (thread tid = pos % T handles it in round pos / T)
+    std::vector<int> edge_k;           // CSR edge -> index of the edge inside its bit (ascending row)
     std::vector<int> edge_row;         // CSR edge -> check
+    std::vector<int> edge_col;         // CSR edge -> bit
     std::vector<int> hist;             // [group][bank] number of lanes of the group that hit the bank
+    int group_of(int e) const { return (pos[edge_col[e]] / group) * DV + edge_k[e]; }
     int bank_of(int e) const { return (prow[edge_row[e]] * DC + kappa[e]) % nbanks; }
+    int &cell(int e) { return hist[(size_t)group_of(e) * nbanks + bank_of(e)]; }
     // pair cost: sum over groups and banks of C(count, 2); moving one edge changes it by count differences
-    long long remove(int e) { int &c = hist[(size_t)edge_group[e] * nbanks + bank_of(e)]; c--; return -(long long)c; }
-    long long add(int e) { int &c = hist[(size_t)edge_group[e] * nbanks + bank_of(e)]; long long d = c; c++; return d; }
+    long long remove(int e) { int &c = cell(e); c--; return -(long long)c; }
+    long long add(int e) { int &c = cell(e); long long d = c; c++; return d; }
     long long wavefronts() const { // what the hardware pays: max bank multiplicity per group
         long long w = 0;
         for (size_t g = 0; g * nbanks < hist.size(); g++) {
@@ -112,6 +121,100 @@ struct LayoutOpt {
     }
 };
 
+struct LayoutResult {
+    std::vector<int> prow, kappa, pos;
+    long long before = 0, after = 0, ideal = 0;
+};
+
+#ifndef BPOSD_LAYOUT_MS
+#define BPOSD_LAYOUT_MS 1500 // wall-clock budget of the layout search per (matrix, precision)
+#endif
+
+// Local search over three kinds of moves, always anchored at an edge that currently conflicts:
+// swap the physical rows of two checks, swap two positions inside a check's row, swap the thread
+// positions of two bits.  Downhill and sideways moves are taken (the plateaus are wide).
+static inline LayoutResult fast_layout_search(int m, int n, int DC, int DV, int elem_bytes, const std::vector<int> &row_ptr,
+                                              const std::vector<int> &col_idx, const std::vector<int> &col_ptr,
+                                              const std::vector<int> &csc_slot) {
+    const int E = row_ptr[m];
+    LayoutOpt L;
+    L.m = m; L.n = n; L.DC = DC; L.DV = DV;
+    L.group = elem_bytes == 8 ? 16 : 32; // lanes served together by one wavefront
+    L.nbanks = L.group;                  // banks in units of the element size
+    L.prow.resize(m); L.kappa.resize(E); L.edge_row.resize(E); L.edge_col.resize(E); L.edge_k.assign(E, 0); L.pos.resize(n);
+    for (int i = 0; i < m; i++) {
+        L.prow[i] = i;
+        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) { L.kappa[e] = e - row_ptr[i]; L.edge_row[e] = i; L.edge_col[e] = col_idx[e]; }
+    }
+    for (int j = 0; j < n; j++) {
+        L.pos[j] = j;
+        for (int q = col_ptr[j]; q < col_ptr[j + 1]; q++) L.edge_k[csc_slot[q]] = q - col_ptr[j];
+    }
+    const int ngroups = ((n + L.group - 1) / L.group) * DV;
+    L.hist.assign((size_t)ngroups * L.nbanks, 0);
+    long long cur = 0, ideal = 0;
+    for (int e = 0; e < E; e++) cur += L.add(e);
+    {
+        std::vector<char> used(ngroups, 0);
+        for (int e = 0; e < E; e++) used[L.group_of(e)] = 1;
+        for (char u : used) ideal += u;
+    }
+    LayoutResult res;
+    res.ideal = ideal;
+    res.before = L.wavefronts() - ideal;
+    std::mt19937 rng(12345u);
+    const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(BPOSD_LAYOUT_MS);
+    const long long budget = 40000ll * std::max(E, 1);
+    auto rem_bit = [&](int j) { long long d = 0; for (int q = col_ptr[j]; q < col_ptr[j + 1]; q++) d += L.remove(csc_slot[q]); return d; };
+    auto add_bit = [&](int j) { long long d = 0; for (int q = col_ptr[j]; q < col_ptr[j + 1]; q++) d += L.add(csc_slot[q]); return d; };
+    auto rem_row = [&](int i) { long long d = 0; for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) d += L.remove(e); return d; };
+    auto add_row = [&](int i) { long long d = 0; for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) d += L.add(e); return d; };
+    for (long long iter = 0; iter < budget && cur > 0 && E > 0; iter++) {
+        if ((iter & 0xFFFF) == 0xFFFF && std::chrono::steady_clock::now() > t_end) break;
+        const int e0 = (int)(rng() % (unsigned)E);
+        if (L.cell(e0) <= 1) continue; // anchor moves at a conflicting edge
+        const unsigned mv = rng() % 3u;
+        if (mv == 0) {
+            const int i1 = L.edge_row[e0], i2 = (int)(rng() % (unsigned)m);
+            if (i1 == i2) continue;
+            long long d = rem_row(i1) + rem_row(i2);
+            std::swap(L.prow[i1], L.prow[i2]);
+            d += add_row(i1) + add_row(i2);
+            if (d <= 0) { cur += d; continue; }
+            rem_row(i1); rem_row(i2);
+            std::swap(L.prow[i1], L.prow[i2]);
+            add_row(i1); add_row(i2);
+        } else if (mv == 1) {
+            // exchange two occupied positions of this row (pad positions of short rows stay at the end:
+            // the kernel keeps +max in positions >= degree)
+            const int i = L.edge_row[e0], dg = row_ptr[i + 1] - row_ptr[i];
+            if (dg < 2) continue;
+            const int e1 = e0, e2 = row_ptr[i] + (int)(rng() % (unsigned)dg);
+            if (e1 == e2) continue;
+            long long d = L.remove(e1) + L.remove(e2);
+            std::swap(L.kappa[e1], L.kappa[e2]);
+            d += L.add(e1) + L.add(e2);
+            if (d <= 0) { cur += d; continue; }
+            L.remove(e1); L.remove(e2);
+            std::swap(L.kappa[e1], L.kappa[e2]);
+            L.add(e1); L.add(e2);
+        } else {
+            const int j1 = L.edge_col[e0], j2 = (int)(rng() % (unsigned)n);
+            if (j1 == j2 || L.pos[j1] / L.group == L.pos[j2] / L.group) continue;
+            long long d = rem_bit(j1) + rem_bit(j2);
+            std::swap(L.pos[j1], L.pos[j2]);
+            d += add_bit(j1) + add_bit(j2);
+            if (d <= 0) { cur += d; continue; }
+            rem_bit(j1); rem_bit(j2);
+            std::swap(L.pos[j1], L.pos[j2]);
+            add_bit(j1); add_bit(j2);
+        }
+    }
+    res.after = L.wavefronts() - ideal;
+    res.prow = L.prow; res.kappa = L.kappa; res.pos = L.pos;
+    return res;
+}
+
 static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vector<int> &row_ptr,
                                      const std::vector<int> &col_idx, const std::vector<int> &col_ptr,
                                      const std::vector<int> &row_idx, const std::vector<int> &csc_slot,
@@ -122,100 +225,44 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
     fast_class(mc, mr, &t.DC, &t.DV);
     t.elem_bytes = elem_bytes;
     t.regular = (m > 0 && minr == t.DC && mr == t.DC && minc == t.DV && mc == t.DV) ? 1 : 0;
-    if ((long long)m * t.DC >= 0xFFFF || m == 0) { t.DC = 0; return cudaSuccess; } // slots must fit in 16 bits
-    const int E = row_ptr[m];
-    LayoutOpt L;
-    L.m = m; L.n = n; L.DC = t.DC; L.DV = t.DV;
-    const int group = elem_bytes == 8 ? 16 : 32; // lanes served together by one wavefront
-    L.nbanks = elem_bytes == 8 ? 16 : 32;        // banks in units of the element size
-    L.prow.resize(m); L.kappa.resize(E); L.edge_row.resize(E); L.edge_group.assign(E, 0);
-    for (int i = 0; i < m; i++) {
-        L.prow[i] = i;
-        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) { L.kappa[e] = e - row_ptr[i]; L.edge_row[e] = i; }
-    }
-    // access groups: bits are dealt to threads as j = tid + r*T with T a multiple of 32, so the lanes
-    // served together are `group` consecutive j; group id = (j / group, k)
-    const int ngroups = ((n + group - 1) / group) * t.DV;
-    for (int j = 0; j < n; j++)
-        for (int q = col_ptr[j]; q < col_ptr[j + 1]; q++) L.edge_group[csc_slot[q]] = (j / group) * t.DV + (q - col_ptr[j]);
-    L.hist.assign((size_t)ngroups * L.nbanks, 0);
-    long long pairs = 0, ideal = 0;
-    for (int e = 0; e < E; e++) pairs += L.add(e);
+    if ((long long)m * t.DC >= 0xFFFF || m == 0 || n >= 0xFFFF) { t.DC = 0; return cudaSuccess; } // slots and bits must fit in 16 bits
+    // the search is deterministic; results are cached per (matrix, precision) for the life of the process
+    static std::mutex mu;
+    static std::map<std::string, LayoutResult> cache;
+    std::string key;
     {
-        std::vector<char> used(ngroups, 0);
-        for (int e = 0; e < E; e++) used[L.edge_group[e]] = 1;
-        for (char u : used) ideal += u;
+        const int head[5] = {m, n, t.DC, t.DV, elem_bytes};
+        key.append(reinterpret_cast<const char *>(head), sizeof(head));
+        key.append(reinterpret_cast<const char *>(row_ptr.data()), row_ptr.size() * sizeof(int));
+        key.append(reinterpret_cast<const char *>(col_idx.data()), col_idx.size() * sizeof(int));
     }
-    t.wavefronts_ideal = ideal;
-    t.conflicts_before = L.wavefronts() - ideal;
-    // local search on the pair cost: swap two physical rows, or two positions inside one row
-    std::mt19937 rng(12345u);
-    const long long budget = std::min<long long>(3000000, 600ll * E);
-    long long cur = pairs;
-    // simulated annealing: uphill moves of size d are accepted with probability exp(-d/temp)
-    auto accept = [&](long long d, long long iter) {
-        if (d <= 0) return true;
-        // a short, cool annealing tail helps tiny graphs; large ones do best with plain descent
-        if (E > 2000 || iter > budget / 2) return false;
-        const double temp = 0.3 * (1.0 - 2.0 * (double)iter / (double)budget) + 1e-3;
-        return (rng() & 0xFFFFFF) < (unsigned)(16777216.0 * std::exp(-(double)d / temp));
-    };
-    for (long long iter = 0; iter < budget && cur > 0; iter++) {
-        if (rng() & 1) {
-            const int i1 = rng() % m, i2 = rng() % m;
-            if (i1 == i2) continue;
-            long long d = 0;
-            for (int e = row_ptr[i1]; e < row_ptr[i1 + 1]; e++) d += L.remove(e);
-            for (int e = row_ptr[i2]; e < row_ptr[i2 + 1]; e++) d += L.remove(e);
-            std::swap(L.prow[i1], L.prow[i2]);
-            for (int e = row_ptr[i1]; e < row_ptr[i1 + 1]; e++) d += L.add(e);
-            for (int e = row_ptr[i2]; e < row_ptr[i2 + 1]; e++) d += L.add(e);
-            if (accept(d, iter)) { cur += d; continue; }
-            for (int e = row_ptr[i1]; e < row_ptr[i1 + 1]; e++) L.remove(e);
-            for (int e = row_ptr[i2]; e < row_ptr[i2 + 1]; e++) L.remove(e);
-            std::swap(L.prow[i1], L.prow[i2]);
-            for (int e = row_ptr[i1]; e < row_ptr[i1 + 1]; e++) L.add(e);
-            for (int e = row_ptr[i2]; e < row_ptr[i2 + 1]; e++) L.add(e);
-        } else {
-            const int i = rng() % m, dg = row_ptr[i + 1] - row_ptr[i];
-            // exchange two occupied positions of this row (pad positions of short rows stay at the end:
-            // the kernel keeps +max in positions >= degree)
-            if (dg < 2) continue;
-            const int p1 = rng() % dg, p2 = rng() % dg;
-            if (p1 == p2) continue;
-            int e1 = -1, e2 = -1;
-            for (int e = row_ptr[i]; e < row_ptr[i] + dg; e++) { if (L.kappa[e] == p1) e1 = e; if (L.kappa[e] == p2) e2 = e; }
-            if (e1 < 0 && e2 < 0) continue;
-            long long d = 0;
-            if (e1 >= 0) d += L.remove(e1);
-            if (e2 >= 0) d += L.remove(e2);
-            if (e1 >= 0) L.kappa[e1] = p2;
-            if (e2 >= 0) L.kappa[e2] = p1;
-            if (e1 >= 0) d += L.add(e1);
-            if (e2 >= 0) d += L.add(e2);
-            if (accept(d, iter)) { cur += d; continue; }
-            if (e1 >= 0) L.remove(e1);
-            if (e2 >= 0) L.remove(e2);
-            if (e1 >= 0) L.kappa[e1] = p1;
-            if (e2 >= 0) L.kappa[e2] = p2;
-            if (e1 >= 0) L.add(e1);
-            if (e2 >= 0) L.add(e2);
+    LayoutResult L;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            if (cache.size() > 64) cache.clear();
+            it = cache.emplace(key, fast_layout_search(m, n, t.DC, t.DV, elem_bytes, row_ptr, col_idx, col_ptr, csc_slot)).first;
         }
+        L = it->second;
     }
-    t.conflicts_after = L.wavefronts() - ideal;
+    t.wavefronts_ideal = L.ideal;
+    t.conflicts_before = L.before;
+    t.conflicts_after = L.after;
     std::vector<int> row_at(m);
     for (int i = 0; i < m; i++) row_at[L.prow[i]] = i;
 
-
-    std::vector<uint16_t> vs((size_t)n * t.DV, 0xFFFF), rowof(m);
+    // tables are indexed by thread position, not by bit: position q is served by thread q % T in round q / T
+    std::vector<uint16_t> vs((size_t)n * t.DV, 0xFFFF), rowof(m), bitof(n);
     std::vector<uint8_t> cd(m, 0);
     for (int p = 0; p < m; p++) { rowof[p] = (uint16_t)row_at[p]; cd[p] = (uint8_t)(row_ptr[row_at[p] + 1] - row_ptr[row_at[p]]); }
-    for (int j = 0; j < n; j++)
+    for (int j = 0; j < n; j++) {
+        bitof[L.pos[j]] = (uint16_t)j;
         for (int q = col_ptr[j]; q < col_ptr[j + 1]; q++) {
             const int i = row_idx[q], e = csc_slot[q];
-            vs[(size_t)j * t.DV + (q - col_ptr[j])] = (uint16_t)(L.prow[i] * t.DC + L.kappa[e]);
+            vs[(size_t)L.pos[j] * t.DV + (q - col_ptr[j])] = (uint16_t)(L.prow[i] * t.DC + L.kappa[e]);
         }
-    (void)col_idx;
+    }
     fast_free(t);
     cudaError_t e = cudaMalloc((void **)&t.d_vslot, vs.size() * sizeof(uint16_t));
     if (e != cudaSuccess) return e;
@@ -223,9 +270,13 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
     if (e != cudaSuccess) return e;
     e = cudaMalloc((void **)&t.d_row_of, rowof.size() * sizeof(uint16_t));
     if (e != cudaSuccess) return e;
+    e = cudaMalloc((void **)&t.d_bit_of, bitof.size() * sizeof(uint16_t));
+    if (e != cudaSuccess) return e;
     e = cudaMemcpy(t.d_vslot, vs.data(), vs.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(t.d_row_of, rowof.data(), rowof.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(t.d_bit_of, bitof.data(), bitof.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
     return cudaMemcpy(t.d_cdeg, cd.data(), cd.size(), cudaMemcpyHostToDevice);
 }
@@ -233,7 +284,8 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
 template <typename real>
 static inline size_t fast_smem_bytes(const FastTables &t, int n, int m) {
     if (t.DC == 0) return (size_t)1 << 40;
-    size_t msgs = ((size_t)m * t.DC * sizeof(real) + 15) / 16 * 16;
+    // the message array doubles as the staging area of the per-shot results ([n] reals + [n] bytes)
+    size_t msgs = (std::max((size_t)m * t.DC * sizeof(real), (size_t)n * (sizeof(real) + 1)) + 15) / 16 * 16;
     size_t meta = ((size_t)m + 15) / 16 * 16;
     size_t prior = ((size_t)n * sizeof(real) + 15) / 16 * 16; // copy of the priors when they are not uniform
     return msgs + meta + prior + 16;
@@ -287,18 +339,24 @@ template <typename real> __device__ __forceinline__ real lt_min(real a, real b) 
 template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
 __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
                                                        const uint8_t *__restrict__ cdeg_tab,
-                                                       const uint16_t *__restrict__ row_of_tab) {
+                                                       const uint16_t *__restrict__ row_of_tab,
+                                                       const uint16_t *__restrict__ bit_of_tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = a.g.m, n = a.g.n;
     const int tid = threadIdx.x, T = blockDim.x;
     real *msg = reinterpret_cast<real *>(smem_raw);
-    uint8_t *meta = smem_raw + ((size_t)m * DC * sizeof(real) + 15) / 16 * 16; // bit0 mismatch, bits1-5 degree, bit7 syndrome
+    const size_t msg_bytes = ((size_t)m * DC * sizeof(real) > (size_t)n * (sizeof(real) + 1) ? (size_t)m * DC * sizeof(real)
+                                                                                             : (size_t)n * (sizeof(real) + 1));
+    uint8_t *meta = smem_raw + (msg_bytes + 15) / 16 * 16; // bit0 mismatch, bits1-5 degree, bit7 syndrome
     unsigned *meta32 = reinterpret_cast<unsigned *>(meta);
-    real *prior_s = reinterpret_cast<real *>(meta + ((size_t)m + 15) / 16 * 16); // [n] priors when they are not uniform
+    real *prior_s = reinterpret_cast<real *>(meta + ((size_t)m + 15) / 16 * 16); // [n] priors by position when they are not uniform
+    real *st_llr = msg;                                         // per-shot result staging (after the last pass)
+    uint8_t *st_dec = reinterpret_cast<uint8_t *>(st_llr + n);
     __shared__ long long sh_shot;
     __shared__ int sh_slot;
 
-    // per-bit registers: byte offsets of the edges' slots (shot independent)
+    // per-position registers: byte offsets of the edges' slots (shot independent).  Position q = tid + r*T
+    // holds bit bit_of_tab[q]; only the prior look-up and the result staging need the bit index.
     unsigned off[VPT][DV];
     int dj[VPT];
 #pragma unroll
@@ -312,9 +370,6 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             dj[r] += (s != 0xFFFFu) ? 1 : 0;
         }
     }
-    if (!REG) // absent slots of short rows hold +max forever: neutral for min and sign
-        for (int p = tid; p < m; p += T)
-            for (int k = cdeg_tab[p]; k < DC; k++) msg[p * DC + k] = real_max<real>();
     unsigned long long n_conv = 0, n_iter = 0;
     const bool uniform = a.uniform_prior != 0;
     const real prior_u = a.prior[0];
@@ -329,7 +384,11 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
 
         for (int p = tid; p < m; p += T) {
             const unsigned s = a.synd[shot * m + row_of_tab[p]] & 1u;
-            meta[p] = (uint8_t)(s | ((unsigned)cdeg_tab[p] << 1) | (s << 7));
+            const unsigned deg = cdeg_tab[p];
+            meta[p] = (uint8_t)(s | (deg << 1) | (s << 7));
+            if (!REG) // absent slots of short rows hold +max: neutral for min and sign (the result staging
+                      // of the previous shot overwrote the array, so they are set again for every shot)
+                for (int k = (int)deg; k < DC; k++) msg[p * DC + k] = real_max<real>();
         }
         real llr[VPT];
         unsigned dprev = 0;
@@ -338,7 +397,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             const int j = tid + r * T;
             llr[r] = 0;
             if (j < n) {
-                const real pj = uniform ? prior_u : prior[j];
+                const real pj = uniform ? prior_u : prior[bit_of_tab[j]];
                 if (!uniform) prior_s[j] = pj;
                 llr[r] = pj;
 #pragma unroll
@@ -460,20 +519,27 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             }
             __syncthreads();
         }
-        const long long base = shot * (long long)n;
+        // stage the results by bit index in the (now idle) message array, then write them out coalesced
 #pragma unroll
         for (int r = 0; r < VPT; r++) {
             const int j = tid + r * T;
             if (j < n) {
-                const uint8_t d = (llr[r] <= 0) ? 1 : 0;
-                if (a.bp) a.bp[base + j] = d;
-                if (final_here) {
-                    if (a.osd0) a.osd0[base + j] = d;
-                    if (a.osdw) a.osdw[base + j] = d;
-                }
-                if (a.llr) a.llr[base + j] = llr[r];
-                else if (!final_here) a.fail_llr[(long long)sh_slot * n + j] = llr[r];
+                const int b = bit_of_tab[j];
+                st_llr[b] = llr[r];
+                st_dec[b] = (llr[r] <= 0) ? 1 : 0;
             }
+        }
+        __syncthreads();
+        const long long base = shot * (long long)n;
+        for (int j = tid; j < n; j += T) {
+            const uint8_t d = st_dec[j];
+            if (a.bp) a.bp[base + j] = d;
+            if (final_here) {
+                if (a.osd0) a.osd0[base + j] = d;
+                if (a.osdw) a.osdw[base + j] = d;
+            }
+            if (a.llr) a.llr[base + j] = st_llr[j];
+            else if (!final_here) a.fail_llr[(long long)sh_slot * n + j] = st_llr[j];
         }
         if (tid == 0) {
             if (a.converge) a.converge[shot] = conv ? 1 : 0;
@@ -523,7 +589,7 @@ static inline cudaError_t fast_occupancy_t(const FastTables &t, int n, int threa
 }
 template <typename real>
 static inline void fast_launch(const FastTables &t, const BpArgs<real> &a, int grid, int threads, int smem, cudaStream_t st) {
-    BPOSD_FAST_DISPATCH(t, a.g.n, (bp_fast_kernel<real, DC, DV, VPT, MAXT, REG><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg, t.d_row_of)));
+    BPOSD_FAST_DISPATCH(t, a.g.n, (bp_fast_kernel<real, DC, DV, VPT, MAXT, REG><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg, t.d_row_of, t.d_bit_of)));
 }
 
 } // namespace bposd

@@ -47,6 +47,14 @@ struct bposd_handle {
     int bp_kernel = 1, bp_threads = 256, bp_ctas_per_sm = 1, bp_smem = 0, bp_grid = 0;
     int osd_threads = 256, osd_smem = 0, osd_ctas_per_sm = 1, osd_S = 0, osd_St = 0;
     bool osd_supported = true;
+    // large-H OSD-0 (T does not fit in shared memory): HBM workspace, one CTA per failed shot
+    bool osd_large = false;
+    int osd_variant = 0; // 0 auto, 1 shared-memory kernel, 2 HBM-resident kernel
+    int osdl_smem = 0, osdl_grid = 0, osdl_npanels = 0;
+    long long osdl_ws_cap = 16ll << 30;
+    uint32_t *d_osdl_mask = nullptr;
+    int *d_osdl_order = nullptr, *d_osdl_piv_row = nullptr, *d_osdl_piv_pos = nullptr, *d_osdl_pstart = nullptr;
+    int osdl_alloc_grid = 0;
     int force_kernel = 0, force_threads = 0;
     bool geometry_ready = false;
     // harness
@@ -203,7 +211,20 @@ static int plan_geometry_t(bposd_handle *h) {
     const size_t osd_smem = (size_t)n * 8 + 256 + ((size_t)m * h->osd_St + 3 * (size_t)h->osd_S + (size_t)nw * (h->osd_S + 64)) * 4 + 128 + 3 * (size_t)n * 2 + 16;
     h->osd_smem = (int)osd_smem;
     h->osd_supported = osd_smem <= (size_t)h->smem_optin && n < 65535 && m < 65535;
-    if (h->osd_supported) {
+    // HBM-resident OSD-0: used when T does not fit (or when forced), only for search depth 0
+    h->osdl_npanels = (n + 31) / 32;
+    h->osdl_smem = (int)(4 * (size_t)m + 4096 + 256 + 2 * ((size_t)m + 2) + (size_t)m + 16);
+    const bool large_ok = h->osd_order == 0 && (size_t)h->osdl_smem <= (size_t)h->smem_optin && m < 65535;
+    h->osd_large = large_ok && (h->osd_variant == 2 || (h->osd_variant == 0 && !h->osd_supported));
+    if (h->osd_variant == 2 && !large_ok)
+        return fail(h, BPOSD_EUNSUP, "the HBM-resident OSD kernel handles OSD-0 (osd_order 0) with m < 65535 only");
+    if (h->osd_large) {
+        CU_TRY(h, cudaFuncSetAttribute(osd0_large_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->osdl_smem));
+        const size_t per_cta = (size_t)h->osdl_npanels * m * 4 + (size_t)n * 4 + 2 * (size_t)std::min(m, n) * 4 + ((size_t)h->osdl_npanels + 1) * 4;
+        h->osdl_grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, h->osdl_ws_cap / (long long)std::max<size_t>(per_cta, 1)));
+        h->osd_supported = true;
+    }
+    if (h->osd_supported && !h->osd_large) {
         CU_TRY(h, cudaFuncSetAttribute(osd_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osd_smem));
         int occ2 = 0;
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, osd_kernel<real>, h->osd_threads, osd_smem));
@@ -232,6 +253,7 @@ extern "C" void bposd_destroy(bposd_t *h) {
     fast_free(h->fast);
     cudaFree(h->d_ctrl); cudaFree(h->d_fail_list); cudaFree(h->d_fail_llr);
     cudaFree(h->d_scratch); cudaFree(h->d_scratch_dec);
+    cudaFree(h->d_osdl_mask); cudaFree(h->d_osdl_order); cudaFree(h->d_osdl_piv_row); cudaFree(h->d_osdl_piv_pos); cudaFree(h->d_osdl_pstart);
     cudaFree(h->d_t1); cudaFree(h->d_t2); cudaFree(h->d_t3); cudaFree(h->d_l_ptr); cudaFree(h->d_l_idx);
     cudaFree(h->b_synd); cudaFree(h->b_err); cudaFree(h->b_osdw); cudaFree(h->b_osd0); cudaFree(h->b_bp);
     cudaFree(h->b_conv); cudaFree(h->b_llr); cudaFree(h->b_iter); cudaFree(h->d_counters); cudaFree(h->d_minw);
@@ -348,6 +370,18 @@ extern "C" int bposd_set_tuning(bposd_t *h, int32_t kernel_plus1, int32_t thread
     return plan_geometry(h);
 }
 
+extern "C" int bposd_set_osd_variant(bposd_t *h, int32_t variant, int64_t workspace_bytes) {
+    if (!h) return BPOSD_EINVAL;
+    if (variant < 0 || variant > 2) return fail(h, BPOSD_EINVAL, "osd variant must be 0 (auto), 1 (shared memory) or 2 (HBM resident)");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int old = h->osd_variant;
+    h->osd_variant = variant;
+    if (workspace_bytes > 0) h->osdl_ws_cap = workspace_bytes;
+    int rc = plan_geometry(h);
+    if (rc != BPOSD_OK) { h->osd_variant = old; std::string keep = h->err; plan_geometry(h); h->err = keep; }
+    return rc;
+}
+
 extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
     if (!h || !info) return BPOSD_EINVAL;
     info->m = h->m; info->n = h->n; info->nnz = h->nnz; info->rank = h->rank; info->k = h->k;
@@ -356,6 +390,8 @@ extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
     info->bp_kernel = h->bp_kernel; info->bp_threads = h->bp_threads; info->bp_ctas_per_sm = h->bp_ctas_per_sm;
     info->bp_smem_bytes = h->bp_smem; info->osd_threads = h->osd_threads; info->osd_smem_bytes = h->osd_smem;
     info->sm_count = h->sm_count; info->ms_scaling_factor = h->alpha;
+    info->osd_variant = !h->osd_supported ? 0 : (h->osd_large ? 2 : 1);
+    info->bp_layout_excess = (int32_t)h->fast.conflicts_after;
     return BPOSD_OK;
 }
 
@@ -431,7 +467,37 @@ static int decode_batch_t(bposd_handle *h, const uint8_t *d_synd, long long B, c
         CU_TRY(h, cudaGetLastError());
         launches++;
         CU_TRY(h, cudaEventRecord(h->ev[1], st));
-        if (osd_on) {
+        if (osd_on && h->osd_large) {
+            const int ogrid = (int)std::min<long long>(Bc, h->osdl_grid);
+            if (h->osdl_alloc_grid < ogrid) {
+                cudaFree(h->d_osdl_mask); cudaFree(h->d_osdl_order); cudaFree(h->d_osdl_piv_row); cudaFree(h->d_osdl_piv_pos); cudaFree(h->d_osdl_pstart);
+                h->d_osdl_mask = nullptr; h->d_osdl_order = h->d_osdl_piv_row = h->d_osdl_piv_pos = h->d_osdl_pstart = nullptr;
+                h->osdl_alloc_grid = 0;
+                const size_t gsz = (size_t)ogrid, mn = (size_t)std::min(m, n);
+                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_mask, gsz * h->osdl_npanels * m * 4));
+                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_order, gsz * n * 4));
+                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_row, gsz * std::max<size_t>(mn, 1) * 4));
+                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_pos, gsz * std::max<size_t>(mn, 1) * 4));
+                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_pstart, gsz * ((size_t)h->osdl_npanels + 1) * 4));
+                h->osdl_alloc_grid = ogrid;
+            }
+            OsdLargeArgs<real> o;
+            o.g = a.g;
+            o.synd = a.synd;
+            o.llr = llr_out ? a.llr : static_cast<const real *>(h->d_fail_llr);
+            o.llr_by_shot = llr_out ? 1 : 0;
+            o.fail_count = h->d_fail_count;
+            o.fail_list = h->d_fail_list;
+            o.osd0 = a.osd0; o.osdw = a.osdw;
+            o.stat = h->d_ctrl + 1;
+            o.maxrank = h->rank;
+            o.npanels = h->osdl_npanels;
+            o.ws_mask = h->d_osdl_mask; o.ws_order = h->d_osdl_order;
+            o.ws_piv_row = h->d_osdl_piv_row; o.ws_piv_pos = h->d_osdl_piv_pos; o.ws_pstart = h->d_osdl_pstart;
+            osd0_large_kernel<real><<<ogrid, 1024, h->osdl_smem, st>>>(o);
+            CU_TRY(h, cudaGetLastError());
+            launches++;
+        } else if (osd_on) {
             OsdArgs<real> o;
             o.g = a.g;
             o.S = h->osd_S; o.St = h->osd_St;

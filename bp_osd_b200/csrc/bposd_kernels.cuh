@@ -532,6 +532,216 @@ __global__ void __launch_bounds__(1024) osd_kernel(OsdArgs<real> a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Large-H OSD-0 (rows a9-a11 when the m x m row-operation matrix does not fit in shared memory,
+// BASELINE config 5: m = 19 200, n = 40 000).  One CTA per failed shot, left-looking panel
+// Gauss-Jordan over GF(2):
+//   * the sorted columns are consumed in panels of 32; the panel's bits, one 32-bit word per
+//     check, are built in shared memory straight from the sparse H (the dense permuted matrix is
+//     never materialised);
+//   * before a panel is factorised, every earlier panel's row operations are replayed on it.  The
+//     operations of panel q are stored in HBM as one 32-bit multiplier mask per check (bit k: "add
+//     pivot row k of panel q to this check"), streamed back coalesced; the <= 32 pivot-row words
+//     are resolved sequentially by one warp (shuffles), folded into four 256-entry XOR tables
+//     (method of four Russians) and applied to all checks with four shared-memory look-ups each;
+//   * factorising the panel scans its 32 columns in order: a column is a pivot iff an unused check
+//     has a 1 in it (lowest such check is taken; the OSD-0 result does not depend on that choice,
+//     row a10); the pivot word is added to every other check that has the bit (Jordan form, so the
+//     transformed syndrome is the solution and no back-substitution is needed);
+//   * the scan stops as soon as rank(H) pivots are found, so columns to the right of the last
+//     pivot are never touched.
+// Work per shot ~ (panels^2 / 2) * m mask words streamed from HBM/L2; memory per CTA
+// panels * m * 4 bytes (96 MB for config 5).
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+struct OsdLargeArgs {
+    GraphDev g;
+    const uint8_t *synd;
+    const real *llr;
+    int llr_by_shot;
+    const int *fail_count;
+    const int *fail_list;
+    uint8_t *osd0, *osdw;
+    unsigned long long *stat;
+    int maxrank;       // rank(H): stop once this many pivots are found
+    int npanels;       // ceil(n / 32)
+    uint32_t *ws_mask; // [grid][npanels][m]
+    int *ws_order;     // [grid][n]
+    int *ws_piv_row;   // [grid][min(m,n)]
+    int *ws_piv_pos;   // [grid][min(m,n)]
+    int *ws_pstart;    // [grid][npanels + 1]
+};
+
+#define OSDL_UNUSED 0xFFFFu
+
+template <typename real>
+__global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GraphDev &g = a.g;
+    const int m = g.m, n = g.n;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    uint32_t *P = reinterpret_cast<uint32_t *>(smem_raw);                  // [m] panel word of every check
+    uint32_t *tab = P + m;                                                 // [4][256] XOR tables
+    uint32_t *Rk = tab + 1024;                                             // [32] resolved pivot-row words
+    int *red = reinterpret_cast<int *>(Rk + 32);                           // [32] block-reduce scratch
+    uint16_t *rowpanel = reinterpret_cast<uint16_t *>(red + 32);           // [m] panel in which the check became a pivot
+    uint8_t *s8 = reinterpret_cast<uint8_t *>(rowpanel + ((m + 1) & ~1));  // [m] transformed syndrome
+    __shared__ int sh_p, sh_rank, sh_cnt;
+
+    uint32_t *maskbase = a.ws_mask + (size_t)blockIdx.x * a.npanels * m;
+    int *order = a.ws_order + (size_t)blockIdx.x * n;
+    const int minmn = m < n ? m : n;
+    int *piv_row = a.ws_piv_row + (size_t)blockIdx.x * minmn;
+    int *piv_pos = a.ws_piv_pos + (size_t)blockIdx.x * minmn;
+    int *pstart = a.ws_pstart + (size_t)blockIdx.x * (a.npanels + 1);
+
+    const int nfail = *a.fail_count;
+    for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
+        const long long shot = a.fail_list[f];
+        const real *llr = a.llr + (a.llr_by_shot ? shot : (long long)f) * n;
+        const uint8_t *synd = a.synd + shot * m;
+        __syncthreads();
+
+        // ---- a9: stable ascending rank sort on (llr, index); keys streamed from global (broadcast loads)
+        for (int j0 = tid; j0 < n; j0 += 8 * T) {
+            unsigned long long kj[8];
+            int rk[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int j = j0 + u * T;
+                kj[u] = (j < n) ? sort_key(llr[j]) : 0ull;
+                rk[u] = 0;
+            }
+            for (int i = 0; i < n; i++) {
+                const unsigned long long ki = sort_key(llr[i]);
+#pragma unroll
+                for (int u = 0; u < 8; u++) rk[u] += (ki < kj[u] || (ki == kj[u] && i < j0 + u * T)) ? 1 : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (j0 + u * T < n) order[rk[u]] = j0 + u * T;
+        }
+        for (int i = tid; i < m; i += T) { rowpanel[i] = OSDL_UNUSED; s8[i] = synd[i] & 1; }
+        if (tid == 0) { sh_rank = 0; pstart[0] = 0; }
+        __syncthreads();
+
+        // ---- a10: elimination, one panel of 32 sorted columns at a time
+        int npan_done = 0;
+        for (int w = 0; w < a.npanels; w++) {
+            if (sh_rank >= a.maxrank) break;
+            uint32_t *Mw = maskbase + (size_t)w * m;
+            for (int i = tid; i < m; i += T) { P[i] = 0; Mw[i] = 0; }
+            __syncthreads();
+            if (tid < 32) {
+                const int t = w * 32 + tid;
+                if (t < n) {
+                    const int j = order[t];
+                    for (int q = g.col_ptr[j]; q < g.col_ptr[j + 1]; q++) atomicOr(&P[g.row_idx[q]], 1u << tid);
+                }
+            }
+            __syncthreads();
+            // replay the row operations of every earlier panel, in order
+            for (int q = 0; q < w; q++) {
+                const int ps = pstart[q], cnt = pstart[q + 1] - ps;
+                if (cnt == 0) continue;
+                const uint32_t *Mq = maskbase + (size_t)q * m;
+                if (warp == 0) {
+                    int pr = 0;
+                    uint32_t cur = 0, mj = 0, R = 0;
+                    if (lane < cnt) { pr = piv_row[ps + lane]; cur = P[pr]; mj = Mq[pr]; }
+                    for (int k = 0; k < cnt; k++) {
+                        const uint32_t rk = __shfl_sync(0xffffffffu, cur, k);
+                        if (lane == k) R = cur;
+                        else if ((mj >> k) & 1u) cur ^= rk;
+                    }
+                    Rk[lane] = (lane < cnt) ? R : 0u;
+                    __syncwarp();
+                    // the parallel step below skips pivot rows of panel q, so their final words go in now
+                    if (lane < cnt) P[pr] = cur;
+                }
+                __syncthreads();
+                {
+                    const int grp = tid >> 8, idx = tid & 255;
+                    if (tid < 1024) {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int b = 0; b < 8; b++) v ^= ((idx >> b) & 1) ? Rk[grp * 8 + b] : 0u;
+                        tab[grp * 256 + idx] = v;
+                    }
+                    if (T < 1024)
+                        for (int e = tid + T; e < 1024; e += T) {
+                            uint32_t v = 0;
+                            for (int b = 0; b < 8; b++) v ^= (((e & 255) >> b) & 1) ? Rk[(e >> 8) * 8 + b] : 0u;
+                            tab[e] = v;
+                        }
+                }
+                __syncthreads();
+                for (int i = tid; i < m; i += T) {
+                    const uint32_t mi = Mq[i];
+                    if (mi && rowpanel[i] != (uint16_t)q)
+                        P[i] ^= tab[mi & 255u] ^ tab[256 + ((mi >> 8) & 255u)] ^ tab[512 + ((mi >> 16) & 255u)] ^ tab[768 + (mi >> 24)];
+                }
+                __syncthreads();
+            }
+            // factorise this panel
+            if (tid == 0) sh_cnt = 0;
+            __syncthreads();
+            for (int c = 0; c < 32; c++) {
+                const int t = w * 32 + c;
+                if (t >= n || sh_rank >= a.maxrank) break;
+                int best = 0x7fffffff;
+                for (int i = tid; i < m; i += T)
+                    if (((P[i] >> c) & 1u) && rowpanel[i] == OSDL_UNUSED) { best = i; break; }
+                for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                if (lane == 0) red[warp] = best;
+                __syncthreads();
+                if (warp == 0) {
+                    int b = (lane < nwarps) ? red[lane] : 0x7fffffff;
+                    for (int o = 16; o > 0; o >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+                    if (lane == 0) sh_p = b;
+                }
+                __syncthreads();
+                const int p = sh_p;
+                if (p == 0x7fffffff) continue; // dependent column: not a pivot (uniform branch)
+                const uint32_t Pp = P[p];
+                const uint8_t sp = s8[p];
+                const int k = sh_cnt;
+                __syncthreads(); // everyone has read sh_p / sh_cnt / P[p] before they change
+                for (int i = tid; i < m; i += T)
+                    if (i != p && ((P[i] >> c) & 1u)) { P[i] ^= Pp; s8[i] ^= sp; Mw[i] |= 1u << k; }
+                if (tid == 0) {
+                    const int r = sh_rank;
+                    piv_row[r] = p; piv_pos[r] = t; rowpanel[p] = (uint16_t)w;
+                    sh_rank = r + 1; sh_cnt = k + 1;
+                }
+                __syncthreads();
+            }
+            if (tid == 0) pstart[w + 1] = sh_rank;
+            npan_done = w + 1;
+            __syncthreads();
+        }
+        (void)npan_done;
+
+        // ---- a11: OSD-0 read-out.  Jordan form: x[pivot column of check p] = transformed syndrome bit of p
+        const long long base = shot * (long long)n;
+        for (int j = tid; j < n; j += T) {
+            if (a.osd0) a.osd0[base + j] = 0;
+            if (a.osdw) a.osdw[base + j] = 0;
+        }
+        __syncthreads();
+        const int rank = sh_rank;
+        for (int r = tid; r < rank; r += T) {
+            const uint8_t x = s8[piv_row[r]];
+            if (x) {
+                const int j = order[piv_pos[r]];
+                if (a.osd0) a.osd0[base + j] = 1;
+                if (a.osdw) a.osdw[base + j] = 1;
+            }
+        }
+        if (tid == 0 && a.stat) atomicAdd(&a.stat[2], 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Harness step kernels (rows a17-a19)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {

@@ -174,6 +174,11 @@ class BpOsdDecoder:
         sel = 0 if bp_kernel is None else int(bp_kernel) + 1
         self._check(_capi.load().bposd_set_tuning(self._h, sel, int(bp_threads), int(workspace_bytes)))
 
+    def set_osd_variant(self, variant=None, workspace_bytes=0):
+        """variant: None (auto), 1 shared-memory OSD kernel, 2 HBM-resident OSD-0 kernel (large H)."""
+        self._check(_capi.load().bposd_set_osd_variant(self._h, 0 if variant is None else int(variant),
+                                                       int(workspace_bytes)))
+
     @property
     def channel_probs(self):
         return self._probs.copy()

@@ -64,6 +64,8 @@ typedef struct {
     int32_t bp_kernel;              /* 0 generic/global, 1 generic/smem, 2 in-place smem  */
     int32_t bp_threads, bp_ctas_per_sm, bp_smem_bytes;
     int32_t osd_threads, osd_smem_bytes, sm_count;
+    int32_t osd_variant;            /* 1 shared-memory OSD kernel, 2 HBM-resident OSD-0 kernel, 0 OSD unsupported */
+    int32_t bp_layout_excess;       /* shared-memory wavefronts per bit sweep above the conflict-free count (kernel 2) */
     double ms_scaling_factor;
 } bposd_info_t;
 
@@ -142,6 +144,11 @@ int bposd_get_stats(const bposd_t *h, bposd_stats_t *stats);
 /* Tuning knobs (0 = keep automatic): BP kernel variant (+1 of bposd_info_t.bp_kernel),
  * threads per CTA, workspace bytes for the failed-shot LLR buffer. */
 int bposd_set_tuning(bposd_t *h, int32_t bp_kernel_plus1, int32_t bp_threads, int64_t workspace_bytes);
+/* OSD kernel variant: 0 automatic, 1 shared-memory kernel (row-operation matrix in shared memory,
+ * OSD-0/E/CS), 2 HBM-resident left-looking kernel (OSD-0 only; chosen automatically when the matrix
+ * does not fit in shared memory, BASELINE config 5).  workspace_bytes > 0 caps the HBM workspace
+ * of variant 2 (ceil(n/32) * m * 4 bytes per concurrently processed failed shot). */
+int bposd_set_osd_variant(bposd_t *h, int32_t variant, int64_t workspace_bytes);
 const char *bposd_last_error(const bposd_t *h);
 const char *bposd_version(void);
 void bposd_destroy(bposd_t *h);

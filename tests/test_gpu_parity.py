@@ -341,3 +341,89 @@ def test_fp32_fast_mode_is_statistically_equivalent(torch_cuda, oracle_mod, cfg_
     mismatch = (out != ref["osdw"]).any(1).mean()
     print(f"fp32: LER {ler:.4f} vs fp64 {ler_ref:.4f} +- {ci:.4f}; decoding mismatch rate {mismatch:.3f}")
     assert abs(ler - ler_ref) <= ci + 2.0 / B
+
+
+# ------------------------------------------------------------------------------------------------
+# Large-H path (BASELINE config 5): HBM-resident OSD-0 kernel, BP with messages outside shared memory
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,p,max_iter", [(1, 0.12, 2), (2, 0.08, 4)])
+def test_hbm_osd0_kernel_matches_shared_memory_kernel_and_oracle(torch_cuda, oracle_mod, cfg_codes, cfg, p, max_iter):
+    """Variant 2 (left-looking panel elimination in HBM) forced on codes that also fit variant 1."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(cfg).hz
+    kw = dict(max_iter=max_iter, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)
+    _, syn = random_syndromes(H, p, 400, seed=21)
+    ref = oracle_mod.OracleDecoder(H, error_rate=p, **kw).decode_batch(syn)
+    assert (~ref["converge"].astype(bool)).sum() > 50
+    d = BpOsdDecoder(H, error_rate=p, **kw)
+    d.set_osd_variant(2)
+    assert d.info()["osd_variant"] == 2
+    r = d.decode_batch(torch.tensor(syn, device="cuda"))
+    assert (r.osd0_decoding.cpu().numpy() == ref["osd0"]).all()
+    assert (r.osdw_decoding.cpu().numpy() == ref["osdw"]).all()
+    assert (r.bp_decoding.cpu().numpy() == ref["bp"]).all()
+    # the HBM kernel does OSD-0 only
+    d2 = BpOsdDecoder(H, error_rate=p, **dict(kw, osd_method="osd_cs", osd_order=3))
+    with pytest.raises(NotImplementedError):
+        d2.set_osd_variant(2)
+    assert d2.info()["osd_variant"] == 1
+
+
+def test_large_h_standin_selects_hbm_osd(torch_cuda, oracle_mod):
+    """[[3600,144]] HGP of a (3,4)-regular 36x48 seed: T = 1728 x 1728 bits (373 KB) exceeds shared memory,
+    so the HBM-resident kernel is chosen automatically; rank-deficient H (redundant checks) included."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    code = hgp(codes.regular_ldpc(36, 48, 3, 4, seed=11), compute_logicals=False)
+    H = code.hz
+    m, n = H.shape
+    assert (m, n) == (1728, 3600)
+    kw = dict(max_iter=6, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)
+    _, syn = random_syndromes(H, 0.06, 64, seed=4)
+    ref = oracle_mod.OracleDecoder(H, error_rate=0.06, **kw).decode_batch(syn)
+    nfail = int((~ref["converge"].astype(bool)).sum())
+    assert nfail >= 8
+    for kernel in (None, 0):   # auto (shared-memory BP) and the HBM/L2-scratch BP used by config 5
+        d = BpOsdDecoder(H, error_rate=0.06, **kw)
+        if kernel is not None:
+            d.set_tuning(bp_kernel=kernel)
+        assert d.info()["osd_variant"] == 2
+        r = d.decode_batch(torch.tensor(syn, device="cuda"))
+        out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
+                   llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
+        assert_exact(out, ref)
+        assert d.stats()["osd_invocations"] == nfail
+    with pytest.raises(NotImplementedError):
+        BpOsdDecoder(H, error_rate=0.06, **dict(kw, osd_method="osd_cs", osd_order=2)).decode_batch(
+            torch.tensor(syn, device="cuda"))
+
+
+def test_config5_full_size(torch_cuda, oracle_mod, cfg_codes):
+    """BASELINE config 5 at full size (m=19200, n=40000): BP from the HBM/L2 scratch + HBM-resident OSD-0.
+    Oracle parity on a handful of shots (its dense elimination needs ~10 s per failed shot) and the
+    size-independent property H x = s for every decoded shot."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(5).hz
+    m, n = H.shape
+    kw = dict(max_iter=12, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)
+    p = 0.03
+    _, syn = random_syndromes(H, p, 24, seed=8)
+    d = BpOsdDecoder(H, error_rate=p, **kw)
+    info = d.info()
+    assert info["bp_kernel"] == 0 and info["osd_variant"] == 2
+    r = d.decode_batch(torch.tensor(syn, device="cuda"))
+    osd0 = r.osd0_decoding.cpu().numpy()
+    conv = r.converge.cpu().numpy()
+    assert (~conv).sum() >= 2, "the case is meant to exercise OSD"
+    resid = (np.asarray(H @ osd0.T) % 2).T
+    assert (resid == syn).all(), "H x != s"
+    o = oracle_mod.OracleDecoder(H, error_rate=p, **kw)
+    pick = list(np.flatnonzero(~conv)[:2]) + list(np.flatnonzero(conv)[:2])
+    for b in pick:
+        o.decode(syn[b])
+        assert bool(conv[b]) == bool(o.converge) and int(r.iter[b]) == o.iter
+        assert (r.bp_decoding[b].cpu().numpy() == o.bp_decoding).all()
+        assert (r.log_prob_ratios[b].cpu().numpy() == o.log_prob_ratios).all()
+        assert (osd0[b] == o.osd0_decoding).all()
