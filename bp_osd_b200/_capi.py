@@ -22,6 +22,10 @@ class Out(C.Structure):
     _fields_ = [("d_osdw", P), ("d_osd0", P), ("d_bp", P), ("d_llr", P), ("d_converge", P), ("d_iter", P)]
 
 
+class CssSector(C.Structure):
+    _fields_ = [("d_fail_x", P), ("d_fail_z", P), ("d_weight_x", P), ("d_weight_z", P)]
+
+
 class Info(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "m", "n", "nnz", "rank", "k", "max_iter", "bp_method", "osd_method", "osd_order", "precision",
@@ -40,12 +44,14 @@ SIGNATURES = {
     "bposd_create": (C.c_int, [P, P, C.c_int32, C.c_int32, P, C.c_int32, C.c_int32, C.c_double, C.c_int32,
                                C.c_int32, C.c_int32, C.c_int32, C.POINTER(P)]),
     "bposd_update_channel_probs": (C.c_int, [P, P]),
-    "bposd_decode_batch": (C.c_int, [P, P, C.c_int64, C.POINTER(Out), P, P]),
+    "bposd_decode_batch": (C.c_int, [P, P, C.c_int64, C.POINTER(Out), P, P, P]),
     "bposd_decode_host": (C.c_int, [P, P, C.c_int64, P, P, P, P, P, P]),
     "bposd_set_channel_thresholds": (C.c_int, [P, P, P, P]),
     "bposd_sample_syndromes": (C.c_int, [P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, P, P, P]),
     "bposd_set_logicals": (C.c_int, [P, P, P, C.c_int32]),
-    "bposd_logical_check": (C.c_int, [P, P, P, C.c_int64, P, P, P, P]),
+    "bposd_logical_check": (C.c_int, [P, P, P, C.c_int64, P, P, P, P, P]),
+    "bposd_channel_update": (C.c_int, [P, P, C.c_int64, P, P, P, P, P]),
+    "bposd_css_counters": (C.c_int, [P, C.c_int64, P, P, P, P, P, P, P]),
     "bposd_sample_and_decode": (C.c_int, [P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, P, P]),
     "bposd_get_info": (C.c_int, [P, C.POINTER(Info)]),
     "bposd_get_stats": (C.c_int, [P, C.POINTER(Stats)]),

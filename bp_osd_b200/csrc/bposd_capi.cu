@@ -33,13 +33,28 @@ struct bposd_handle {
     int uniform = 0, uniform_prior = 0;
     // fast-kernel tables
     FastTables fast;
-    // control words: [0] queue, [1] converged, [2] iterations, [3] osd invocations, then int fail_count
-    unsigned long long *d_ctrl = nullptr;
-    int *d_fail_count = nullptr;
-    int *d_fail_list = nullptr;
-    void *d_fail_llr = nullptr;
+    // Two decode slots: each owns its control words, failed-shot workspace, staging buffers, events and
+    // (for the host-buffer pipeline) a stream, so chunk i+1 can be copied in while chunk i decodes.
+    struct Slot {
+        // control words: [0] queue, [1] converged, [2] iterations, [3] osd invocations, [4] (int) fail_count
+        unsigned long long *d_ctrl = nullptr;
+        unsigned long long *h_ctrl = nullptr; // pinned copy of words 0..3
+        int *d_fail_list = nullptr;
+        void *d_fail_llr = nullptr;
+        long long fail_list_cap = 0, fail_llr_cap = 0;
+        uint8_t *b_synd = nullptr, *b_err = nullptr, *b_osdw = nullptr, *b_osd0 = nullptr, *b_bp = nullptr, *b_conv = nullptr;
+        void *b_llr = nullptr;
+        int32_t *b_iter = nullptr;
+        long long b_cap = 0;
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // BP start, BP end, OSD end, everything enqueued for the chunk
+        cudaStream_t stream = nullptr;
+        bool pending = false;
+        long long pending_shots = 0;
+        int pending_launches = 0;
+    } slot[2];
     long long fail_cap = 0; // shots per chunk the failed-shot workspace can hold
     long long workspace_bytes = 2ll << 30;
+    long long host_chunk_min = 16384, host_chunk_max = 131072; // shots per chunk of the host-buffer pipeline
     void *d_scratch = nullptr; // global-mode BP scratch
     uint8_t *d_scratch_dec = nullptr;
     size_t scratch_bytes = 0;
@@ -62,13 +77,9 @@ struct bposd_handle {
     int *d_l_ptr = nullptr, *d_l_idx = nullptr;
     int K = 0;
     // internal buffers for decode_host / sample_and_decode
-    uint8_t *b_synd = nullptr, *b_err = nullptr, *b_osdw = nullptr, *b_osd0 = nullptr, *b_bp = nullptr, *b_conv = nullptr;
-    void *b_llr = nullptr;
-    int32_t *b_iter = nullptr;
-    long long b_cap = 0, fail_list_cap = 0, fail_llr_cap = 0;
     unsigned long long *d_counters = nullptr; // 8 words
     int *d_minw = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    double *d_cu_tab = nullptr; // channel-update tables [4, n]
     bposd_stats_t stats{};
     std::string err;
 };
@@ -251,13 +262,18 @@ extern "C" void bposd_destroy(bposd_t *h) {
     cudaFree(h->d_row_ptr); cudaFree(h->d_col_idx); cudaFree(h->d_col_ptr); cudaFree(h->d_row_idx); cudaFree(h->d_csc_slot);
     cudaFree(h->d_prior64); cudaFree(h->d_prior32); cudaFree(h->d_weight);
     fast_free(h->fast);
-    cudaFree(h->d_ctrl); cudaFree(h->d_fail_list); cudaFree(h->d_fail_llr);
+    for (auto &sl : h->slot) {
+        cudaFree(sl.d_ctrl); cudaFree(sl.d_fail_list); cudaFree(sl.d_fail_llr);
+        if (sl.h_ctrl) cudaFreeHost(sl.h_ctrl);
+        cudaFree(sl.b_synd); cudaFree(sl.b_err); cudaFree(sl.b_osdw); cudaFree(sl.b_osd0); cudaFree(sl.b_bp);
+        cudaFree(sl.b_conv); cudaFree(sl.b_llr); cudaFree(sl.b_iter);
+        for (auto &e : sl.ev) if (e) cudaEventDestroy(e);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     cudaFree(h->d_scratch); cudaFree(h->d_scratch_dec);
     cudaFree(h->d_osdl_mask); cudaFree(h->d_osdl_order); cudaFree(h->d_osdl_piv_row); cudaFree(h->d_osdl_piv_pos); cudaFree(h->d_osdl_pstart);
     cudaFree(h->d_t1); cudaFree(h->d_t2); cudaFree(h->d_t3); cudaFree(h->d_l_ptr); cudaFree(h->d_l_idx);
-    cudaFree(h->b_synd); cudaFree(h->b_err); cudaFree(h->b_osdw); cudaFree(h->b_osd0); cudaFree(h->b_bp);
-    cudaFree(h->b_conv); cudaFree(h->b_llr); cudaFree(h->b_iter); cudaFree(h->d_counters); cudaFree(h->d_minw);
-    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    cudaFree(h->d_counters); cudaFree(h->d_minw); cudaFree(h->d_cu_tab);
     delete h;
 }
 
@@ -335,12 +351,15 @@ extern "C" int bposd_create(const int32_t *indptr, const int32_t *indices, int32
     CR_TRY(cudaMalloc((void **)&h->d_prior32, n * sizeof(float)));
     CR_TRY(cudaMalloc((void **)&h->d_weight, n * sizeof(double)));
     if (upload_probs(h) != BPOSD_OK) return die(BPOSD_ECUDA);
-    CR_TRY(cudaMalloc((void **)&h->d_ctrl, 8 * sizeof(unsigned long long)));
-    CR_TRY(cudaMemset(h->d_ctrl, 0, 8 * sizeof(unsigned long long)));
-    h->d_fail_count = reinterpret_cast<int *>(h->d_ctrl + 4);
+    for (auto &sl : h->slot) {
+        CR_TRY(cudaMalloc((void **)&sl.d_ctrl, 8 * sizeof(unsigned long long)));
+        CR_TRY(cudaMemset(sl.d_ctrl, 0, 8 * sizeof(unsigned long long)));
+        CR_TRY(cudaMallocHost((void **)&sl.h_ctrl, 8 * sizeof(unsigned long long)));
+        for (auto &e : sl.ev) CR_TRY(cudaEventCreate(&e));
+        CR_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    }
     CR_TRY(cudaMalloc((void **)&h->d_counters, 8 * sizeof(unsigned long long)));
     CR_TRY(cudaMalloc((void **)&h->d_minw, sizeof(int)));
-    for (auto &e : h->ev) CR_TRY(cudaEventCreate(&e));
     if (fast_supported(h->max_col_deg, h->max_row_deg, bp_method)) {
         cudaError_t e = fast_build(h->fast, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot, precision / 8);
         if (e != cudaSuccess) { h->err = std::string("fast_build: ") + cudaGetErrorString(e); return die(BPOSD_ECUDA); }
@@ -401,172 +420,253 @@ extern "C" int bposd_get_stats(const bposd_t *h, bposd_stats_t *stats) {
     return BPOSD_OK;
 }
 
+// Enqueue one chunk (BP -> OSD -> control-word read-back) on `st`.  No host synchronisation.
 template <typename real>
-static int decode_batch_t(bposd_handle *h, const uint8_t *d_synd, long long B, const bposd_out_t *out,
-                          const void *d_priors, cudaStream_t st) {
+static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st, const uint8_t *d_synd, long long Bc,
+                        const bposd_out_t &out, const void *d_priors, const double *d_weights) {
     const int n = h->n, m = h->m;
     const bool osd_on = h->osd_method != BPOSD_OSD_OFF;
-    if (osd_on && !h->osd_supported)
-        return fail(h, BPOSD_EUNSUP, "OSD for this matrix size needs more shared memory than an SM has; use osd_method off");
-    real *llr_out = static_cast<real *>(out->d_llr);
+    real *llr_out = static_cast<real *>(out.d_llr);
     const bool need_ws = osd_on && !llr_out;
-    long long chunk = B;
-    if (need_ws) {
-        chunk = std::min(B, h->fail_cap);
-        if (!h->d_fail_llr || chunk > h->fail_llr_cap) {
-            cudaFree(h->d_fail_llr);
-            h->d_fail_llr = nullptr;
-            CU_TRY(h, cudaMalloc(&h->d_fail_llr, (size_t)chunk * n * sizeof(real)));
-            h->fail_llr_cap = chunk;
+    if (need_ws && (!sl.d_fail_llr || Bc > sl.fail_llr_cap)) {
+        cudaFree(sl.d_fail_llr);
+        sl.d_fail_llr = nullptr; sl.fail_llr_cap = 0;
+        const long long cap = std::max(Bc, (long long)1024);
+        CU_TRY(h, cudaMalloc(&sl.d_fail_llr, (size_t)cap * n * sizeof(real)));
+        sl.fail_llr_cap = cap;
+    }
+    if (!sl.d_fail_list || Bc > sl.fail_list_cap) {
+        cudaFree(sl.d_fail_list);
+        sl.d_fail_list = nullptr; sl.fail_list_cap = 0;
+        CU_TRY(h, cudaMalloc((void **)&sl.d_fail_list, (size_t)Bc * sizeof(int)));
+        sl.fail_list_cap = Bc;
+    }
+    int *d_fail_count = reinterpret_cast<int *>(sl.d_ctrl + 4);
+    CU_TRY(h, cudaMemsetAsync(sl.d_ctrl, 0, 8 * sizeof(unsigned long long), st));
+    int launches = 0;
+    BpArgs<real> a;
+    a.g = graph_of(h);
+    a.max_iter = h->max_iter;
+    a.method = h->bp_method;
+    a.alpha0 = (real)h->alpha;
+    a.uniform_prior = d_priors ? 0 : h->uniform_prior;
+    if (d_priors) { a.prior = static_cast<const real *>(d_priors); a.prior_stride = n; }
+    else { a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32; a.prior_stride = 0; }
+    a.synd = d_synd;
+    a.B = Bc;
+    a.bp = out.d_bp; a.osd0 = out.d_osd0; a.osdw = out.d_osdw;
+    a.llr = llr_out;
+    a.converge = out.d_converge; a.iter = out.d_iter;
+    a.fail_count = d_fail_count;
+    a.fail_list = sl.d_fail_list;
+    a.fail_llr = static_cast<real *>(sl.d_fail_llr);
+    a.osd_off = osd_on ? 0 : 1;
+    a.queue = sl.d_ctrl;
+    a.stat = sl.d_ctrl + 1;
+    a.g_scratch = static_cast<real *>(h->d_scratch);
+    a.g_dec = h->d_scratch_dec;
+    const int grid = (int)std::min<long long>(Bc, h->bp_grid);
+    CU_TRY(h, cudaEventRecord(sl.ev[0], st));
+    if (h->bp_kernel == 2) fast_launch<real>(h->fast, a, grid, h->bp_threads, h->bp_smem, st);
+    else if (h->bp_kernel == 1) bp_generic_kernel<real, true><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
+    else bp_generic_kernel<real, false><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    launches++;
+    CU_TRY(h, cudaEventRecord(sl.ev[1], st));
+    if (osd_on && h->osd_large) {
+        const int ogrid = (int)std::min<long long>(Bc, h->osdl_grid);
+        if (h->osdl_alloc_grid < ogrid) {
+            cudaFree(h->d_osdl_mask); cudaFree(h->d_osdl_order); cudaFree(h->d_osdl_piv_row); cudaFree(h->d_osdl_piv_pos); cudaFree(h->d_osdl_pstart);
+            h->d_osdl_mask = nullptr; h->d_osdl_order = h->d_osdl_piv_row = h->d_osdl_piv_pos = h->d_osdl_pstart = nullptr;
+            h->osdl_alloc_grid = 0;
+            const size_t gsz = (size_t)ogrid, mn = (size_t)std::min(m, n);
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_mask, gsz * h->osdl_npanels * m * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_order, gsz * n * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_row, gsz * std::max<size_t>(mn, 1) * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_pos, gsz * std::max<size_t>(mn, 1) * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_pstart, gsz * ((size_t)h->osdl_npanels + 1) * 4));
+            h->osdl_alloc_grid = ogrid;
         }
-    }
-    chunk = std::min<long long>(chunk, 1ll << 30);
-    if (!h->d_fail_list || chunk > h->fail_list_cap) { // fail list holds one chunk
-        cudaFree(h->d_fail_list);
-        h->d_fail_list = nullptr;
-        CU_TRY(h, cudaMalloc((void **)&h->d_fail_list, (size_t)chunk * sizeof(int)));
-        h->fail_list_cap = chunk;
-    }
-    CU_TRY(h, cudaMemsetAsync(h->d_ctrl, 0, 8 * sizeof(unsigned long long), st));
-    h->stats = bposd_stats_t{};
-    float ms_bp = 0, ms_osd = 0;
-    int launches = 0, chunks = 0;
-    for (long long c0 = 0; c0 < B; c0 += chunk) {
-        const long long Bc = std::min(chunk, B - c0);
-        CU_TRY(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(unsigned long long), st));       // queue
-        CU_TRY(h, cudaMemsetAsync(h->d_fail_count, 0, sizeof(int), st));
-        BpArgs<real> a;
-        a.g = graph_of(h);
-        a.max_iter = h->max_iter;
-        a.method = h->bp_method;
-        a.alpha0 = (real)h->alpha;
-        a.uniform_prior = d_priors ? 0 : h->uniform_prior;
-        if (d_priors) { a.prior = static_cast<const real *>(d_priors) + c0 * n; a.prior_stride = n; }
-        else { a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32; a.prior_stride = 0; }
-        a.synd = d_synd + c0 * m;
-        a.B = Bc;
-        a.bp = out->d_bp ? out->d_bp + c0 * n : nullptr;
-        a.osd0 = out->d_osd0 ? out->d_osd0 + c0 * n : nullptr;
-        a.osdw = out->d_osdw ? out->d_osdw + c0 * n : nullptr;
-        a.llr = llr_out ? llr_out + c0 * n : nullptr;
-        a.converge = out->d_converge ? out->d_converge + c0 : nullptr;
-        a.iter = out->d_iter ? out->d_iter + c0 : nullptr;
-        a.fail_count = h->d_fail_count;
-        a.fail_list = h->d_fail_list;
-        a.fail_llr = static_cast<real *>(h->d_fail_llr);
-        a.osd_off = osd_on ? 0 : 1;
-        a.queue = h->d_ctrl;
-        a.stat = h->d_ctrl + 1;
-        a.g_scratch = static_cast<real *>(h->d_scratch);
-        a.g_dec = h->d_scratch_dec;
-        const int grid = (int)std::min<long long>(Bc, h->bp_grid);
-        CU_TRY(h, cudaEventRecord(h->ev[0], st));
-        if (h->bp_kernel == 2) fast_launch<real>(h->fast, a, grid, h->bp_threads, h->bp_smem, st);
-        else if (h->bp_kernel == 1) bp_generic_kernel<real, true><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
-        else bp_generic_kernel<real, false><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
+        OsdLargeArgs<real> o;
+        o.g = a.g;
+        o.synd = a.synd;
+        o.llr = llr_out ? llr_out : static_cast<const real *>(sl.d_fail_llr);
+        o.llr_by_shot = llr_out ? 1 : 0;
+        o.fail_count = d_fail_count;
+        o.fail_list = sl.d_fail_list;
+        o.osd0 = a.osd0; o.osdw = a.osdw;
+        o.stat = sl.d_ctrl + 1;
+        o.maxrank = h->rank;
+        o.npanels = h->osdl_npanels;
+        o.ws_mask = h->d_osdl_mask; o.ws_order = h->d_osdl_order;
+        o.ws_piv_row = h->d_osdl_piv_row; o.ws_piv_pos = h->d_osdl_piv_pos; o.ws_pstart = h->d_osdl_pstart;
+        osd0_large_kernel<real><<<ogrid, 1024, h->osdl_smem, st>>>(o);
         CU_TRY(h, cudaGetLastError());
         launches++;
-        CU_TRY(h, cudaEventRecord(h->ev[1], st));
-        if (osd_on && h->osd_large) {
-            const int ogrid = (int)std::min<long long>(Bc, h->osdl_grid);
-            if (h->osdl_alloc_grid < ogrid) {
-                cudaFree(h->d_osdl_mask); cudaFree(h->d_osdl_order); cudaFree(h->d_osdl_piv_row); cudaFree(h->d_osdl_piv_pos); cudaFree(h->d_osdl_pstart);
-                h->d_osdl_mask = nullptr; h->d_osdl_order = h->d_osdl_piv_row = h->d_osdl_piv_pos = h->d_osdl_pstart = nullptr;
-                h->osdl_alloc_grid = 0;
-                const size_t gsz = (size_t)ogrid, mn = (size_t)std::min(m, n);
-                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_mask, gsz * h->osdl_npanels * m * 4));
-                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_order, gsz * n * 4));
-                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_row, gsz * std::max<size_t>(mn, 1) * 4));
-                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_pos, gsz * std::max<size_t>(mn, 1) * 4));
-                CU_TRY(h, cudaMalloc((void **)&h->d_osdl_pstart, gsz * ((size_t)h->osdl_npanels + 1) * 4));
-                h->osdl_alloc_grid = ogrid;
-            }
-            OsdLargeArgs<real> o;
-            o.g = a.g;
-            o.synd = a.synd;
-            o.llr = llr_out ? a.llr : static_cast<const real *>(h->d_fail_llr);
-            o.llr_by_shot = llr_out ? 1 : 0;
-            o.fail_count = h->d_fail_count;
-            o.fail_list = h->d_fail_list;
-            o.osd0 = a.osd0; o.osdw = a.osdw;
-            o.stat = h->d_ctrl + 1;
-            o.maxrank = h->rank;
-            o.npanels = h->osdl_npanels;
-            o.ws_mask = h->d_osdl_mask; o.ws_order = h->d_osdl_order;
-            o.ws_piv_row = h->d_osdl_piv_row; o.ws_piv_pos = h->d_osdl_piv_pos; o.ws_pstart = h->d_osdl_pstart;
-            osd0_large_kernel<real><<<ogrid, 1024, h->osdl_smem, st>>>(o);
-            CU_TRY(h, cudaGetLastError());
-            launches++;
-        } else if (osd_on) {
-            OsdArgs<real> o;
-            o.g = a.g;
-            o.S = h->osd_S; o.St = h->osd_St;
-            o.method = h->osd_method; o.order = h->osd_order; o.uniform = d_priors ? 0 : h->uniform;
-            o.weight = h->d_weight;
-            o.synd = a.synd;
-            o.llr = llr_out ? a.llr : static_cast<const real *>(h->d_fail_llr);
-            o.llr_by_shot = llr_out ? 1 : 0;
-            o.fail_count = h->d_fail_count;
-            o.fail_list = h->d_fail_list;
-            o.osd0 = a.osd0; o.osdw = a.osdw;
-            o.stat = h->d_ctrl + 1;
-            const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
-            osd_kernel<real><<<ogrid, h->osd_threads, h->osd_smem, st>>>(o);
-            CU_TRY(h, cudaGetLastError());
-            launches++;
-        }
-        CU_TRY(h, cudaEventRecord(h->ev[2], st));
-        chunks++;
-        if (c0 + chunk < B || true) {
-            // events are re-used per chunk, so collect this chunk's times before the next one
-            CU_TRY(h, cudaEventSynchronize(h->ev[2]));
-            float t = 0;
-            CU_TRY(h, cudaEventElapsedTime(&t, h->ev[0], h->ev[1])); ms_bp += t;
-            CU_TRY(h, cudaEventElapsedTime(&t, h->ev[1], h->ev[2])); ms_osd += t;
-        }
+    } else if (osd_on) {
+        OsdArgs<real> o;
+        o.g = a.g;
+        o.S = h->osd_S; o.St = h->osd_St;
+        o.method = h->osd_method; o.order = h->osd_order;
+        o.uniform = (d_priors || d_weights) ? 0 : h->uniform;
+        o.weight = d_weights ? d_weights : h->d_weight;
+        o.weight_stride = d_weights ? n : 0;
+        o.synd = a.synd;
+        o.llr = llr_out ? llr_out : static_cast<const real *>(sl.d_fail_llr);
+        o.llr_by_shot = llr_out ? 1 : 0;
+        o.fail_count = d_fail_count;
+        o.fail_list = sl.d_fail_list;
+        o.osd0 = a.osd0; o.osdw = a.osdw;
+        o.stat = sl.d_ctrl + 1;
+        const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
+        osd_kernel<real><<<ogrid, h->osd_threads, h->osd_smem, st>>>(o);
+        CU_TRY(h, cudaGetLastError());
+        launches++;
     }
-    unsigned long long ctrl[4];
-    CU_TRY(h, cudaMemcpyAsync(ctrl, h->d_ctrl, sizeof(ctrl), cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaStreamSynchronize(st));
-    h->stats.shots = B;
-    h->stats.bp_converged = (int64_t)ctrl[1];
-    h->stats.bp_iterations = (int64_t)ctrl[2];
-    h->stats.osd_invocations = (int64_t)ctrl[3];
-    h->stats.ms_bp = ms_bp; h->stats.ms_osd = ms_osd;
-    h->stats.launches = launches; h->stats.chunks = chunks;
+    CU_TRY(h, cudaEventRecord(sl.ev[2], st));
+    CU_TRY(h, cudaMemcpyAsync(sl.h_ctrl, sl.d_ctrl, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    sl.pending = true;
+    sl.pending_shots = Bc;
+    sl.pending_launches = launches;
+    return BPOSD_OK;
+}
+
+// Wait for a slot's chunk (ev[3] must have been recorded after everything enqueued for it) and fold its
+// counters and CUDA-event times into the handle's statistics.
+static int collect_chunk(bposd_handle *h, bposd_handle::Slot &sl) {
+    if (!sl.pending) return BPOSD_OK;
+    sl.pending = false;
+    CU_TRY(h, cudaEventSynchronize(sl.ev[3]));
+    float t = 0;
+    CU_TRY(h, cudaEventElapsedTime(&t, sl.ev[0], sl.ev[1])); h->stats.ms_bp += t;
+    CU_TRY(h, cudaEventElapsedTime(&t, sl.ev[1], sl.ev[2])); h->stats.ms_osd += t;
+    h->stats.shots += sl.pending_shots;
+    h->stats.bp_converged += (int64_t)sl.h_ctrl[1];
+    h->stats.bp_iterations += (int64_t)sl.h_ctrl[2];
+    h->stats.osd_invocations += (int64_t)sl.h_ctrl[3];
+    h->stats.launches += sl.pending_launches;
+    h->stats.chunks += 1;
+    return BPOSD_OK;
+}
+
+static int check_osd_supported(bposd_handle *h) {
+    if (h->osd_method != BPOSD_OSD_OFF && !h->osd_supported)
+        return fail(h, BPOSD_EUNSUP, "OSD for this matrix size needs more shared memory than an SM has (the HBM-resident "
+                                     "kernel handles OSD-0 only); use osd_method osd0 or off");
+    return BPOSD_OK;
+}
+
+template <typename real>
+static int decode_batch_t(bposd_handle *h, const uint8_t *d_synd, long long B, const bposd_out_t *out,
+                          const void *d_priors, const double *d_weights, cudaStream_t st) {
+    const int n = h->n, m = h->m;
+    int rc = check_osd_supported(h);
+    if (rc) return rc;
+    const bool need_ws = h->osd_method != BPOSD_OSD_OFF && !out->d_llr;
+    long long chunk = std::min<long long>(need_ws ? std::min(B, h->fail_cap) : B, 1ll << 30);
+    h->stats = bposd_stats_t{};
+    bposd_handle::Slot &sl = h->slot[0];
+    for (long long c0 = 0; c0 < B; c0 += chunk) {
+        const long long Bc = std::min(chunk, B - c0);
+        bposd_out_t o{};
+        o.d_bp = out->d_bp ? out->d_bp + c0 * n : nullptr;
+        o.d_osd0 = out->d_osd0 ? out->d_osd0 + c0 * n : nullptr;
+        o.d_osdw = out->d_osdw ? out->d_osdw + c0 * n : nullptr;
+        o.d_llr = out->d_llr ? static_cast<void *>(static_cast<real *>(out->d_llr) + c0 * n) : nullptr;
+        o.d_converge = out->d_converge ? out->d_converge + c0 : nullptr;
+        o.d_iter = out->d_iter ? out->d_iter + c0 : nullptr;
+        rc = launch_chunk<real>(h, sl, st, d_synd + c0 * m, Bc, o,
+                                d_priors ? static_cast<const void *>(static_cast<const real *>(d_priors) + c0 * n) : nullptr,
+                                d_weights ? d_weights + c0 * n : nullptr);
+        if (rc) return rc;
+        CU_TRY(h, cudaEventRecord(sl.ev[3], st));
+        rc = collect_chunk(h, sl); // the control words and events are re-used by the next chunk
+        if (rc) return rc;
+    }
     return BPOSD_OK;
 }
 
 extern "C" int bposd_decode_batch(bposd_t *h, const uint8_t *d_synd, int64_t B, const bposd_out_t *out,
-                                  const void *d_priors, void *stream) {
+                                  const void *d_priors, const double *d_weights, void *stream) {
     if (!h) return BPOSD_EINVAL;
     if (!out || (!d_synd && B > 0 && h->m > 0)) return fail(h, BPOSD_EINVAL, "NULL argument");
     if (B < 0) return fail(h, BPOSD_EINVAL, "negative batch size");
     CU_TRY(h, cudaSetDevice(h->device));
     if (B == 0) { h->stats = bposd_stats_t{}; return BPOSD_OK; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return h->precision == 64 ? decode_batch_t<double>(h, d_synd, B, out, d_priors, st)
-                              : decode_batch_t<float>(h, d_synd, B, out, d_priors, st);
+    return h->precision == 64 ? decode_batch_t<double>(h, d_synd, B, out, d_priors, d_weights, st)
+                              : decode_batch_t<float>(h, d_synd, B, out, d_priors, d_weights, st);
 }
 
-static int ensure_buffers(bposd_handle *h, long long B, bool want_llr, bool want_err) {
+static int ensure_buffers(bposd_handle *h, bposd_handle::Slot &sl, long long B, bool want_llr, bool want_err) {
     const size_t rs = h->precision == 64 ? 8 : 4;
-    if (B > h->b_cap) {
-        cudaFree(h->b_synd); cudaFree(h->b_osdw); cudaFree(h->b_osd0); cudaFree(h->b_bp); cudaFree(h->b_conv);
-        cudaFree(h->b_iter); cudaFree(h->b_err); cudaFree(h->b_llr);
-        h->b_synd = h->b_osdw = h->b_osd0 = h->b_bp = h->b_conv = h->b_err = nullptr;
-        h->b_iter = nullptr; h->b_llr = nullptr;
-        h->b_cap = 0;
-        CU_TRY(h, cudaMalloc((void **)&h->b_synd, (size_t)B * std::max(h->m, 1)));
-        CU_TRY(h, cudaMalloc((void **)&h->b_osdw, (size_t)B * h->n));
-        CU_TRY(h, cudaMalloc((void **)&h->b_osd0, (size_t)B * h->n));
-        CU_TRY(h, cudaMalloc((void **)&h->b_bp, (size_t)B * h->n));
-        CU_TRY(h, cudaMalloc((void **)&h->b_conv, (size_t)B));
-        CU_TRY(h, cudaMalloc((void **)&h->b_iter, (size_t)B * 4));
-        h->b_cap = B;
+    if (B > sl.b_cap) {
+        cudaFree(sl.b_synd); cudaFree(sl.b_osdw); cudaFree(sl.b_osd0); cudaFree(sl.b_bp); cudaFree(sl.b_conv);
+        cudaFree(sl.b_iter); cudaFree(sl.b_err); cudaFree(sl.b_llr);
+        sl.b_synd = sl.b_osdw = sl.b_osd0 = sl.b_bp = sl.b_conv = sl.b_err = nullptr;
+        sl.b_iter = nullptr; sl.b_llr = nullptr;
+        sl.b_cap = 0;
+        CU_TRY(h, cudaMalloc((void **)&sl.b_synd, (size_t)B * std::max(h->m, 1)));
+        CU_TRY(h, cudaMalloc((void **)&sl.b_osdw, (size_t)B * h->n));
+        CU_TRY(h, cudaMalloc((void **)&sl.b_osd0, (size_t)B * h->n));
+        CU_TRY(h, cudaMalloc((void **)&sl.b_bp, (size_t)B * h->n));
+        CU_TRY(h, cudaMalloc((void **)&sl.b_conv, (size_t)B));
+        CU_TRY(h, cudaMalloc((void **)&sl.b_iter, (size_t)B * 4));
+        sl.b_cap = B;
     }
-    if (want_llr && !h->b_llr) CU_TRY(h, cudaMalloc(&h->b_llr, (size_t)h->b_cap * h->n * rs));
-    if (want_err && !h->b_err) CU_TRY(h, cudaMalloc((void **)&h->b_err, (size_t)h->b_cap * h->n));
+    if (want_llr && !sl.b_llr) CU_TRY(h, cudaMalloc(&sl.b_llr, (size_t)sl.b_cap * h->n * rs));
+    if (want_err && !sl.b_err) CU_TRY(h, cudaMalloc((void **)&sl.b_err, (size_t)sl.b_cap * h->n));
+    return BPOSD_OK;
+}
+
+// Host-buffer decode: the batch is cut into chunks that alternate between the two slots, each on its
+// own stream (H2D -> BP -> OSD -> D2H in stream order), so the copies of one chunk overlap the
+// kernels of the other.  Kernels that share a per-handle scratch (HBM-scratch BP, HBM OSD) run
+// single-slot.
+template <typename real>
+static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, uint8_t *h_osdw, uint8_t *h_osd0,
+                         uint8_t *h_bp, void *h_llr, uint8_t *h_conv, int32_t *h_iter) {
+    const int n = h->n, m = h->m;
+    int rc = check_osd_supported(h);
+    if (rc) return rc;
+    const bool need_ws = h->osd_method != BPOSD_OSD_OFF && !h_llr;
+    const bool pipelined = h->bp_kernel != 0 && !h->osd_large && B >= 2 * h->host_chunk_min;
+    long long chunk = B;
+    if (pipelined) chunk = std::min<long long>(std::max<long long>((B + 15) / 16, h->host_chunk_min), h->host_chunk_max);
+    if (need_ws) chunk = std::min(chunk, h->fail_cap);
+    const int nslots = pipelined ? 2 : 1;
+    h->stats = bposd_stats_t{};
+    long long idx = 0;
+    for (long long c0 = 0; c0 < B; c0 += chunk, idx++) {
+        const long long Bc = std::min(chunk, B - c0);
+        bposd_handle::Slot &sl = h->slot[idx % nslots];
+        rc = collect_chunk(h, sl); // the slot's previous chunk must have left its buffers
+        if (rc) return rc;
+        rc = ensure_buffers(h, sl, std::min(chunk, B), h_llr != nullptr, false);
+        if (rc) return rc;
+        cudaStream_t st = sl.stream;
+        CU_TRY(h, cudaMemcpyAsync(sl.b_synd, h_synd + c0 * m, (size_t)Bc * m, cudaMemcpyHostToDevice, st));
+        bposd_out_t o{};
+        o.d_osdw = h_osdw ? sl.b_osdw : nullptr;
+        o.d_osd0 = h_osd0 ? sl.b_osd0 : nullptr;
+        o.d_bp = h_bp ? sl.b_bp : nullptr;
+        o.d_llr = h_llr ? sl.b_llr : nullptr;
+        o.d_converge = h_conv ? sl.b_conv : nullptr;
+        o.d_iter = h_iter ? sl.b_iter : nullptr;
+        rc = launch_chunk<real>(h, sl, st, sl.b_synd, Bc, o, nullptr, nullptr);
+        if (rc) return rc;
+        if (h_osdw) CU_TRY(h, cudaMemcpyAsync(h_osdw + c0 * n, sl.b_osdw, (size_t)Bc * n, cudaMemcpyDeviceToHost, st));
+        if (h_osd0) CU_TRY(h, cudaMemcpyAsync(h_osd0 + c0 * n, sl.b_osd0, (size_t)Bc * n, cudaMemcpyDeviceToHost, st));
+        if (h_bp) CU_TRY(h, cudaMemcpyAsync(h_bp + c0 * n, sl.b_bp, (size_t)Bc * n, cudaMemcpyDeviceToHost, st));
+        if (h_llr) CU_TRY(h, cudaMemcpyAsync(static_cast<real *>(h_llr) + c0 * n, sl.b_llr, (size_t)Bc * n * sizeof(real), cudaMemcpyDeviceToHost, st));
+        if (h_conv) CU_TRY(h, cudaMemcpyAsync(h_conv + c0, sl.b_conv, (size_t)Bc, cudaMemcpyDeviceToHost, st));
+        if (h_iter) CU_TRY(h, cudaMemcpyAsync(h_iter + c0, sl.b_iter, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaEventRecord(sl.ev[3], st));
+    }
+    for (int k = 0; k < 2; k++) {
+        rc = collect_chunk(h, h->slot[k]);
+        if (rc) return rc;
+    }
     return BPOSD_OK;
 }
 
@@ -575,29 +675,9 @@ extern "C" int bposd_decode_host(bposd_t *h, const uint8_t *h_synd, int64_t B, u
     if (!h) return BPOSD_EINVAL;
     if (B < 0 || (!h_synd && B > 0 && h->m > 0)) return fail(h, BPOSD_EINVAL, "bad argument");
     CU_TRY(h, cudaSetDevice(h->device));
-    if (B == 0) return BPOSD_OK;
-    int rc = ensure_buffers(h, B, h_llr != nullptr, false);
-    if (rc) return rc;
-    const size_t rs = h->precision == 64 ? 8 : 4;
-    cudaStream_t st = nullptr;
-    CU_TRY(h, cudaMemcpyAsync(h->b_synd, h_synd, (size_t)B * h->m, cudaMemcpyHostToDevice, st));
-    bposd_out_t o{};
-    o.d_osdw = h_osdw ? h->b_osdw : nullptr;
-    o.d_osd0 = h_osd0 ? h->b_osd0 : nullptr;
-    o.d_bp = h_bp ? h->b_bp : nullptr;
-    o.d_llr = h_llr ? h->b_llr : nullptr;
-    o.d_converge = h_conv ? h->b_conv : nullptr;
-    o.d_iter = h_iter ? h->b_iter : nullptr;
-    rc = bposd_decode_batch(h, h->b_synd, B, &o, nullptr, st);
-    if (rc) return rc;
-    if (h_osdw) CU_TRY(h, cudaMemcpyAsync(h_osdw, h->b_osdw, (size_t)B * h->n, cudaMemcpyDeviceToHost, st));
-    if (h_osd0) CU_TRY(h, cudaMemcpyAsync(h_osd0, h->b_osd0, (size_t)B * h->n, cudaMemcpyDeviceToHost, st));
-    if (h_bp) CU_TRY(h, cudaMemcpyAsync(h_bp, h->b_bp, (size_t)B * h->n, cudaMemcpyDeviceToHost, st));
-    if (h_llr) CU_TRY(h, cudaMemcpyAsync(h_llr, h->b_llr, (size_t)B * h->n * rs, cudaMemcpyDeviceToHost, st));
-    if (h_conv) CU_TRY(h, cudaMemcpyAsync(h_conv, h->b_conv, (size_t)B, cudaMemcpyDeviceToHost, st));
-    if (h_iter) CU_TRY(h, cudaMemcpyAsync(h_iter, h->b_iter, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaStreamSynchronize(st));
-    return BPOSD_OK;
+    if (B == 0) { h->stats = bposd_stats_t{}; return BPOSD_OK; }
+    return h->precision == 64 ? decode_host_t<double>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter)
+                              : decode_host_t<float>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter);
 }
 
 extern "C" int bposd_set_channel_thresholds(bposd_t *h, const uint32_t *t1, const uint32_t *t2, const uint32_t *t3) {
@@ -653,10 +733,11 @@ extern "C" int bposd_set_logicals(bposd_t *h, const int32_t *indptr, const int32
 }
 
 static int logical_launch(bposd_handle *h, const uint8_t *d_err, const uint8_t *d_dec, long long B, uint8_t *d_fail,
-                          unsigned long long *d_count, int *d_minw, cudaStream_t st) {
+                          unsigned long long *d_count, int *d_minw, cudaStream_t st, int *d_resid_weight = nullptr) {
     LogicalArgs a;
     a.n = h->n; a.K = h->K; a.l_ptr = h->d_l_ptr; a.l_idx = h->d_l_idx;
     a.errors = d_err; a.dec = d_dec; a.B = B; a.fail = d_fail; a.fail_count = d_count; a.min_weight = d_minw;
+    a.resid_weight = d_resid_weight;
     const int grid = (int)std::min<long long>((B + 7) / 8, (long long)h->sm_count * 8);
     logical_check_kernel<<<std::max(grid, 1), 256, 0, st>>>(a);
     CU_TRY(h, cudaGetLastError());
@@ -664,14 +745,77 @@ static int logical_launch(bposd_handle *h, const uint8_t *d_err, const uint8_t *
 }
 
 extern "C" int bposd_logical_check(bposd_t *h, const uint8_t *d_err, const uint8_t *d_dec, int64_t B, uint8_t *d_fail,
-                                   int64_t *d_fail_count, int32_t *d_min_weight, void *stream) {
+                                   int64_t *d_fail_count, int32_t *d_min_weight, int32_t *d_resid_weight, void *stream) {
     if (!h) return BPOSD_EINVAL;
     if (!h->d_l_ptr) return fail(h, BPOSD_EINVAL, "call bposd_set_logicals first");
     if (B < 0 || ((!d_err || !d_dec) && B > 0)) return fail(h, BPOSD_EINVAL, "bad argument");
     CU_TRY(h, cudaSetDevice(h->device));
     if (B == 0) return BPOSD_OK;
     return logical_launch(h, d_err, d_dec, B, d_fail, reinterpret_cast<unsigned long long *>(d_fail_count), d_min_weight,
-                          static_cast<cudaStream_t>(stream));
+                          static_cast<cudaStream_t>(stream), d_resid_weight);
+}
+
+extern "C" int bposd_channel_update(bposd_t *h, const uint8_t *d_first, int64_t B, const double *h_p0, const double *h_p1,
+                                    void *d_priors, double *d_weights, void *stream) {
+    if (!h) return BPOSD_EINVAL;
+    if (B < 0 || !h_p0 || !h_p1 || ((!d_first || !d_priors) && B > 0)) return fail(h, BPOSD_EINVAL, "bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int n = h->n;
+    for (int j = 0; j < n; j++)
+        if (!(h_p0[j] >= 0.0 && h_p0[j] <= 1.0) || !(h_p1[j] >= 0.0 && h_p1[j] <= 1.0))
+            return fail(h, BPOSD_EINVAL, "channel probabilities must lie in [0, 1]");
+    // tables [prior0 | prior1 | weight0 | weight1], the same expressions as upload_probs (rows a3, a14)
+    std::vector<double> tab(4 * (size_t)n);
+    for (int j = 0; j < n; j++) {
+        tab[j] = std::log((1.0 - h_p0[j]) / h_p0[j]);
+        tab[n + j] = std::log((1.0 - h_p1[j]) / h_p1[j]);
+        tab[2 * (size_t)n + j] = std::log(1 / h_p0[j]);
+        tab[3 * (size_t)n + j] = std::log(1 / h_p1[j]);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!h->d_cu_tab) CU_TRY(h, cudaMalloc((void **)&h->d_cu_tab, 4 * (size_t)n * sizeof(double)));
+    // stream-ordered with the kernel below; the staging vector is pageable, so the copy returns after staging
+    CU_TRY(h, cudaMemcpyAsync(h->d_cu_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (B == 0) return BPOSD_OK;
+    const long long total = (long long)B * n;
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+    const double *t = h->d_cu_tab;
+    if (h->precision == 64)
+        channel_update_kernel<double><<<grid, 256, 0, st>>>(d_first, total, n, t, t + n, t + 2 * (size_t)n, t + 3 * (size_t)n,
+                                                            static_cast<double *>(d_priors), d_weights);
+    else
+        channel_update_kernel<float><<<grid, 256, 0, st>>>(d_first, total, n, t, t + n, t + 2 * (size_t)n, t + 3 * (size_t)n,
+                                                           static_cast<float *>(d_priors), d_weights);
+    CU_TRY(h, cudaGetLastError());
+    return BPOSD_OK;
+}
+
+extern "C" int bposd_css_counters(bposd_t *h, int64_t B, const bposd_css_sector_t *osdw, const bposd_css_sector_t *osd0,
+                                  const bposd_css_sector_t *bp, const uint8_t *d_conv_x, const uint8_t *d_conv_z,
+                                  int64_t *h_counters, void *stream) {
+    if (!h) return BPOSD_EINVAL;
+    if (B < 0 || !osdw || !osd0 || !bp || !h_counters || ((!d_conv_x || !d_conv_z) && B > 0)) return fail(h, BPOSD_EINVAL, "bad argument");
+    for (const bposd_css_sector_t *s : {osdw, osd0, bp})
+        if ((!s->d_fail_x || !s->d_fail_z) && B > 0) return fail(h, BPOSD_EINVAL, "failure flags missing");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (B == 0) return BPOSD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU_TRY(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    const int big = 0x7fffffff;
+    CU_TRY(h, cudaMemcpyAsync(h->d_minw, &big, sizeof(int), cudaMemcpyHostToDevice, st));
+    auto conv = [](const bposd_css_sector_t *s) { CssSector c; c.fail_x = s->d_fail_x; c.fail_z = s->d_fail_z; c.weight_x = s->d_weight_x; c.weight_z = s->d_weight_z; return c; };
+    const int grid = (int)std::max<long long>(1, std::min<long long>((B + 255) / 256, (long long)h->sm_count * 4));
+    css_counters_kernel<<<grid, 256, 0, st>>>(B, conv(osdw), conv(osd0), conv(bp), d_conv_x, d_conv_z, h->d_counters, h->d_minw);
+    CU_TRY(h, cudaGetLastError());
+    unsigned long long c[8];
+    int minw = 0;
+    CU_TRY(h, cudaMemcpyAsync(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(&minw, h->d_minw, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    h_counters[0] += B;
+    for (int k = 1; k <= 5; k++) h_counters[k] += (int64_t)c[k];
+    if (minw != big && (h_counters[6] <= 0 || minw < h_counters[6])) h_counters[6] = minw;
+    return BPOSD_OK;
 }
 
 __global__ void bp_success_kernel(const uint8_t *fail, const uint8_t *conv, long long B, unsigned long long *count) {
@@ -692,26 +836,27 @@ extern "C" int bposd_sample_and_decode(bposd_t *h, uint64_t seed, uint64_t shot0
     CU_TRY(h, cudaSetDevice(h->device));
     if (B == 0) return BPOSD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = ensure_buffers(h, B, false, true);
+    bposd_handle::Slot &sl = h->slot[0];
+    int rc = ensure_buffers(h, sl, B, false, true);
     if (rc) return rc;
-    rc = bposd_sample_syndromes(h, seed, shot0, B, sector, h->b_err, h->b_synd, stream);
+    rc = bposd_sample_syndromes(h, seed, shot0, B, sector, sl.b_err, sl.b_synd, stream);
     if (rc) return rc;
     bposd_out_t o{};
-    o.d_osdw = h->b_osdw; o.d_osd0 = h->b_osd0; o.d_bp = h->b_bp; o.d_converge = h->b_conv;
-    rc = bposd_decode_batch(h, h->b_synd, B, &o, nullptr, stream);
+    o.d_osdw = sl.b_osdw; o.d_osd0 = sl.b_osd0; o.d_bp = sl.b_bp; o.d_converge = sl.b_conv;
+    rc = bposd_decode_batch(h, sl.b_synd, B, &o, nullptr, nullptr, stream);
     if (rc) return rc;
     // d_counters: [0] osdw failures, [1] osd0 failures, [2] bp successes; b_iter reused as fail flags for bp
     CU_TRY(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), st));
     const int big = 0x7fffffff;
     CU_TRY(h, cudaMemcpyAsync(h->d_minw, &big, sizeof(int), cudaMemcpyHostToDevice, st));
-    rc = logical_launch(h, h->b_err, h->b_osdw, B, nullptr, h->d_counters + 0, h->d_minw, st);
+    rc = logical_launch(h, sl.b_err, sl.b_osdw, B, nullptr, h->d_counters + 0, h->d_minw, st);
     if (rc) return rc;
-    rc = logical_launch(h, h->b_err, h->b_osd0, B, nullptr, h->d_counters + 1, h->d_minw, st);
+    rc = logical_launch(h, sl.b_err, sl.b_osd0, B, nullptr, h->d_counters + 1, h->d_minw, st);
     if (rc) return rc;
-    uint8_t *bpfail = reinterpret_cast<uint8_t *>(h->b_iter);
-    rc = logical_launch(h, h->b_err, h->b_bp, B, bpfail, nullptr, nullptr, st);
+    uint8_t *bpfail = reinterpret_cast<uint8_t *>(sl.b_iter);
+    rc = logical_launch(h, sl.b_err, sl.b_bp, B, bpfail, nullptr, nullptr, st);
     if (rc) return rc;
-    bp_success_kernel<<<std::max(1, std::min(h->sm_count * 4, (int)((B + 255) / 256))), 256, 0, st>>>(bpfail, h->b_conv, B, h->d_counters + 2);
+    bp_success_kernel<<<std::max(1, std::min(h->sm_count * 4, (int)((B + 255) / 256))), 256, 0, st>>>(bpfail, sl.b_conv, B, h->d_counters + 2);
     CU_TRY(h, cudaGetLastError());
     unsigned long long c[8];
     int minw = 0;

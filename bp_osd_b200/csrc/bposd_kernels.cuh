@@ -255,7 +255,8 @@ struct OsdArgs {
     int method;   // 0 osd0, 1 osd_e, 2 osd_cs
     int order;    // search depth w
     int uniform;  // 1: all channel probabilities equal and in (0,1): weight = popcount
-    const double *weight; // [n] log(1/p_j)
+    const double *weight; // [n] log(1/p_j), or [B, n] per shot when weight_stride == n
+    long long weight_stride;
     const uint8_t *synd;
     const real *llr;      // [B, n] if llr_by_shot else [capacity, n] indexed by fail slot
     int llr_by_shot;
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(1024) osd_kernel(OsdArgs<real> a) {
         const long long shot = a.fail_list[f];
         const real *llr = a.llr + (a.llr_by_shot ? shot : (long long)f) * n;
         const uint8_t *synd = a.synd + shot * m;
+        const double *weight = a.weight + shot * a.weight_stride;
         __syncthreads();
 
         // ---- a9: stable ascending rank sort on (llr, index) ----
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(1024) osd_kernel(OsdArgs<real> a) {
                     unsigned mask = __ballot_sync(0xffffffffu, x);
                     while (mask) { // ascending j, sequential fp64 accumulation (row a14)
                         const int b = __ffs(mask) - 1;
-                        W += a.weight[j0 + b];
+                        W += weight[j0 + b];
                         mask &= mask - 1;
                     }
                 }
@@ -807,6 +809,7 @@ struct LogicalArgs {
     uint8_t *fail;
     unsigned long long *fail_count;
     int *min_weight;
+    int *resid_weight; // [B] Hamming weight of e ^ d per shot (may be NULL)
 };
 
 // one warp per shot: lanes split the logical rows; a shot fails if any row has odd overlap
@@ -828,11 +831,12 @@ __global__ void __launch_bounds__(256) logical_check_kernel(LogicalArgs a) {
             any |= acc;
         }
         any = __any_sync(0xffffffffu, any);
-        if (any && a.min_weight) {
+        if ((any && a.min_weight) || a.resid_weight) {
             int wsum = 0;
             for (int j = lane; j < a.n; j += 32) wsum += (e[j] ^ d[j]) & 1;
             for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-            minw = min(minw, wsum);
+            if (any) minw = min(minw, wsum);
+            if (a.resid_weight && lane == 0) a.resid_weight[b] = wsum;
         }
         if (lane == 0) {
             if (a.fail) a.fail[b] = (uint8_t)any;
@@ -843,6 +847,58 @@ __global__ void __launch_bounds__(256) logical_check_kernel(LogicalArgs a) {
         if (a.fail_count && nfail) atomicAdd(a.fail_count, nfail);
         if (a.min_weight && minw != 0x7fffffff) atomicMin(a.min_weight, minw);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Harness kernels for the two-sector CSS simulation (css_decode_sim.py:207-248, 250-365)
+// ---------------------------------------------------------------------------------------------
+// Per-shot channel update: the second sector's probability of qubit j is one of two host-computed
+// values, selected by the first sector's decoding bit.  Emits BP priors log((1-p)/p) and OSD
+// weights log(1/p); the logarithms are taken on the host (glibc) so the values are the ones
+// update_channel_probs would have produced.
+template <typename real>
+__global__ void __launch_bounds__(256) channel_update_kernel(const uint8_t *__restrict__ first, long long total, int n,
+                                                             const double *__restrict__ prior0, const double *__restrict__ prior1,
+                                                             const double *__restrict__ w0, const double *__restrict__ w1,
+                                                             real *__restrict__ priors, double *__restrict__ weights) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % n);
+        const bool one = first[i] != 0;
+        priors[i] = (real)(one ? prior1[j] : prior0[j]);
+        if (weights) weights[i] = one ? w1[j] : w0[j];
+    }
+}
+
+struct CssSector {
+    const uint8_t *fail_x, *fail_z; // [B] logical X / Z failure flags of one decoding (osdw, osd0 or bp)
+    const int *weight_x, *weight_z; // [B] residual weights (may be NULL: no min-weight tracking)
+};
+
+// counters: [0] shots, [1] bp_converge_x, [2] bp_converge_z, [3] bp_success, [4] osd0_success, [5] osdw_success,
+// [6] minimum weight of a failing residual (X checked first, Z only if X passed: the reference's `elif`).
+__global__ void __launch_bounds__(256) css_counters_kernel(long long B, CssSector osdw, CssSector osd0, CssSector bp,
+                                                           const uint8_t *conv_x, const uint8_t *conv_z,
+                                                           unsigned long long *counters, int *min_weight) {
+    unsigned long long c[5] = {0, 0, 0, 0, 0};
+    int minw = 0x7fffffff;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const bool cx = conv_x[b] != 0, cz = conv_z[b] != 0;
+        c[0] += cx; c[1] += cz;
+        if (cx && cz && !bp.fail_x[b] && !bp.fail_z[b]) c[2]++;
+        if (osd0.fail_x[b]) { if (osd0.weight_x) minw = min(minw, osd0.weight_x[b]); }
+        else if (osd0.fail_z[b]) { if (osd0.weight_z) minw = min(minw, osd0.weight_z[b]); }
+        else c[3]++;
+        if (osdw.fail_x[b]) { if (osdw.weight_x) minw = min(minw, osdw.weight_x[b]); }
+        else if (osdw.fail_z[b]) { if (osdw.weight_z) minw = min(minw, osdw.weight_z[b]); }
+        else c[4]++;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
+        if ((threadIdx.x & 31) == 0 && c[k]) atomicAdd(&counters[1 + k], c[k]);
+    }
+    for (int o = 16; o > 0; o >>= 1) minw = min(minw, __shfl_xor_sync(0xffffffffu, minw, o));
+    if ((threadIdx.x & 31) == 0 && minw != 0x7fffffff) atomicMin(min_weight, minw);
 }
 
 } // namespace bposd

@@ -235,13 +235,17 @@ class BpOsdDecoder:
                                                    _ptr(llr), _ptr(conv), _ptr(it)))
         return BatchResult(osdw, osd0, bp, llr, None if conv is None else conv.astype(bool), it)
 
-    def decode_batch(self, syndromes, return_llr: bool = True, return_all: bool = True, priors=None, out=None):
+    def decode_batch(self, syndromes, return_llr: bool = True, return_all: bool = True, priors=None, out=None,
+                     weights=None):
         """Decode ``syndromes[B, m]``.
 
         A CUDA ``torch.Tensor`` (uint8/bool/int, 0/1) is decoded in place on its device and the
         result holds CUDA tensors; a numpy array goes through pinned-staging copies
         (``bposd_decode_host``) and the result holds numpy arrays.  ``priors`` (CUDA tensor
-        [B, n] of prior LLRs in the handle's precision) selects per-shot channel priors.
+        [B, n] of prior LLRs log((1-p)/p) in the handle's precision) selects per-shot channel priors and
+        ``weights`` (CUDA float64 tensor [B, n] of log(1/p)) the matching per-shot OSD weights -- together
+        they are the batched form of ``update_channel_probs`` before every shot
+        (css_decode_sim.py:207-248).
         ``out`` may hold preallocated result buffers (keys ``osdw osd0 bp llr converge iter``; CUDA
         tensors for CUDA input, numpy arrays -- ideally pinned -- for host input).
         """
@@ -285,12 +289,19 @@ class BpOsdDecoder:
                         and priors.dtype == tdt):
                     raise ValueError("priors must be a CUDA tensor [B, n] in the decoder's precision")
                 pri = priors.contiguous()
+            wts = None
+            if weights is not None:
+                if not (isinstance(weights, torch.Tensor) and weights.is_cuda and weights.shape == (B, self.n)
+                        and weights.dtype == torch.float64):
+                    raise ValueError("weights must be a CUDA float64 tensor [B, n]")
+                wts = weights.contiguous()
             o = _capi.Out(osdw.data_ptr(), osd0.data_ptr() if osd0 is not None else None,
                           bp.data_ptr() if bp is not None else None,
                           llr.data_ptr() if llr is not None else None, conv.data_ptr(), it.data_ptr())
             stream = torch.cuda.current_stream(dev).cuda_stream
             self._check(_capi.load().bposd_decode_batch(self._h, s.data_ptr(), B, C.byref(o),
-                                                        pri.data_ptr() if pri is not None else None, stream))
+                                                        pri.data_ptr() if pri is not None else None,
+                                                        wts.data_ptr() if wts is not None else None, stream))
             return BatchResult(osdw, osd0, bp, llr, conv.bool(), it)
         s = np.asarray(syndromes)
         if s.ndim != 2 or s.shape[1] != self.m:
@@ -330,16 +341,36 @@ class BpOsdDecoder:
                                                         syn.data_ptr(), stream))
         return err, syn
 
-    def logical_check(self, errors, decodings):
-        """fail[b] = ((L @ (e ^ d)) % 2).any() on the device for CUDA uint8 tensors [B, n]."""
+    def logical_check(self, errors, decodings, return_weight: bool = False):
+        """fail[b] = ((L @ (e ^ d)) % 2).any() on the device for CUDA uint8 tensors [B, n];
+        with ``return_weight`` also the Hamming weight of every residual (int32 [B])."""
         import torch
         B = errors.shape[0]
         fail = torch.empty(B, dtype=torch.uint8, device=errors.device)
+        wt = torch.empty(B, dtype=torch.int32, device=errors.device) if return_weight else None
         stream = torch.cuda.current_stream(errors.device).cuda_stream
         self._check(_capi.load().bposd_logical_check(self._h, errors.contiguous().data_ptr(),
                                                      decodings.contiguous().data_ptr(), B, fail.data_ptr(),
-                                                     None, None, stream))
-        return fail.bool()
+                                                     None, None, wt.data_ptr() if wt is not None else None, stream))
+        return (fail.bool(), wt) if return_weight else fail.bool()
+
+    def channel_update(self, first_decoding, probs_if0, probs_if1):
+        """Per-shot priors / OSD weights of this decoder given the other sector's decoding (CUDA uint8 [B, n]).
+        Returns (priors [B, n] in the decoder's precision, weights [B, n] float64) for ``decode_batch``."""
+        import torch
+        d = first_decoding.contiguous()
+        B = d.shape[0]
+        p0 = np.ascontiguousarray(probs_if0, dtype=np.float64)
+        p1 = np.ascontiguousarray(probs_if1, dtype=np.float64)
+        if p0.shape != (self.n,) or p1.shape != (self.n,) or d.shape[1] != self.n:
+            raise ValueError(f"channel update needs [B, {self.n}] decodings and two probability vectors of length {self.n}")
+        tdt = torch.float64 if self.precision == 64 else torch.float32
+        pri = torch.empty((B, self.n), dtype=tdt, device=d.device)
+        wts = torch.empty((B, self.n), dtype=torch.float64, device=d.device)
+        stream = torch.cuda.current_stream(d.device).cuda_stream
+        self._check(_capi.load().bposd_channel_update(self._h, d.data_ptr(), B, _ptr(p0), _ptr(p1), pri.data_ptr(),
+                                                      wts.data_ptr(), stream))
+        return pri, wts
 
     def sample_and_decode(self, seed: int, shot0: int, B: int, sector: int = 0, counters=None) -> np.ndarray:
         """One Monte-Carlo step of B shots on the device; returns / accumulates int64 counters[8]:

@@ -43,22 +43,32 @@ def _min_pos(x, y):
     return min(x, y)
 
 
-def all_reduce_counters(counters, group=None, device=None) -> np.ndarray:
-    """One all-reduce(SUM) over the counter vector; the min slot rides along as a second tiny MIN reduce."""
+def all_reduce_vector(vec, min_slots=(), group=None, device=None) -> np.ndarray:
+    """One all-reduce(SUM) over an int64 vector; the slots in ``min_slots`` hold minima where 0 means
+    "nothing seen yet" and ride along as a second tiny MIN reduce."""
     import torch
     import torch.distributed as dist
 
-    c = np.asarray(counters, dtype=np.int64)
+    c = np.asarray(vec, dtype=np.int64)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return c.copy()
-    t = torch.from_numpy(c.copy())
     big = np.iinfo(np.int64).max
-    mn = torch.tensor([c[MIN_SLOT] if c[MIN_SLOT] > 0 else big], dtype=torch.int64)
-    if device is not None:
-        t, mn = t.to(device), mn.to(device)
-    t[MIN_SLOT] = 0
+    t = torch.from_numpy(c.copy())
+    mn = torch.tensor([c[s] if c[s] > 0 else big for s in min_slots] or [big], dtype=torch.int64)
+    for s in min_slots:
+        t[s] = 0
+    if device is not None and dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", device) if isinstance(device, int) else device
+        t, mn = t.to(dev), mn.to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
     out = t.cpu().numpy()
-    out[MIN_SLOT] = 0 if int(mn.item()) == big else int(mn.item())
+    mn = mn.cpu().numpy()
+    for k, s in enumerate(min_slots):
+        out[s] = 0 if int(mn[k]) == big else int(mn[k])
     return out
+
+
+def all_reduce_counters(counters, group=None, device=None) -> np.ndarray:
+    """The path's single collective: the counter vector of ``sample_and_decode`` (slot 7 is a minimum)."""
+    return all_reduce_vector(counters, min_slots=(MIN_SLOT,), group=group, device=device)

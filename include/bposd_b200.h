@@ -99,13 +99,17 @@ int bposd_update_channel_probs(bposd_t *h, const double *h_channel_probs);
  * d_syndromes is [B, m] uint8 (0/1) on the device.  Asynchronous on `stream` except for a
  * final stream synchronise that collects bposd_stats_t.
  * d_priors_per_shot: NULL, or [B, n] prior LLRs log((1-p)/p) in the handle's precision, one
- * row per shot (the per-shot channel update of css_decode_sim.py:207-248). */
+ * row per shot (the per-shot channel update of css_decode_sim.py:207-248).
+ * d_weights_per_shot: NULL, or [B, n] OSD weights log(1/p) (double), one row per shot; the reference's
+ * update_channel_probs changes the BP priors and the OSD weights together (row a16). */
 int bposd_decode_batch(bposd_t *h, const uint8_t *d_syndromes, int64_t B, const bposd_out_t *out,
-                       const void *d_priors_per_shot, void *stream);
+                       const void *d_priors_per_shot, const double *d_weights_per_shot, void *stream);
 
 /* Same, with host buffers: copies h_syndromes [B, m] to the device, decodes, copies the
  * requested outputs back (NULL = not wanted).  This is what the reference-facing
- * `decode()` / `decode_batch(numpy)` call goes through; pinned staging is internal. */
+ * `decode()` / `decode_batch(numpy)` call goes through.  Large batches are cut into chunks that are
+ * double-buffered over two internal streams, so the copies overlap the kernels; pass pinned host
+ * memory for the copies to be asynchronous. */
 int bposd_decode_host(bposd_t *h, const uint8_t *h_syndromes, int64_t B, uint8_t *h_osdw,
                       uint8_t *h_osd0, uint8_t *h_bp, void *h_llr, uint8_t *h_converge,
                       int32_t *h_iter);
@@ -129,7 +133,28 @@ int bposd_set_logicals(bposd_t *h, const int32_t *h_indptr, const int32_t *h_ind
  * be NULL; css_decode_sim.py:261-264). */
 int bposd_logical_check(bposd_t *h, const uint8_t *d_errors, const uint8_t *d_decodings,
                         int64_t B, uint8_t *d_fail, int64_t *d_fail_count, int32_t *d_min_weight,
-                        void *stream);
+                        int32_t *d_resid_weight /* [B] weight of e ^ d per shot, may be NULL */, void *stream);
+
+/* Per-shot channel update between the two sectors of a CSS decode (`_channel_update`,
+ * css_decode_sim.py:207-248): the second decoder's probability of qubit j is h_probs_if1[j] where the
+ * first sector's decoding d_first_decoding[b, j] is 1 and h_probs_if0[j] where it is 0.  Writes the
+ * BP priors log((1-p)/p) ([B, n], handle precision) and the OSD weights log(1/p) ([B, n] double, may be
+ * NULL) that bposd_decode_batch takes as d_priors_per_shot / d_weights_per_shot. */
+int bposd_channel_update(bposd_t *h, const uint8_t *d_first_decoding, int64_t B, const double *h_probs_if0,
+                         const double *h_probs_if1, void *d_priors_out, double *d_weights_out, void *stream);
+
+/* Counters of the two-sector simulation (`_encoded_error_rates`, css_decode_sim.py:250-365) from the
+ * per-shot flags of bposd_logical_check.  X failures are looked at first, Z only where X passed (the
+ * reference's `elif`).  Accumulates into h_counters[8] (int64): [0] shots, [1] bp_converge_x,
+ * [2] bp_converge_z, [3] bp_success (both sectors converged and no logical error), [4] osd0_success,
+ * [5] osdw_success, [6] minimum weight of a failing osdw/osd0 residual (min-combined, 0 = none yet). */
+typedef struct {
+    const uint8_t *d_fail_x, *d_fail_z;     /* [B] */
+    const int32_t *d_weight_x, *d_weight_z; /* [B] residual weights, may be NULL */
+} bposd_css_sector_t;
+int bposd_css_counters(bposd_t *h, int64_t B, const bposd_css_sector_t *osdw, const bposd_css_sector_t *osd0,
+                       const bposd_css_sector_t *bp, const uint8_t *d_converge_x, const uint8_t *d_converge_z,
+                       int64_t *h_counters, void *stream);
 
 /* One Monte-Carlo step of one sector, all on the device (css_decode_sim.py:163-205 for a
  * single sector): sample B errors starting at global shot index shot0, syndromes, decode,

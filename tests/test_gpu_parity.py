@@ -427,3 +427,61 @@ def test_config5_full_size(torch_cuda, oracle_mod, cfg_codes):
         assert (r.bp_decoding[b].cpu().numpy() == o.bp_decoding).all()
         assert (r.log_prob_ratios[b].cpu().numpy() == o.log_prob_ratios).all()
         assert (osd0[b] == o.osd0_decoding).all()
+
+
+def test_per_shot_priors_and_osd_weights(torch_cuda, oracle_mod, cfg_codes):
+    """priors + weights per shot == update_channel_probs before every shot, including the OSD-CS weighting (row a16)."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(2).hz
+    n = H.shape[1]
+    kw = dict(max_iter=5, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=5)
+    rng = np.random.default_rng(5)
+    B = 48
+    probs = rng.uniform(0.01, 0.2, size=(B, n))
+    probs[:, ::7] = 0.0          # exact zeros occur in the x->z update (css_decode_sim.py:218-219)
+    _, syn = random_syndromes(H, 0.08, B, seed=9)
+    d = BpOsdDecoder(H, error_rate=0.08, **kw)
+    with np.errstate(divide="ignore"):
+        pri = torch.tensor(np.log((1 - probs) / probs), device="cuda", dtype=torch.float64)
+        wts = torch.tensor(np.log(1 / probs), device="cuda", dtype=torch.float64)
+    r = d.decode_batch(torch.tensor(syn, device="cuda"), priors=pri, weights=wts)
+    o = oracle_mod.OracleDecoder(H, error_rate=0.08, **kw)
+    nosd = 0
+    for b in range(B):
+        o.update_channel_probs(probs[b])
+        o.decode(syn[b])
+        nosd += 0 if o.converge else 1
+        assert (r.bp_decoding[b].cpu().numpy() == o.bp_decoding).all()
+        assert (r.osd0_decoding[b].cpu().numpy() == o.osd0_decoding).all()
+        assert (r.osdw_decoding[b].cpu().numpy() == o.osdw_decoding).all(), f"shot {b}"
+        assert bool(r.converge[b]) == o.converge and int(r.iter[b]) == o.iter
+    assert nosd > 10
+
+
+def test_host_buffer_pipeline(torch_cuda, oracle_mod, cfg_codes):
+    """decode_batch(numpy) cuts large batches into double-buffered chunks on two streams; results and
+    statistics must equal the single-launch device path."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(2).hz
+    B = 40000  # >= 2 x 16384 shots -> pipelined in 3 chunks
+    _, syn = random_syndromes(H, 0.06, B, seed=12)
+    d = BpOsdDecoder(H, error_rate=0.06, **MS_CS7)
+    rd = d.decode_batch(torch.tensor(syn, device="cuda"))
+    sd = d.stats()
+    for want_llr in (True, False):
+        rh = d.decode_batch(syn, return_llr=want_llr)
+        sh = d.stats()
+        assert sh["chunks"] == 3 and sh["shots"] == B
+        for k in ("bp_converged", "bp_iterations", "osd_invocations"):
+            assert sh[k] == sd[k]
+        assert (rh.osdw_decoding == rd.osdw_decoding.cpu().numpy()).all()
+        assert (rh.osd0_decoding == rd.osd0_decoding.cpu().numpy()).all()
+        assert (rh.bp_decoding == rd.bp_decoding.cpu().numpy()).all()
+        assert (rh.converge == rd.converge.cpu().numpy()).all()
+        assert (rh.iter == rd.iter.cpu().numpy()).all()
+        if want_llr:
+            assert (rh.log_prob_ratios == rd.log_prob_ratios.cpu().numpy()).all()
+    ref = oracle_mod.OracleDecoder(H, error_rate=0.06, **MS_CS7).decode_batch(syn[-2000:], want_llr=False)
+    assert (rh.osdw_decoding[-2000:] == ref["osdw"]).all()
