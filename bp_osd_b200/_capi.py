@@ -30,7 +30,7 @@ class Info(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "m", "n", "nnz", "rank", "k", "max_iter", "bp_method", "osd_method", "osd_order", "precision",
         "device", "bp_kernel", "bp_threads", "bp_ctas_per_sm", "bp_smem_bytes", "osd_threads",
-        "osd_smem_bytes", "sm_count", "osd_variant", "bp_layout_excess")] + [("ms_scaling_factor", C.c_double)]
+        "osd_smem_bytes", "sm_count", "osd_variant", "bp_layout_excess", "bp_cluster_size", "reserved")] + [("ms_scaling_factor", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -56,6 +56,7 @@ SIGNATURES = {
     "bposd_get_info": (C.c_int, [P, C.POINTER(Info)]),
     "bposd_get_stats": (C.c_int, [P, C.POINTER(Stats)]),
     "bposd_set_tuning": (C.c_int, [P, C.c_int32, C.c_int32, C.c_int64]),
+    "bposd_set_cluster_size": (C.c_int, [P, C.c_int32]),
     "bposd_set_osd_variant": (C.c_int, [P, C.c_int32, C.c_int64]),
     "bposd_last_error": (C.c_char_p, [P]),
     "bposd_version": (C.c_char_p, []),

@@ -1,6 +1,6 @@
 // bp_fast_kernel.cuh -- in-place shared-memory min-sum BP for sm_100a (rows a3-a8, bit-exact in fp64).
 //
-// One message array in shared memory, check-major with a fixed row stride DC: slot = prow*DC + kappa,
+// One message array in shared memory, check-major with a fixed row stride RS >= DC: slot = prow*RS + kappa,
 // where prow is the *physical* row the host layout pass assigned to a check and kappa its edge's
 // physical position in that row (min is order independent, so both are free; the host pass picks
 // them to make the bit-side gathers/scatters bank-conflict free, see fast_build).  A pass is two
@@ -55,6 +55,15 @@ static inline void fast_class(int max_col_deg, int max_row_deg, int *DC, int *DV
     else { *DC = 16; *DV = 8; }
 }
 
+// Row stride of the message array in elements.  A check's row is moved with 16-byte vector accesses by
+// the thread that owns it, so 8 consecutive rows must start in 8 different 16-byte bank groups: the
+// stride is padded to an odd number of 16-byte chunks (64-byte rows would be 4-way conflicted).
+// fp32 rows of 6 use 8-byte accesses and a 24-byte stride, which is conflict free as it is.
+__host__ __device__ constexpr int fast_row_stride(int DC, int elem_bytes) {
+    return (DC * elem_bytes) % 16 != 0 ? DC
+           : (((DC * elem_bytes) / 16) % 2 == 1 ? DC : DC + 16 / elem_bytes);
+}
+
 static inline void fast_free(FastTables &t) {
     cudaFree(t.d_vslot); cudaFree(t.d_cdeg); cudaFree(t.d_row_of); cudaFree(t.d_bit_of);
     t.d_vslot = nullptr; t.d_cdeg = nullptr; t.d_row_of = nullptr; t.d_bit_of = nullptr;
@@ -96,7 +105,7 @@ static inline int fast_default_threads(int n, int m) {
 // permutation and the in-row edge positions minimises the total number of wavefronts.
 // ---------------------------------------------------------------------------------------------
 struct LayoutOpt {
-    int m, n, DC, DV, nbanks, group;
+    int m, n, DC, DV, RS, nbanks, group;
     std::vector<int> prow;             // check -> physical row
     std::vector<int> kappa;            // CSR edge -> position inside its physical row
     std::vector<int> pos;              // bit -> position (thread tid = pos % T handles it in round pos / T)
@@ -105,7 +114,7 @@ struct LayoutOpt {
     std::vector<int> edge_col;         // CSR edge -> bit
     std::vector<int> hist;             // [group][bank] number of lanes of the group that hit the bank
     int group_of(int e) const { return (pos[edge_col[e]] / group) * DV + edge_k[e]; }
-    int bank_of(int e) const { return (prow[edge_row[e]] * DC + kappa[e]) % nbanks; }
+    int bank_of(int e) const { return (prow[edge_row[e]] * RS + kappa[e]) % nbanks; }
     int &cell(int e) { return hist[(size_t)group_of(e) * nbanks + bank_of(e)]; }
     // pair cost: sum over groups and banks of C(count, 2); moving one edge changes it by count differences
     long long remove(int e) { int &c = cell(e); c--; return -(long long)c; }
@@ -138,7 +147,7 @@ static inline LayoutResult fast_layout_search(int m, int n, int DC, int DV, int 
                                               const std::vector<int> &csc_slot) {
     const int E = row_ptr[m];
     LayoutOpt L;
-    L.m = m; L.n = n; L.DC = DC; L.DV = DV;
+    L.m = m; L.n = n; L.DC = DC; L.DV = DV; L.RS = fast_row_stride(DC, elem_bytes);
     L.group = elem_bytes == 8 ? 16 : 32; // lanes served together by one wavefront
     L.nbanks = L.group;                  // banks in units of the element size
     L.prow.resize(m); L.kappa.resize(E); L.edge_row.resize(E); L.edge_col.resize(E); L.edge_k.assign(E, 0); L.pos.resize(n);
@@ -225,7 +234,8 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
     fast_class(mc, mr, &t.DC, &t.DV);
     t.elem_bytes = elem_bytes;
     t.regular = (m > 0 && minr == t.DC && mr == t.DC && minc == t.DV && mc == t.DV) ? 1 : 0;
-    if ((long long)m * t.DC >= 0xFFFF || m == 0 || n >= 0xFFFF) { t.DC = 0; return cudaSuccess; } // slots and bits must fit in 16 bits
+    const int RS = fast_row_stride(t.DC, elem_bytes);
+    if ((long long)m * RS >= 0xFFFF || m == 0 || n >= 0xFFFF) { t.DC = 0; return cudaSuccess; } // slots and bits must fit in 16 bits
     // the search is deterministic; results are cached per (matrix, precision) for the life of the process
     static std::mutex mu;
     static std::map<std::string, LayoutResult> cache;
@@ -260,7 +270,7 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
         bitof[L.pos[j]] = (uint16_t)j;
         for (int q = col_ptr[j]; q < col_ptr[j + 1]; q++) {
             const int i = row_idx[q], e = csc_slot[q];
-            vs[(size_t)L.pos[j] * t.DV + (q - col_ptr[j])] = (uint16_t)(L.prow[i] * t.DC + L.kappa[e]);
+            vs[(size_t)L.pos[j] * t.DV + (q - col_ptr[j])] = (uint16_t)(L.prow[i] * RS + L.kappa[e]);
         }
     }
     fast_free(t);
@@ -285,7 +295,7 @@ template <typename real>
 static inline size_t fast_smem_bytes(const FastTables &t, int n, int m) {
     if (t.DC == 0) return (size_t)1 << 40;
     // the message array doubles as the staging area of the per-shot results ([n] reals + [n] bytes)
-    size_t msgs = (std::max((size_t)m * t.DC * sizeof(real), (size_t)n * (sizeof(real) + 1)) + 15) / 16 * 16;
+    size_t msgs = (std::max((size_t)m * fast_row_stride(t.DC, (int)sizeof(real)) * sizeof(real), (size_t)n * (sizeof(real) + 1)) + 15) / 16 * 16;
     size_t meta = ((size_t)m + 15) / 16 * 16;
     size_t prior = ((size_t)n * sizeof(real) + 15) / 16 * 16; // copy of the priors when they are not uniform
     return msgs + meta + prior + 16;
@@ -336,6 +346,52 @@ __device__ __forceinline__ double with_sign_word(double x, uint32_t w) { return 
 __device__ __forceinline__ float with_sign_word(float, uint32_t w) { return __uint_as_float(w); }
 template <typename real> __device__ __forceinline__ real lt_min(real a, real b) { return (a < b) ? a : b; } // `if (a < t) t = a`
 
+// One check of the min-sum check sweep (row a4), in place on its DC-slot row.  `mt` is the check's meta
+// byte (bit 7 syndrome, bits 1-5 degree).
+template <typename real, int DC, bool REG>
+__device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alpha, uint32_t alpha_w) {
+    real v[DC], suf[DC];
+    uint32_t sw[DC];
+    RowIO<real, DC>::load(row, v);
+    uint32_t X = (mt & 0x80u) << 24;
+#pragma unroll
+    for (int k = 0; k < DC; k++) { sw[k] = sign_word(v[k]); X ^= sw[k]; v[k] = abs_bits(v[k]); }
+    // suffix minima first, then one running prefix minimum: out[k] = min(prefix before k, suffix after k)
+    suf[DC - 1] = v[DC - 1];
+#pragma unroll
+    for (int k = DC - 2; k >= 1; k--) suf[k] = lt_min(v[k], suf[k + 1]);
+    real out[DC];
+    real run = v[0];
+    out[0] = (DC > 1) ? suf[DC > 1 ? 1 : 0] : real_max<real>();
+#pragma unroll
+    for (int k = 1; k < DC - 1; k++) { out[k] = lt_min(suf[k + 1], run); run = lt_min(v[k], run); }
+    if (DC > 1) out[DC - 1] = run;
+    const real all_min = (DC > 1) ? lt_min(v[DC - 1], run) : v[0];
+    if (all_min == (real)0) {
+        // some message is +-0: "<= 0" counts +0 as negative, the sign bit does not -> exact path
+        // (the magnitudes are already in v; a zero magnitude with a clear sign bit is the +0 case)
+        int tot = (int)(mt >> 7);
+#pragma unroll
+        for (int k = 0; k < DC; k++) tot += ((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < DC; k++) {
+            const int sg = tot + (((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0);
+            out[k] = out[k] * ((sg & 1) ? -alpha : alpha);
+        }
+    } else {
+        // sign of edge k = syndrome ^ (parity of all sign bits) ^ own sign bit; fold it into alpha
+        const uint32_t XA = (X & 0x80000000u) ^ alpha_w;
+#pragma unroll
+        for (int k = 0; k < DC; k++) out[k] = out[k] * with_sign_word(alpha, XA ^ (sw[k] & 0x80000000u));
+    }
+    if (!REG) {
+        const int deg = (mt >> 1) & 0x1f;
+#pragma unroll
+        for (int k = 0; k < DC; k++) out[k] = (k < deg) ? out[k] : real_max<real>();
+    }
+    RowIO<real, DC>::store(row, out);
+}
+
 template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
 __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
                                                        const uint8_t *__restrict__ cdeg_tab,
@@ -345,7 +401,8 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
     const int m = a.g.m, n = a.g.n;
     const int tid = threadIdx.x, T = blockDim.x;
     real *msg = reinterpret_cast<real *>(smem_raw);
-    const size_t msg_bytes = ((size_t)m * DC * sizeof(real) > (size_t)n * (sizeof(real) + 1) ? (size_t)m * DC * sizeof(real)
+    constexpr int RS = fast_row_stride(DC, (int)sizeof(real)); // row stride in elements (>= DC, see fast_row_stride)
+    const size_t msg_bytes = ((size_t)m * RS * sizeof(real) > (size_t)n * (sizeof(real) + 1) ? (size_t)m * RS * sizeof(real)
                                                                                              : (size_t)n * (sizeof(real) + 1));
     uint8_t *meta = smem_raw + (msg_bytes + 15) / 16 * 16; // bit0 mismatch, bits1-5 degree, bit7 syndrome
     unsigned *meta32 = reinterpret_cast<unsigned *>(meta);
@@ -388,7 +445,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             meta[p] = (uint8_t)(s | (deg << 1) | (s << 7));
             if (!REG) // absent slots of short rows hold +max: neutral for min and sign (the result staging
                       // of the previous shot overwrote the array, so they are set again for every shot)
-                for (int k = (int)deg; k < DC; k++) msg[p * DC + k] = real_max<real>();
+                for (int k = (int)deg; k < DC; k++) msg[p * RS + k] = real_max<real>();
         }
         real llr[VPT];
         unsigned dprev = 0;
@@ -422,46 +479,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
                 const unsigned mt = meta[p];
                 if (mt & 1u) ok = false;
                 if (last) continue;
-                real v[DC], suf[DC];
-                uint32_t sw[DC];
-                RowIO<real, DC>::load(msg + (size_t)p * DC, v);
-                uint32_t X = (mt & 0x80u) << 24;
-#pragma unroll
-                for (int k = 0; k < DC; k++) { sw[k] = sign_word(v[k]); X ^= sw[k]; v[k] = abs_bits(v[k]); }
-                // suffix minima first, then one running prefix minimum: out[k] = min(prefix before k, suffix after k)
-                suf[DC - 1] = v[DC - 1];
-#pragma unroll
-                for (int k = DC - 2; k >= 1; k--) suf[k] = lt_min(v[k], suf[k + 1]);
-                real out[DC];
-                real run = v[0];
-                out[0] = (DC > 1) ? suf[DC > 1 ? 1 : 0] : real_max<real>();
-#pragma unroll
-                for (int k = 1; k < DC - 1; k++) { out[k] = lt_min(suf[k + 1], run); run = lt_min(v[k], run); }
-                if (DC > 1) out[DC - 1] = run;
-                const real all_min = (DC > 1) ? lt_min(v[DC - 1], run) : v[0];
-                if (all_min == (real)0) {
-                    // some message is +-0: "<= 0" counts +0 as negative, the sign bit does not -> exact path
-                    // (the magnitudes are already in v; a zero magnitude with a clear sign bit is the +0 case)
-                    int tot = (int)(mt >> 7);
-#pragma unroll
-                    for (int k = 0; k < DC; k++) tot += ((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0;
-#pragma unroll
-                    for (int k = 0; k < DC; k++) {
-                        const int sg = tot + (((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0);
-                        out[k] = out[k] * ((sg & 1) ? -alpha : alpha);
-                    }
-                } else {
-                    // sign of edge k = syndrome ^ (parity of all sign bits) ^ own sign bit; fold it into alpha
-                    const uint32_t XA = (X & 0x80000000u) ^ alpha_w;
-#pragma unroll
-                    for (int k = 0; k < DC; k++) out[k] = out[k] * with_sign_word(alpha, XA ^ (sw[k] & 0x80000000u));
-                }
-                if (!REG) {
-                    const int deg = (mt >> 1) & 0x1f;
-#pragma unroll
-                    for (int k = 0; k < DC; k++) out[k] = (k < deg) ? out[k] : real_max<real>();
-                }
-                RowIO<real, DC>::store(msg + (size_t)p * DC, out);
+                fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w);
             }
             const int all_ok = __syncthreads_and(ok ? 1 : 0);
             if (it > 1 && all_ok) { conv = true; iters = it - 1; break; }
@@ -501,7 +519,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
 #pragma unroll
                         for (int k = 0; k < DV; k++)
                             if (REG || k < dj[r]) {
-                                const unsigned p = off[r][k] / (unsigned)(DC * sizeof(real));
+                                const unsigned p = off[r][k] / (unsigned)(RS * sizeof(real));
                                 atomicXor(&meta32[p >> 2], 1u << ((p & 3u) * 8u));
                             }
                     }

@@ -7,6 +7,7 @@
 #include "../../include/bposd_b200.h"
 #include "bposd_kernels.cuh"
 #include "bp_fast_kernel.cuh"
+#include "bp_cluster_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -33,6 +34,9 @@ struct bposd_handle {
     int uniform = 0, uniform_prior = 0;
     // fast-kernel tables
     FastTables fast;
+    // cluster-kernel tables (built on demand, when the messages exceed one SM's shared memory)
+    ClusterTables clus;
+    int clus_nclusters = 0;
     // Two decode slots: each owns its control words, failed-shot workspace, staging buffers, events and
     // (for the host-buffer pipeline) a stream, so chunk i+1 can be copied in while chunk i decodes.
     struct Slot {
@@ -70,7 +74,7 @@ struct bposd_handle {
     uint32_t *d_osdl_mask = nullptr;
     int *d_osdl_order = nullptr, *d_osdl_piv_row = nullptr, *d_osdl_piv_pos = nullptr, *d_osdl_pstart = nullptr;
     int osdl_alloc_grid = 0;
-    int force_kernel = 0, force_threads = 0;
+    int force_kernel = 0, force_threads = 0, force_cluster = 0;
     bool geometry_ready = false;
     // harness
     uint32_t *d_t1 = nullptr, *d_t2 = nullptr, *d_t3 = nullptr;
@@ -184,8 +188,47 @@ static int plan_geometry_t(bposd_handle *h) {
         kernel = 0; smem = (size_t)m + 16;
     }
     if (want == 0) { kernel = 0; smem = (size_t)m + 16; }
+    // cluster kernel: min-sum, supported degrees, and either forced or nothing smem-resident fits
+    if ((want == 3 || (want < 0 && kernel == 0)) && fast_supported(h->max_col_deg, h->max_row_deg, h->bp_method) && m > 0) {
+        int DCc = 0, DVc = 0;
+        fast_class(h->max_col_deg, h->max_row_deg, &DCc, &DVc);
+        // candidate cluster sizes: those whose per-CTA slice fits in shared memory, preferring CTAs of at most
+        // 512 threads (128 registers per thread: the fp64 row code spills below that), then the smaller cluster
+        std::vector<int> cand;
+        for (int pass = 0; pass < 2; pass++)
+            for (int c : {2, 4, 8, 16}) {
+                if (h->force_cluster > 0 && c != h->force_cluster) continue;
+                const int rpc = (m + c - 1) / c, bpc = (n + c - 1) / c;
+                const int need_t = ((bpc + 7) / 8 + 31) / 32 * 32;
+                if (cluster_smem_bytes<real>(DCc, rpc, bpc, true) > (size_t)h->smem_optin || need_t > 1024) continue;
+                if ((pass == 0) == (need_t <= 512)) cand.push_back(c);
+            }
+        bool done = false;
+        for (int CL : cand) {
+            if (h->clus.CL != CL || h->clus.elem_bytes != (int)rs) {
+                cudaError_t e = cluster_build(h->clus, CL, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot, (int)rs);
+                if (e != cudaSuccess) return fail(h, BPOSD_ECUDA, std::string("cluster_build: ") + cudaGetErrorString(e));
+            }
+            const int min_t = std::max(32, ((h->clus.bits_per_cta + 7) / 8 + 31) / 32 * 32);
+            const int ct = h->force_threads > 0 ? std::max(h->force_threads, min_t) : min_t;
+            const size_t csmem = cluster_smem_bytes<real>(h->clus.DC, h->clus.rows_per_cta, h->clus.bits_per_cta, true);
+            int ncl = 0;
+            cudaError_t e = ct <= 1024 ? cluster_prepare<real>(h->clus, ct, csmem, &ncl) : cudaErrorInvalidConfiguration;
+            if (e == cudaSuccess && ncl >= 1) {
+                h->bp_kernel = 3; h->bp_threads = ct; h->bp_smem = (int)csmem; h->bp_ctas_per_sm = 1;
+                h->clus_nclusters = ncl; h->bp_grid = ncl * CL;
+                kernel = 3;
+                done = true;
+                break;
+            }
+            cudaGetLastError();
+        }
+        if (!done && want == 3) return fail(h, BPOSD_EUNSUP, "the cluster BP kernel cannot be launched for this matrix / cluster size");
+    } else if (want == 3) return fail(h, BPOSD_EUNSUP, "the cluster BP kernel needs min-sum and row/column degrees up to 16/8");
     int occ = 0;
-    if (kernel == 2) {
+    if (kernel == 3) {
+        occ = 1;
+    } else if (kernel == 2) {
         threads = std::min(threads, fast_maxt(n));
         if (threads * fast_vpt(n) < n) threads = fast_default_threads(n, m);
         CU_TRY(h, fast_set_smem_t<real>(h->fast, n, smem));
@@ -198,11 +241,13 @@ static int plan_geometry_t(bposd_handle *h) {
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bp_generic_kernel<real, false>, threads, smem));
     }
     if (occ < 1) return fail(h, BPOSD_EUNSUP, "BP kernel does not fit on an SM");
-    h->bp_kernel = kernel;
-    h->bp_threads = threads;
-    h->bp_smem = (int)smem;
-    h->bp_ctas_per_sm = occ;
-    h->bp_grid = occ * h->sm_count;
+    if (kernel != 3) {
+        h->bp_kernel = kernel;
+        h->bp_threads = threads;
+        h->bp_smem = (int)smem;
+        h->bp_ctas_per_sm = occ;
+        h->bp_grid = occ * h->sm_count;
+    }
     if (kernel == 0) {
         const size_t per_cta = (2 * (size_t)E + n) * rs;
         const size_t need = per_cta * h->bp_grid;
@@ -262,6 +307,7 @@ extern "C" void bposd_destroy(bposd_t *h) {
     cudaFree(h->d_row_ptr); cudaFree(h->d_col_idx); cudaFree(h->d_col_ptr); cudaFree(h->d_row_idx); cudaFree(h->d_csc_slot);
     cudaFree(h->d_prior64); cudaFree(h->d_prior32); cudaFree(h->d_weight);
     fast_free(h->fast);
+    cluster_free(h->clus);
     for (auto &sl : h->slot) {
         cudaFree(sl.d_ctrl); cudaFree(sl.d_fail_list); cudaFree(sl.d_fail_llr);
         if (sl.h_ctrl) cudaFreeHost(sl.h_ctrl);
@@ -380,12 +426,21 @@ extern "C" int bposd_update_channel_probs(bposd_t *h, const double *probs) {
 
 extern "C" int bposd_set_tuning(bposd_t *h, int32_t kernel_plus1, int32_t threads, int64_t workspace_bytes) {
     if (!h) return BPOSD_EINVAL;
-    if (kernel_plus1 < 0 || kernel_plus1 > 3) return fail(h, BPOSD_EINVAL, "bp kernel selector out of range");
+    if (kernel_plus1 < 0 || kernel_plus1 > 4) return fail(h, BPOSD_EINVAL, "bp kernel selector out of range");
     if (threads < 0 || threads > 1024 || (threads % 32)) return fail(h, BPOSD_EINVAL, "threads must be a multiple of 32 up to 1024");
     CU_TRY(h, cudaSetDevice(h->device));
     h->force_kernel = kernel_plus1;
     h->force_threads = threads;
     if (workspace_bytes > 0) h->workspace_bytes = workspace_bytes;
+    return plan_geometry(h);
+}
+
+extern "C" int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size) {
+    if (!h) return BPOSD_EINVAL;
+    if (cluster_size != 0 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8 && cluster_size != 16)
+        return fail(h, BPOSD_EINVAL, "cluster size must be 0 (automatic), 2, 4, 8 or 16");
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->force_cluster = cluster_size;
     return plan_geometry(h);
 }
 
@@ -410,7 +465,9 @@ extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
     info->bp_smem_bytes = h->bp_smem; info->osd_threads = h->osd_threads; info->osd_smem_bytes = h->osd_smem;
     info->sm_count = h->sm_count; info->ms_scaling_factor = h->alpha;
     info->osd_variant = !h->osd_supported ? 0 : (h->osd_large ? 2 : 1);
-    info->bp_layout_excess = (int32_t)h->fast.conflicts_after;
+    info->bp_layout_excess = h->bp_kernel == 3 ? (int32_t)(1000 * h->clus.remote_edges / std::max<long long>(h->clus.total_edges, 1))
+                                               : (int32_t)h->fast.conflicts_after;
+    info->bp_cluster_size = h->bp_kernel == 3 ? h->clus.CL : 1;
     return BPOSD_OK;
 }
 
@@ -467,7 +524,10 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     a.g_dec = h->d_scratch_dec;
     const int grid = (int)std::min<long long>(Bc, h->bp_grid);
     CU_TRY(h, cudaEventRecord(sl.ev[0], st));
-    if (h->bp_kernel == 2) fast_launch<real>(h->fast, a, grid, h->bp_threads, h->bp_smem, st);
+    if (h->bp_kernel == 3) {
+        const int ncl = (int)std::min<long long>(Bc, h->clus_nclusters);
+        CU_TRY(h, cluster_launch<real>(h->clus, a, ncl, h->bp_threads, (size_t)h->bp_smem, st));
+    } else if (h->bp_kernel == 2) fast_launch<real>(h->fast, a, grid, h->bp_threads, h->bp_smem, st);
     else if (h->bp_kernel == 1) bp_generic_kernel<real, true><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
     else bp_generic_kernel<real, false><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
     CU_TRY(h, cudaGetLastError());

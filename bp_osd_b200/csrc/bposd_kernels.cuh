@@ -195,8 +195,12 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(BpArgs<real> a) {
                     for (int e = beg; e < end; e++) {
                         par ^= dec_s[g.col_idx[e]];
                         if (!last) {
+                            // tanh is evaluated once per edge: the value is parked in b2c[e], which the bit
+                            // sweep overwrites before anything reads it again
+                            const real th = r_tanh(b2c[e] / 2);
+                            b2c[e] = th;
                             c2b[e] = t;
-                            t *= r_tanh(b2c[e] / 2);
+                            t *= th;
                         }
                     }
                     if (it > 1 && par != synd_s[i]) ok = false;
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(BpArgs<real> a) {
                         for (int e = end - 1; e >= beg; e--) {
                             real x = c2b[e] * t;
                             c2b[e] = sgn * r_log((1 + x) / (1 - x));
-                            t *= r_tanh(b2c[e] / 2);
+                            t *= b2c[e];
                         }
                     }
                 }

@@ -170,9 +170,13 @@ class BpOsdDecoder:
         return {k: getattr(st, k) for k, _ in _capi.Stats._fields_}
 
     def set_tuning(self, bp_kernel=None, bp_threads=0, workspace_bytes=0):
-        """bp_kernel: None (auto), 0 generic/global, 1 generic/smem, 2 in-place smem."""
+        """bp_kernel: None (auto), 0 generic/global, 1 generic/smem, 2 in-place smem, 3 cluster DSMEM."""
         sel = 0 if bp_kernel is None else int(bp_kernel) + 1
         self._check(_capi.load().bposd_set_tuning(self._h, sel, int(bp_threads), int(workspace_bytes)))
+
+    def set_cluster_size(self, cluster_size=0):
+        """Thread-block-cluster size of BP kernel 3 (0 = smallest that fits, else 2, 4, 8 or 16)."""
+        self._check(_capi.load().bposd_set_cluster_size(self._h, int(cluster_size)))
 
     def set_osd_variant(self, variant=None, workspace_bytes=0):
         """variant: None (auto), 1 shared-memory OSD kernel, 2 HBM-resident OSD-0 kernel (large H)."""

@@ -61,11 +61,14 @@ typedef struct {
 typedef struct {
     int32_t m, n, nnz, rank, k;     /* k = n - rank                                      */
     int32_t max_iter, bp_method, osd_method, osd_order, precision, device;
-    int32_t bp_kernel;              /* 0 generic/global, 1 generic/smem, 2 in-place smem  */
+    int32_t bp_kernel;              /* 0 generic/global, 1 generic/smem, 2 in-place smem, 3 cluster DSMEM */
     int32_t bp_threads, bp_ctas_per_sm, bp_smem_bytes;
     int32_t osd_threads, osd_smem_bytes, sm_count;
     int32_t osd_variant;            /* 1 shared-memory OSD kernel, 2 HBM-resident OSD-0 kernel, 0 OSD unsupported */
-    int32_t bp_layout_excess;       /* shared-memory wavefronts per bit sweep above the conflict-free count (kernel 2) */
+    int32_t bp_layout_excess;       /* kernel 2: shared-memory wavefronts per bit sweep above the conflict-free count;
+                                       kernel 3: edges whose bit and check live in different CTAs, per mille */
+    int32_t bp_cluster_size;        /* CTAs per cluster of kernel 3, else 1 */
+    int32_t reserved;
     double ms_scaling_factor;
 } bposd_info_t;
 
@@ -169,6 +172,9 @@ int bposd_get_stats(const bposd_t *h, bposd_stats_t *stats);
 /* Tuning knobs (0 = keep automatic): BP kernel variant (+1 of bposd_info_t.bp_kernel),
  * threads per CTA, workspace bytes for the failed-shot LLR buffer. */
 int bposd_set_tuning(bposd_t *h, int32_t bp_kernel_plus1, int32_t bp_threads, int64_t workspace_bytes);
+/* Thread-block-cluster size of BP kernel variant 3 (messages split over the shared memory of 2, 4, 8 or
+ * 16 CTAs, reached through distributed shared memory); 0 = smallest size that fits. */
+int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size);
 /* OSD kernel variant: 0 automatic, 1 shared-memory kernel (row-operation matrix in shared memory,
  * OSD-0/E/CS), 2 HBM-resident left-looking kernel (OSD-0 only; chosen automatically when the matrix
  * does not fit in shared memory, BASELINE config 5).  workspace_bytes > 0 caps the HBM workspace

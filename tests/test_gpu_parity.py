@@ -64,7 +64,7 @@ def test_g1_readme_known_answer_on_gpu(torch_cuda):
 
 
 @pytest.mark.parametrize("name", golden_names())
-@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
 def test_golden_fixtures(torch_cuda, cfg_codes, name, kernel):
     g = load_golden(name)
     H = cfg_codes(g["cfg"]).hz
@@ -81,7 +81,7 @@ def test_golden_fixtures(torch_cuda, cfg_codes, name, kernel):
     (3, 0.06, 200, dict(MS_CS7, max_iter=30)),
     (4, 0.05, 300, dict(max_iter=20, bp_method="ms", ms_scaling_factor=0.9, osd_method="osd_e", osd_order=10)),
 ], ids=["d5", "d5-osd_e9", "hgp400", "hgp400-osd0", "hgp1922", "hgp1922-it30", "lp882-ms-e10"])
-@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
 def test_min_sum_bit_exact(torch_cuda, oracle_mod, cfg_codes, cfg, p, B, kw, kernel):
     H = cfg_codes(cfg).hz
     _, syn = random_syndromes(H, p, B, seed=12345)
@@ -384,7 +384,7 @@ def test_large_h_standin_selects_hbm_osd(torch_cuda, oracle_mod):
     ref = oracle_mod.OracleDecoder(H, error_rate=0.06, **kw).decode_batch(syn)
     nfail = int((~ref["converge"].astype(bool)).sum())
     assert nfail >= 8
-    for kernel in (None, 0):   # auto (shared-memory BP) and the HBM/L2-scratch BP used by config 5
+    for kernel in (None, 0, 3):   # auto (shared-memory BP), the HBM/L2-scratch BP and the cluster (DSMEM) BP of config 5
         d = BpOsdDecoder(H, error_rate=0.06, **kw)
         if kernel is not None:
             d.set_tuning(bp_kernel=kernel)
@@ -412,7 +412,8 @@ def test_config5_full_size(torch_cuda, oracle_mod, cfg_codes):
     _, syn = random_syndromes(H, p, 24, seed=8)
     d = BpOsdDecoder(H, error_rate=p, **kw)
     info = d.info()
-    assert info["bp_kernel"] == 0 and info["osd_variant"] == 2
+    # messages (1.07 MB in fp64) exceed one SM: the cluster kernel splits them over distributed shared memory
+    assert info["bp_kernel"] == 3 and info["bp_cluster_size"] in (8, 16) and info["osd_variant"] == 2
     r = d.decode_batch(torch.tensor(syn, device="cuda"))
     osd0 = r.osd0_decoding.cpu().numpy()
     conv = r.converge.cpu().numpy()
@@ -485,3 +486,57 @@ def test_host_buffer_pipeline(torch_cuda, oracle_mod, cfg_codes):
             assert (rh.log_prob_ratios == rd.log_prob_ratios.cpu().numpy()).all()
     ref = oracle_mod.OracleDecoder(H, error_rate=0.06, **MS_CS7).decode_batch(syn[-2000:], want_llr=False)
     assert (rh.osdw_decoding[-2000:] == ref["osdw"]).all()
+
+
+@pytest.mark.parametrize("cl", [2, 4, 8, 16])
+@pytest.mark.parametrize("precision", [64, 32])
+def test_cluster_kernel_sizes(torch_cuda, oracle_mod, cfg_codes, cl, precision):
+    """BP kernel 3 (messages split over a thread-block cluster, bit sweep through distributed shared memory)
+    forced on a code that also fits one CTA: every cluster size must reproduce the oracle bit for bit in fp64
+    and equal the single-CTA kernel in fp32 (same arithmetic, same order)."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(2).hz
+    _, syn = random_syndromes(H, 0.06, 1500, seed=31)
+    d = BpOsdDecoder(H, error_rate=0.06, precision=precision, **MS_CS7)
+    d.set_tuning(bp_kernel=3)
+    try:
+        d.set_cluster_size(cl)
+    except NotImplementedError:
+        pytest.skip(f"cluster size {cl} cannot be scheduled on this device")
+    info = d.info()
+    assert info["bp_kernel"] == 3 and info["bp_cluster_size"] == cl
+    r = d.decode_batch(torch.tensor(syn, device="cuda"))
+    out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
+               llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
+    if precision == 64:
+        ref = oracle_mod.OracleDecoder(H, error_rate=0.06, **MS_CS7).decode_batch(syn)
+        assert_exact(out, ref)
+    else:
+        d2 = BpOsdDecoder(H, error_rate=0.06, precision=32, **MS_CS7)
+        d2.set_tuning(bp_kernel=2)
+        r2 = d2.decode_batch(torch.tensor(syn, device="cuda"))
+        assert (out["llr"] == r2.log_prob_ratios.cpu().numpy()).all()
+        assert (out["osdw"] == r2.osdw_decoding.cpu().numpy()).all()
+        assert (out["iter"] == r2.iter.cpu().numpy()).all()
+
+
+def test_cluster_kernel_irregular_and_per_shot_priors(torch_cuda, oracle_mod):
+    """Irregular degrees (absent slots), a row count that does not divide the cluster size, non-uniform priors."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = hgp(codes.rep_code(7)).hz          # rows of weight 3-4, columns of weight 1-2; m = 42, n = 85
+    m, n = H.shape
+    kw = dict(max_iter=9, bp_method="ms", ms_scaling_factor=0.8, osd_method="osd_e", osd_order=4)
+    rng = np.random.default_rng(17)
+    probs = rng.uniform(0.02, 0.2, size=n)
+    _, syn = random_syndromes(H, 0.1, 800, seed=3)
+    ref = oracle_mod.OracleDecoder(H, channel_probs=probs, **kw).decode_batch(syn)
+    for cl in (2, 4, 8):
+        d = BpOsdDecoder(H, channel_probs=probs, **kw)
+        d.set_tuning(bp_kernel=3)
+        d.set_cluster_size(cl)
+        r = d.decode_batch(torch.tensor(syn, device="cuda"))
+        out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
+                   llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
+        assert_exact(out, ref)
