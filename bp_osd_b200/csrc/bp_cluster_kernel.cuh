@@ -152,8 +152,57 @@ __device__ __forceinline__ void st_dsmem_u32(uint32_t a, uint32_t v) { asm volat
 __device__ __forceinline__ void st_dsmem_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 __device__ __forceinline__ void xor_dsmem_u32(uint32_t a, uint32_t v) { asm volatile("red.shared::cluster.xor.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
-__global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, ClusterDev t) {
+// Register-frugal form of the check update (row a4) for CTAs of up to 1024 threads (64 registers each):
+// pass 1 streams the row once for (smallest, second smallest, position of the smallest, sign parity), pass 2
+// streams it again and overwrites every slot with "minimum over the other edges" = second smallest at the
+// position of the smallest, smallest elsewhere -- the same values as the prefix/suffix form of
+// fast_check_row (min is exact; on a tie both forms give the tied value).  "<= 0" counts zero as negative.
+template <typename real, int DC, bool REG>
+__device__ __forceinline__ void cluster_check_row(real *row, unsigned mt, real alpha) {
+    constexpr int CH = (sizeof(real) == 8) ? 2 : ((DC % 4 == 0) ? 4 : 2); // elements per vector access
+    real min1 = real_max<real>(), min2 = real_max<real>();
+    int arg = -1;
+    unsigned par = mt >> 7;
+    const int deg = REG ? DC : (int)((mt >> 1) & 0x1f);
+#pragma unroll
+    for (int k0 = 0; k0 < DC; k0 += CH) {
+        real v[CH];
+        RowIO<real, CH>::load(row + k0, v);
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const real av = abs_bits(v[u]);
+            par ^= (sign_word(v[u]) >> 31) | (av == (real)0 ? 1u : 0u);
+            if (av < min1) { min2 = min1; min1 = av; arg = k0 + u; }
+            else if (av < min2) min2 = av;
+        }
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < DC; k0 += CH) {
+        real v[CH], out[CH];
+        RowIO<real, CH>::load(row + k0, v);
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const unsigned neg = (sign_word(v[u]) >> 31) | (abs_bits(v[u]) == (real)0 ? 1u : 0u);
+            const real mag = (k0 + u == arg) ? min2 : min1;
+            out[u] = mag * (((par ^ neg) & 1u) ? -alpha : alpha);
+            if (!REG && k0 + u >= deg) out[u] = real_max<real>();
+        }
+        RowIO<real, CH>::store(row + k0, out);
+    }
+}
+
+template <typename real>
+__device__ __forceinline__ real slot_load(unsigned char *smem, uint32_t off, bool is_remote) {
+    return is_remote ? ld_dsmem(off, (real)0) : *reinterpret_cast<const real *>(smem + off);
+}
+template <typename real>
+__device__ __forceinline__ void slot_store(unsigned char *smem, uint32_t off, bool is_remote, real v) {
+    if (is_remote) st_dsmem(off, v);
+    else *reinterpret_cast<real *>(smem + off) = v;
+}
+
+template <typename real, int DC, int DV, int VPT, bool REG>
+__global__ void __launch_bounds__(1024, 1) bp_cluster_kernel(BpArgs<real> a, ClusterDev t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = a.g.m, n = a.g.n;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -169,10 +218,14 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
     const uint32_t msg_s = smem_u32(msg), meta_s = smem_u32(meta);
     const unsigned slots_per_cta = (unsigned)rpc * RS;
 
-    // cluster-window addresses of the slots of this thread's bits (shot independent)
+    // slots of this thread's bits (shot independent): a byte offset into this CTA's array for a local slot, a
+    // cluster-window address for a slot that lives in another CTA (bit r*DV+k of `remote`).  Local slots use
+    // plain ld/st.shared: the shared::cluster path is several times narrower than the SM's own shared-memory
+    // pipe (measured: ~17 B/clk per SM), so only the edges that really cross CTAs should take it.
     uint32_t off[VPT][DV];
     int dj[VPT];
     unsigned valid = 0;
+    unsigned long long remote = 0;
 #pragma unroll
     for (int r = 0; r < VPT; r++) {
         const int lq = tid + r * T;
@@ -185,7 +238,9 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
             const uint32_t s = have ? t.vslot[q * DV + k] : BPC_NONE;
             off[r][k] = 0;
             if (s != BPC_NONE) {
-                off[r][k] = mapa_u32(msg_s + (s % slots_per_cta) * (unsigned)sizeof(real), s / slots_per_cta);
+                const uint32_t owner = s / slots_per_cta, byte_off = (s % slots_per_cta) * (unsigned)sizeof(real);
+                if (owner == rank) off[r][k] = byte_off;
+                else { off[r][k] = mapa_u32(msg_s + byte_off, owner); remote |= 1ull << (r * DV + k); }
                 dj[r]++;
             }
         }
@@ -225,7 +280,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                 llr[r] = pj;
 #pragma unroll
                 for (int k = 0; k < DV; k++)
-                    if (REG || k < dj[r]) st_dsmem(off[r][k], pj);
+                    if (REG || k < dj[r]) slot_store<real>(smem_raw, off[r][k], (remote >> (r * DV + k)) & 1ull, pj);
             }
         }
         cluster_sync_all();
@@ -237,14 +292,13 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
             const bool last = it > a.max_iter;
             pow2 *= (real)0.5;
             const real alpha = (a.alpha0 == (real)0) ? (real)1 - pow2 : a.alpha0;
-            const uint32_t alpha_w = sign_word(alpha);
             bool ok = true;
             // ---- check sweep over this CTA's rows (a4) + local convergence vote for the previous pass (a7)
             for (int p = tid; p < rpc; p += T) {
                 const unsigned mt = meta[p];
                 if (mt & 1u) ok = false;
                 if (last) continue;
-                fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w);
+                cluster_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha);
             }
             const int cta_ok = __syncthreads_and(ok ? 1 : 0);
             if (tid < CL) st_dsmem_u32(mapa_u32(smem_u32(&sh_vote[it & 1][rank]), tid), (uint32_t)cta_ok);
@@ -256,7 +310,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
             // ---- bit sweep (a6 + a8) through distributed shared memory
             // remote loads take ~200 cycles: issue the gathers of four bits back to back before using any
             unsigned dnow = 0;
-            constexpr int BATCH = 4;
+            constexpr int BATCH = VPT < 4 ? VPT : 4;
 #pragma unroll
             for (int r0 = 0; r0 < VPT; r0 += BATCH) {
                 real c[BATCH][DV];
@@ -265,7 +319,8 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                     const int r = r0 + u;
 #pragma unroll
                     for (int k = 0; k < DV; k++)
-                        c[u][k] = (r < VPT && ((valid >> r) & 1u) && (REG || k < dj[r])) ? ld_dsmem(off[r][k], (real)0) : (real)0;
+                        c[u][k] = (r < VPT && ((valid >> r) & 1u) && (REG || k < dj[r]))
+                                      ? slot_load<real>(smem_raw, off[r][k], (remote >> (r * DV + k)) & 1ull) : (real)0;
                 }
 #pragma unroll
                 for (int u = 0; u < BATCH; u++) {
@@ -282,7 +337,8 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
 #pragma unroll
                         for (int k = DV - 1; k >= 0; k--)
                             if (REG || k < dj[r]) {
-                                st_dsmem(off[r][k], (REG && k == DV - 1) ? pre[k] : pre[k] + sfx);
+                                slot_store<real>(smem_raw, off[r][k], (remote >> (r * DV + k)) & 1ull,
+                                                 (REG && k == DV - 1) ? pre[k] : pre[k] + sfx);
                                 sfx = (REG && k == DV - 1) ? c[u][k] : sfx + c[u][k];
                             }
                     }
@@ -344,20 +400,31 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
 }
 
 // ---- dispatch ------------------------------------------------------------------------------------
-static inline int cluster_maxt(int threads) { return threads <= 256 ? 256 : (threads <= 512 ? 512 : (threads <= 768 ? 768 : 1024)); }
+// bits per thread: the smallest of {1, 2, 3, 4, 6, 8} that lets a CTA of <= 1024 threads cover its bits
+static inline int cluster_vpt(int bits_per_cta) {
+    for (int v : {1, 2, 3, 4, 6, 8})
+        if ((bits_per_cta + v - 1) / v <= 1024) return v;
+    return 0;
+}
+static inline int cluster_threads(int bits_per_cta) {
+    const int v = cluster_vpt(bits_per_cta);
+    return v ? std::max(32, ((bits_per_cta + v - 1) / v + 31) / 32 * 32) : 0;
+}
 
 #define BPOSD_CL_REG(EXPR) do { if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } while (0)
 #define BPOSD_CL_GEOM(DCv, DVv, EXPR)                                                            \
     do {                                                                                         \
-        constexpr int DC = DCv, DV = DVv, VPT = 8;                                               \
-        if (maxt__ == 256) { constexpr int MAXT = 256; BPOSD_CL_REG(EXPR); }                     \
-        else if (maxt__ == 512) { constexpr int MAXT = 512; BPOSD_CL_REG(EXPR); }                \
-        else if (maxt__ == 768) { constexpr int MAXT = 768; BPOSD_CL_REG(EXPR); }                \
-        else { constexpr int MAXT = 1024; BPOSD_CL_REG(EXPR); }                                  \
+        constexpr int DC = DCv, DV = DVv;                                                        \
+        if (vpt__ == 1) { constexpr int VPT = 1; BPOSD_CL_REG(EXPR); }                           \
+        else if (vpt__ == 2) { constexpr int VPT = 2; BPOSD_CL_REG(EXPR); }                      \
+        else if (vpt__ == 3) { constexpr int VPT = 3; BPOSD_CL_REG(EXPR); }                      \
+        else if (vpt__ == 4) { constexpr int VPT = 4; BPOSD_CL_REG(EXPR); }                      \
+        else if (vpt__ == 6) { constexpr int VPT = 6; BPOSD_CL_REG(EXPR); }                      \
+        else { constexpr int VPT = 8; BPOSD_CL_REG(EXPR); }                                      \
     } while (0)
-#define BPOSD_CL_DISPATCH(t, threads, EXPR)                                                      \
+#define BPOSD_CL_DISPATCH(t, EXPR)                                                               \
     do {                                                                                         \
-        const int maxt__ = cluster_maxt(threads);                                                \
+        const int vpt__ = cluster_vpt(t.bits_per_cta);                                           \
         const bool reg__ = t.regular != 0;                                                       \
         if (t.DC == 4) BPOSD_CL_GEOM(4, 2, EXPR);                                                \
         else if (t.DC == 6) BPOSD_CL_GEOM(6, 3, EXPR);                                           \
@@ -368,8 +435,8 @@ static inline int cluster_maxt(int threads) { return threads <= 256 ? 256 : (thr
 template <typename real>
 static inline cudaError_t cluster_prepare(const ClusterTables &t, int threads, size_t smem, int *max_clusters) {
     cudaError_t e = cudaSuccess;
-    BPOSD_CL_DISPATCH(t, threads, {
-        auto kern = (bp_cluster_kernel<real, DC, DV, VPT, MAXT, REG>);
+    BPOSD_CL_DISPATCH(t, {
+        auto kern = (bp_cluster_kernel<real, DC, DV, VPT, REG>);
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess && t.CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e == cudaSuccess) {
@@ -392,14 +459,14 @@ static inline cudaError_t cluster_launch(const ClusterTables &t, const BpArgs<re
     d.vslot = t.d_vslot; d.cdeg = t.d_cdeg; d.row_of = t.d_row_of; d.bit_of = t.d_bit_of;
     d.rows_per_cta = t.rows_per_cta; d.bits_per_cta = t.bits_per_cta; d.CL = t.CL;
     cudaError_t e = cudaSuccess;
-    BPOSD_CL_DISPATCH(t, threads, {
+    BPOSD_CL_DISPATCH(t, {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(nclusters * t.CL, 1, 1); cfg.blockDim = dim3(threads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = t.CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, bp_cluster_kernel<real, DC, DV, VPT, MAXT, REG>, a, d);
+        e = cudaLaunchKernelEx(&cfg, bp_cluster_kernel<real, DC, DV, VPT, REG>, a, d);
     });
     return e;
 }

@@ -192,28 +192,25 @@ static int plan_geometry_t(bposd_handle *h) {
     if ((want == 3 || (want < 0 && kernel == 0)) && fast_supported(h->max_col_deg, h->max_row_deg, h->bp_method) && m > 0) {
         int DCc = 0, DVc = 0;
         fast_class(h->max_col_deg, h->max_row_deg, &DCc, &DVc);
-        // candidate cluster sizes: those whose per-CTA slice fits in shared memory, preferring CTAs of at most
-        // 512 threads (128 registers per thread: the fp64 row code spills below that), then the smaller cluster
+        // candidate cluster sizes: the smallest cluster whose per-CTA slice fits in shared memory first (fewer remote
+        // edges, more shots in flight), larger ones as fall-backs if the device cannot schedule it
         std::vector<int> cand;
-        for (int pass = 0; pass < 2; pass++)
-            for (int c : {2, 4, 8, 16}) {
-                if (h->force_cluster > 0 && c != h->force_cluster) continue;
-                const int rpc = (m + c - 1) / c, bpc = (n + c - 1) / c;
-                const int need_t = ((bpc + 7) / 8 + 31) / 32 * 32;
-                if (cluster_smem_bytes<real>(DCc, rpc, bpc, true) > (size_t)h->smem_optin || need_t > 1024) continue;
-                if ((pass == 0) == (need_t <= 512)) cand.push_back(c);
-            }
+        for (int c : {2, 4, 8, 16}) {
+            if (h->force_cluster > 0 && c != h->force_cluster) continue;
+            const int rpc = (m + c - 1) / c, bpc = (n + c - 1) / c;
+            if (cluster_smem_bytes<real>(DCc, rpc, bpc, true) > (size_t)h->smem_optin || cluster_vpt(bpc) == 0) continue;
+            cand.push_back(c);
+        }
         bool done = false;
         for (int CL : cand) {
             if (h->clus.CL != CL || h->clus.elem_bytes != (int)rs) {
                 cudaError_t e = cluster_build(h->clus, CL, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot, (int)rs);
                 if (e != cudaSuccess) return fail(h, BPOSD_ECUDA, std::string("cluster_build: ") + cudaGetErrorString(e));
             }
-            const int min_t = std::max(32, ((h->clus.bits_per_cta + 7) / 8 + 31) / 32 * 32);
-            const int ct = h->force_threads > 0 ? std::max(h->force_threads, min_t) : min_t;
+            const int ct = cluster_threads(h->clus.bits_per_cta);
             const size_t csmem = cluster_smem_bytes<real>(h->clus.DC, h->clus.rows_per_cta, h->clus.bits_per_cta, true);
             int ncl = 0;
-            cudaError_t e = ct <= 1024 ? cluster_prepare<real>(h->clus, ct, csmem, &ncl) : cudaErrorInvalidConfiguration;
+            cudaError_t e = (ct > 0 && ct <= 1024) ? cluster_prepare<real>(h->clus, ct, csmem, &ncl) : cudaErrorInvalidConfiguration;
             if (e == cudaSuccess && ncl >= 1) {
                 h->bp_kernel = 3; h->bp_threads = ct; h->bp_smem = (int)csmem; h->bp_ctas_per_sm = 1;
                 h->clus_nclusters = ncl; h->bp_grid = ncl * CL;

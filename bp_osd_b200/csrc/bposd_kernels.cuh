@@ -64,6 +64,12 @@ __device__ __forceinline__ double ms_alpha(double alpha0, int it) {
 __device__ __forceinline__ float ms_alpha(float alpha0, int it) {
     return alpha0 == 0.0f ? 1.0f - ldexpf(1.0f, -it) : alpha0;
 }
+// Product-sum in fp32 (fast mode only): a product of tanh values rounds to exactly +-1 once every incoming
+// message exceeds ~17, and log((1+x)/(1-x)) then returns +-inf, which turns the next bit sums into NaN.
+// The fast mode keeps x one ulp inside (-1, 1), i.e. caps a check message at log(2^25) ~ 17.3.  The fp64
+// mode applies no clipping, exactly like the reference (row a5).
+__device__ __forceinline__ double ps_clamp(double x) { return x; }
+__device__ __forceinline__ float ps_clamp(float x) { return fminf(fmaxf(x, -0.99999994f), 0.99999994f); }
 __device__ __forceinline__ double r_tanh(double x) { return tanh(x); }
 __device__ __forceinline__ float r_tanh(float x) { return tanhf(x); }
 __device__ __forceinline__ double r_log(double x) { return log(x); }
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(BpArgs<real> a) {
                         t = 1;
                         const real sgn = synd_s[i] ? (real)-1 : (real)1;
                         for (int e = end - 1; e >= beg; e--) {
-                            real x = c2b[e] * t;
+                            real x = ps_clamp(c2b[e] * t);
                             c2b[e] = sgn * r_log((1 + x) / (1 - x));
                             t *= b2c[e];
                         }
