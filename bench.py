@@ -116,9 +116,11 @@ def _cpu_work(args):
     ex, _ = sample_errors(SEED, shot0, shots, z, np.full(_W["n"], CFG["p"]), z)
     s = dec.syndrome(ex)
     t = time.perf_counter()
+    x0, n0 = dec.totals
     out = dec.decode_batch(s, want_llr=False)
     dt = time.perf_counter() - t
-    return shots, dt, int(out["converge"].sum())
+    x1, n1 = dec.totals
+    return shots, dt, int(out["converge"].sum()), x1 - x0, n1 - n0
 
 
 class CpuArm:
@@ -132,6 +134,8 @@ class CpuArm:
         t = time.perf_counter()
         res = self.pool.map(_cpu_work, jobs)
         wall = time.perf_counter() - t
+        self.elim_wordxors = sum(r[3] for r in res)   # algorithmic elimination ops counted by the oracle
+        self.osd_shots = sum(r[4] for r in res)
         return sum(r[0] for r in res), wall
 
     def close(self):
@@ -345,6 +349,17 @@ def run_gpu(args):
             arm.step(0, 50)
             nshots, wall = arm.step(10**6, args.cpu_shots_per_core)
             arm.close()
+            if arm.osd_shots:
+                # OSD roofline: algorithmic 32-bit word ops per OSD shot = bit-packed elimination word
+                # XORs as counted by the oracle on this sample + candidates x (XOR + POPC) x ceil(rank/32)
+                ncand = info["k"] + CFG["osd_order"] * (CFG["osd_order"] - 1) // 2
+                ops_shot = arm.elim_wordxors / arm.osd_shots + ncand * 2 * ((info["rank"] + 31) // 32)
+                peak_ops = dec.int32_peak()
+                ach = ops_shot * (osd_inv / args.steps) / (ms_osd / args.steps * 1e-3) if ms_osd > 0 else None
+                roofline["osd"] = {"bound": "int32 alu (LOP3)", "achieved": ach, "peak": peak_ops, "unit": "ops/s",
+                                   "frac": ach / peak_ops if ach else None,
+                                   "algorithmic_ops_per_osd_shot": ops_shot, "osd_shots_sampled": arm.osd_shots,
+                                   "note": "peak = LOP3 microbenchmark in this run; ops per shot from the oracle's count"}
             cpu_baseline = {"value": nshots / wall, "unit": "shots/s", "cores": arm.cores, "kind": "port",
                             "sample": f"{args.cpu_shots_per_core} shots/core x {arm.cores} cores of the same workload, "
                                       "oracle/bposd_oracle.c (restatement of ldpc v2; ldpc not installable offline)"}

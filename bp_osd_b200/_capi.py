@@ -56,6 +56,7 @@ SIGNATURES = {
     "bposd_get_info": (C.c_int, [P, C.POINTER(Info)]),
     "bposd_get_stats": (C.c_int, [P, C.POINTER(Stats)]),
     "bposd_set_tuning": (C.c_int, [P, C.c_int32, C.c_int32, C.c_int64]),
+    "bposd_int32_peak": (C.c_int, [P, C.POINTER(C.c_double)]),
     "bposd_set_cluster_size": (C.c_int, [P, C.c_int32]),
     "bposd_set_osd_variant": (C.c_int, [P, C.c_int32, C.c_int64]),
     "bposd_last_error": (C.c_char_p, [P]),

@@ -83,8 +83,15 @@ constexpr int kCheckUnroll = BPOSD_CHECK_UNROLL; // rows of the check sweep inte
 #ifndef BPOSD_REGCAP32
 #define BPOSD_REGCAP32 64
 #endif
-static inline int fast_vpt(int n) { return n <= 256 ? 2 : 8; }
-static inline int fast_maxt(int n) { return n <= 256 ? 128 : (n <= 2048 ? 256 : (n <= 4096 ? 512 : 1024)); }
+// the 256 < n <= 2048 class (the bench code) can be re-tuned at build time: bits per thread, CTA size cap
+#ifndef BPOSD_MID_VPT
+#define BPOSD_MID_VPT 8
+#endif
+#ifndef BPOSD_MID_MAXT
+#define BPOSD_MID_MAXT 256
+#endif
+static inline int fast_vpt(int n) { return n <= 256 ? 2 : (n <= 2048 ? BPOSD_MID_VPT : 8); }
+static inline int fast_maxt(int n) { return n <= 256 ? 128 : (n <= 2048 ? BPOSD_MID_MAXT : (n <= 4096 ? 512 : 1024)); }
 template <typename real, int MAXT> constexpr int fast_minb() {
     constexpr int cap = sizeof(real) == 8 ? BPOSD_REGCAP64 : BPOSD_REGCAP32;
     return (65536 / (MAXT * cap)) < 1 ? 1 : (65536 / (MAXT * cap));
@@ -578,7 +585,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
     do {                                                                                         \
         constexpr int DC = DCv, DV = DVv;                                                        \
         if (maxt__ == 128) { constexpr int VPT = 2, MAXT = 128; BPOSD_FAST_REG(EXPR); }          \
-        else if (maxt__ == 256) { constexpr int VPT = 8, MAXT = 256; BPOSD_FAST_REG(EXPR); }     \
+        else if (maxt__ == BPOSD_MID_MAXT) { constexpr int VPT = BPOSD_MID_VPT, MAXT = BPOSD_MID_MAXT; BPOSD_FAST_REG(EXPR); } \
         else if (maxt__ == 512) { constexpr int VPT = 8, MAXT = 512; BPOSD_FAST_REG(EXPR); }     \
         else { constexpr int VPT = 8, MAXT = 1024; BPOSD_FAST_REG(EXPR); }                       \
     } while (0)

@@ -432,6 +432,30 @@ extern "C" int bposd_set_tuning(bposd_t *h, int32_t kernel_plus1, int32_t thread
     return plan_geometry(h);
 }
 
+extern "C" int bposd_int32_peak(bposd_t *h, double *ops_per_s) {
+    if (!h || !ops_per_s) return BPOSD_EINVAL;
+    CU_TRY(h, cudaSetDevice(h->device));
+    uint32_t *d_out = nullptr;
+    CU_TRY(h, cudaMalloc((void **)&d_out, 4));
+    const int iters = 1 << 16, grid = h->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CU_TRY(h, cudaEventCreate(&e0));
+    CU_TRY(h, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) { // first repetition warms up
+        CU_TRY(h, cudaEventRecord(e0, nullptr));
+        lop3_peak_kernel<<<grid, threads>>>(d_out, iters);
+        CU_TRY(h, cudaEventRecord(e1, nullptr));
+        CU_TRY(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *ops_per_s = 8.0 * iters * (double)grid * threads / (best * 1e-3);
+    return BPOSD_OK;
+}
+
 extern "C" int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size) {
     if (!h) return BPOSD_EINVAL;
     if (cluster_size != 0 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8 && cluster_size != 16)

@@ -351,43 +351,60 @@ __global__ void __launch_bounds__(1024) osd_kernel(OsdArgs<real> a) {
         // of the T columns named by the rows of c; a pivot row p is the lowest unused row set in
         // it; the row operation "rows i in v\{p} += row p" is, column by column of T,
         // "if bit p of Tc[r] then Tc[r] ^= v\{p}".
+        // Pivot search is speculative and parallel: every warp reduces one of the next nwarps columns against the
+        // current T; the first of them (in sorted order) that has a 1 in an unused row is the next pivot, the ones
+        // before it are dependent columns for good (they were tested against the same T), the ones after it are
+        // simply tested again after the row operation.
         for (;;) {
-            if (warp == 0) {
-                int t = sh_t, rank = sh_rank, nnp = sh_nnp, found = 0, p = 0;
-                while (t < n && rank < maxrank) {
-                    const int c = order[t];
-                    int best = 0x7fffffff;
+            const int t0 = sh_t, rank0 = sh_rank, nnp0 = sh_nnp; // uniform: written before the last barrier
+            if (t0 >= n || rank0 >= maxrank) break;
+            const int lim = min(nwarps, n - t0);
+            {
+                int best = 0x7fffffff;
+                uint32_t *mine = wscr + (size_t)warp * (S + 64);
+                if (warp < lim) {
+                    const int c = order[t0 + warp];
                     for (int w = lane; w < S; w += 32) {
-                        uint32_t v = reduced_col_word(g, Tc, St, c, w);
-                        vmask[w] = v;
-                        uint32_t cand = v & ~used[w];
+                        const uint32_t v = reduced_col_word(g, Tc, St, c, w);
+                        mine[w] = v;
+                        const uint32_t cand = v & ~used[w];
                         if (cand && best == 0x7fffffff) best = w * 32 + __ffs(cand) - 1;
                     }
                     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-                    __syncwarp();
-                    if (best != 0x7fffffff) {
-                        p = best;
-                        if (lane == 0) {
-                            prow[c] = (uint16_t)p;
-                            used[p >> 5] |= 1u << (p & 31);
-                            vmask[p >> 5] &= ~(1u << (p & 31));
-                        }
-                        rank++; t++; found = 1;
-                        __syncwarp();
-                        break;
-                    }
-                    if (lane == 0) np[nnp] = (uint16_t)t;
-                    nnp++; t++;
                 }
-                if (lane == 0) { sh_found = found; sh_p = p; sh_t = t; sh_rank = rank; sh_nnp = nnp; }
+                if (lane == 0) red_c[warp] = best;
             }
             __syncthreads();
-            if (!sh_found) break;
-            const int p = sh_p, pw = p >> 5, pb = p & 31;
+            int wi = 0;
+            while (wi < lim && red_c[wi] == 0x7fffffff) wi++;
+            if (tid < wi) np[nnp0 + tid] = (uint16_t)(t0 + tid);
+            if (wi == lim) { // no pivot among these columns
+                if (tid == 0) { sh_t = t0 + lim; sh_nnp = nnp0 + lim; }
+                __syncthreads();
+                continue;
+            }
+            const int p = red_c[wi], pw = p >> 5, pb = p & 31;
+            const uint32_t *vm = wscr + (size_t)wi * (S + 64);
+            if (tid == 0) { // nobody reads these again before the barrier below
+                prow[order[t0 + wi]] = (uint16_t)p;
+                used[pw] |= 1u << pb;
+                sh_t = t0 + wi + 1; sh_rank = rank0 + 1; sh_nnp = nnp0 + wi;
+            }
+            const uint32_t keep = ~(1u << pb);
             for (int r = tid; r < m; r += T) {
                 uint32_t *col = Tc + (size_t)r * St;
-                if ((col[pw] >> pb) & 1u)
-                    for (int w = 0; w < S; w++) col[w] ^= vmask[w];
+                if ((col[pw] >> pb) & 1u) {
+                    int w = 0;
+                    for (; w + 4 <= S; w += 4) { // four independent read-modify-writes in flight
+                        const uint32_t c0 = col[w], c1 = col[w + 1], c2 = col[w + 2], c3 = col[w + 3];
+                        const uint32_t v0 = vm[w], v1 = vm[w + 1], v2 = vm[w + 2], v3 = vm[w + 3];
+                        col[w] = c0 ^ (w == pw ? v0 & keep : v0);
+                        col[w + 1] = c1 ^ (w + 1 == pw ? v1 & keep : v1);
+                        col[w + 2] = c2 ^ (w + 2 == pw ? v2 & keep : v2);
+                        col[w + 3] = c3 ^ (w + 3 == pw ? v3 & keep : v3);
+                    }
+                    for (; w < S; w++) col[w] ^= (w == pw ? vm[w] & keep : vm[w]);
+                }
             }
             __syncthreads();
         }
@@ -877,6 +894,22 @@ __global__ void __launch_bounds__(256) channel_update_kernel(const uint8_t *__re
         priors[i] = (real)(one ? prior1[j] : prior0[j]);
         if (weights) weights[i] = one ? w1[j] : w0[j];
     }
+}
+
+// INT32 logic-op calibration for the OSD roofline ("measure a LOP3 microbenchmark peak in the
+// same run"): eight independent LOP3 chains per thread, 8 * iters logic ops per thread.
+__global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t *out, int iters) {
+    uint32_t a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = threadIdx.x * 2654435761u + j * 40503u + blockIdx.x;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = a[j] ^ (a[(j + 1) & 7] & a[(j + 3) & 7]); // one LOP3 each
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r ^= a[j];
+    if (r == 0x12345678u) out[0] = r; // keeps the chains alive
 }
 
 struct CssSector {

@@ -174,6 +174,12 @@ class BpOsdDecoder:
         sel = 0 if bp_kernel is None else int(bp_kernel) + 1
         self._check(_capi.load().bposd_set_tuning(self._h, sel, int(bp_threads), int(workspace_bytes)))
 
+    def int32_peak(self) -> float:
+        """Measured LOP3 rate of the device in ops/s (denominator of the OSD roofline)."""
+        v = C.c_double()
+        self._check(_capi.load().bposd_int32_peak(self._h, C.byref(v)))
+        return float(v.value)
+
     def set_cluster_size(self, cluster_size=0):
         """Thread-block-cluster size of BP kernel 3 (0 = smallest that fits, else 2, 4, 8 or 16)."""
         self._check(_capi.load().bposd_set_cluster_size(self._h, int(cluster_size)))

@@ -172,6 +172,8 @@ int bposd_get_stats(const bposd_t *h, bposd_stats_t *stats);
 /* Tuning knobs (0 = keep automatic): BP kernel variant (+1 of bposd_info_t.bp_kernel),
  * threads per CTA, workspace bytes for the failed-shot LLR buffer. */
 int bposd_set_tuning(bposd_t *h, int32_t bp_kernel_plus1, int32_t bp_threads, int64_t workspace_bytes);
+/* Measured INT32 logic-op (LOP3) rate of the device in ops/s: the denominator of the OSD roofline. */
+int bposd_int32_peak(bposd_t *h, double *ops_per_s);
 /* Thread-block-cluster size of BP kernel variant 3 (messages split over the shared memory of 2, 4, 8 or
  * 16 CTAs, reached through distributed shared memory); 0 = smallest size that fits. */
 int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size);

@@ -50,6 +50,7 @@ typedef struct {
     int *order, *piv_col, *nonpiv;
     uint64_t *work;
     long stat_elim_wordxors;
+    long total_elim_wordxors, total_osd; /* accumulated over decodes (algorithmic-op count of SURVEY.md 8d) */
 } oracle_t;
 
 /* ------------------------------------------------------------------ helpers */
@@ -147,6 +148,8 @@ int oracle_converge(const oracle_t *o) { return o->converge; }
 int oracle_iter(const oracle_t *o) { return o->iter; }
 int oracle_osd_ran(const oracle_t *o) { return o->osd_ran; }
 long oracle_stat_elim_wordxors(const oracle_t *o) { return o->stat_elim_wordxors; }
+long oracle_total_elim_wordxors(const oracle_t *o) { return o->total_elim_wordxors; }
+long oracle_total_osd(const oracle_t *o) { return o->total_osd; }
 const double *oracle_llr(const oracle_t *o) { return o->llr; }
 const uint8_t *oracle_bp_decoding(const oracle_t *o) { return o->bp_dec; }
 const uint8_t *oracle_osd0_decoding(const oracle_t *o) { return o->osd0; }
@@ -325,6 +328,8 @@ static void osd_decode(oracle_t *o, const uint8_t *synd) {
         rank++;
     }
     o->stat_elim_wordxors = xors;
+    o->total_elim_wordxors += xors;
+    o->total_osd += 1;
     for (int t = 0; t < n; t++)
         if (!is_piv[t]) o->nonpiv[nnp++] = t; /* non-pivots keep sorted order */
 

@@ -43,7 +43,9 @@ def lib():
         for name in ("rank", "k", "converge", "iter", "osd_ran"):
             f = getattr(L, "oracle_" + name)
             f.restype, f.argtypes = C.c_int, [P]
-        L.oracle_stat_elim_wordxors.restype, L.oracle_stat_elim_wordxors.argtypes = C.c_long, [P]
+        for name in ("stat_elim_wordxors", "total_elim_wordxors", "total_osd"):
+            f = getattr(L, "oracle_" + name)
+            f.restype, f.argtypes = C.c_long, [P]
         for name in ("llr", "bp_decoding", "osd0_decoding", "osdw_decoding"):
             f = getattr(L, "oracle_" + name)
             f.restype, f.argtypes = P, [P]
@@ -164,6 +166,11 @@ class OracleDecoder:
     @property
     def elim_wordxors(self):
         return int(lib().oracle_stat_elim_wordxors(self._h))
+
+    @property
+    def totals(self):
+        """(32-bit word XORs spent in GF(2) elimination, OSD invocations) accumulated over all decodes."""
+        return int(lib().oracle_total_elim_wordxors(self._h)), int(lib().oracle_total_osd(self._h))
 
     def syndrome(self, errors):
         e = np.ascontiguousarray(errors, dtype=np.uint8).reshape(-1, self.n)
