@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbposd_b200.so")
 SOURCES = ["bposd_capi.cu"]
-DEPS = ["bposd_capi.cu", "bposd_kernels.cuh", "bp_fast_kernel.cuh", os.path.join("..", "..", "include", "bposd_b200.h")]
+DEPS = ["bposd_capi.cu", "bposd_kernels.cuh", "bp_fast_kernel.cuh", "bp_cluster_kernel.cuh", "osd_panel_kernel.cuh", os.path.join("..", "..", "include", "bposd_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -185,7 +185,7 @@ class BpOsdDecoder:
         self._check(_capi.load().bposd_set_cluster_size(self._h, int(cluster_size)))
 
     def set_osd_variant(self, variant=None, workspace_bytes=0):
-        """variant: None (auto), 1 shared-memory OSD kernel, 2 HBM-resident OSD-0 kernel (large H)."""
+        """variant: None (auto), 3 panel kernel, 1 T-matrix kernel, 2 HBM-resident OSD-0 kernel (large H)."""
         self._check(_capi.load().bposd_set_osd_variant(self._h, 0 if variant is None else int(variant),
                                                        int(workspace_bytes)))
 

@@ -64,7 +64,7 @@ typedef struct {
     int32_t bp_kernel;              /* 0 generic/global, 1 generic/smem, 2 in-place smem, 3 cluster DSMEM */
     int32_t bp_threads, bp_ctas_per_sm, bp_smem_bytes;
     int32_t osd_threads, osd_smem_bytes, sm_count;
-    int32_t osd_variant;            /* 1 shared-memory OSD kernel, 2 HBM-resident OSD-0 kernel, 0 OSD unsupported */
+    int32_t osd_variant;            /* 3 panel kernel, 1 T-matrix kernel, 2 HBM-resident OSD-0 kernel, 0 OSD unsupported */
     int32_t bp_layout_excess;       /* kernel 2: shared-memory wavefronts per bit sweep above the conflict-free count;
                                        kernel 3: edges whose bit and check live in different CTAs, per mille */
     int32_t bp_cluster_size;        /* CTAs per cluster of kernel 3, else 1 */
@@ -177,9 +177,11 @@ int bposd_int32_peak(bposd_t *h, double *ops_per_s);
 /* Thread-block-cluster size of BP kernel variant 3 (messages split over the shared memory of 2, 4, 8 or
  * 16 CTAs, reached through distributed shared memory); 0 = smallest size that fits. */
 int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size);
-/* OSD kernel variant: 0 automatic, 1 shared-memory kernel (row-operation matrix in shared memory,
- * OSD-0/E/CS), 2 HBM-resident left-looking kernel (OSD-0 only; chosen automatically when the matrix
- * does not fit in shared memory, BASELINE config 5).  workspace_bytes > 0 caps the HBM workspace
+/* OSD kernel variant: 0 automatic, 1 T-matrix kernel (m x m row-operation matrix in shared memory, one
+ * sweep per pivot; OSD-0/E/CS; the default when it fits), 3 panel kernel (pivot-block multiplier masks in
+ * shared memory, left-looking replay with four-Russians tables; OSD-0/E/CS; same results, currently slower),
+ * 2 HBM-resident left-looking kernel (OSD-0 only; chosen automatically when neither fits in shared memory,
+ * BASELINE config 5).  workspace_bytes > 0 caps the HBM workspace
  * of variant 2 (ceil(n/32) * m * 4 bytes per concurrently processed failed shot). */
 int bposd_set_osd_variant(bposd_t *h, int32_t variant, int64_t workspace_bytes);
 const char *bposd_last_error(const bposd_t *h);

@@ -540,3 +540,44 @@ def test_cluster_kernel_irregular_and_per_shot_priors(torch_cuda, oracle_mod):
         out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
                    llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
         assert_exact(out, ref)
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+@pytest.mark.parametrize("cfg,p,max_iter,osd_method,osd_order,nonuniform", [
+    (1, 0.12, 2, "osd0", 0, False),
+    (1, 0.12, 2, "osd_cs", 7, False),
+    (1, 0.12, 2, "osd_cs", 21, True),      # order == n - rank, non-uniform channel: ordered fp64 weights
+    (1, 0.12, 2, "osd_e", 9, False),
+    (1, 0.12, 2, "osd_e", 6, True),
+    (2, 0.08, 3, "osd_cs", 7, False),
+    (2, 0.08, 3, "osd_cs", 40, False),     # pairs reach into the second kept candidate panel
+    (2, 0.08, 3, "osd_cs", 36, True),
+    (2, 0.08, 3, "osd_e", 10, False),
+    (3, 0.06, 8, "osd_cs", 7, False),
+    (3, 0.06, 8, "osd_e", 5, True),
+])
+def test_osd_kernel_variants(torch_cuda, oracle_mod, cfg_codes, variant, cfg, p, max_iter, osd_method, osd_order, nonuniform):
+    """Both shared-memory OSD kernels (3: pivot-block panels, 1: T matrix) against the oracle: OSD-0, OSD-E, OSD-CS,
+    uniform and non-uniform channels, rank-deficient H (cfg 3), search depth beyond one panel."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(cfg).hz
+    n = H.shape[1]
+    kw = dict(max_iter=max_iter, bp_method="ms", ms_scaling_factor=0, osd_method=osd_method, osd_order=osd_order)
+    B = 300 if cfg < 3 else 120
+    _, syn = random_syndromes(H, p, B, seed=77)
+    if nonuniform:
+        probs = np.random.default_rng(9).uniform(0.5 * p, 1.5 * p, size=n)
+        ref = oracle_mod.OracleDecoder(H, channel_probs=probs, **kw).decode_batch(syn)
+        d = BpOsdDecoder(H, channel_probs=probs, **kw)
+    else:
+        ref = oracle_mod.OracleDecoder(H, error_rate=p, **kw).decode_batch(syn)
+        d = BpOsdDecoder(H, error_rate=p, **kw)
+    assert (~ref["converge"].astype(bool)).sum() > B // 4
+    d.set_osd_variant(variant)
+    assert d.info()["osd_variant"] == variant
+    r = d.decode_batch(torch.tensor(syn, device="cuda"))
+    bad0 = np.flatnonzero((r.osd0_decoding.cpu().numpy() != ref["osd0"]).any(1))
+    badw = np.flatnonzero((r.osdw_decoding.cpu().numpy() != ref["osdw"]).any(1))
+    assert bad0.size == 0, f"osd0 differs for shots {bad0[:10]}"
+    assert badw.size == 0, f"osdw differs for shots {badw[:10]}"
