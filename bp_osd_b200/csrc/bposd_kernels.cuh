@@ -297,7 +297,7 @@ __device__ __forceinline__ uint32_t reduced_col_word(const GraphDev &g, const ui
 }
 
 template <typename real>
-__global__ void __launch_bounds__(1024) osd_kernel(OsdArgs<real> a) {
+__global__ void __launch_bounds__(1024, 1) osd_kernel(OsdArgs<real> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GraphDev &g = a.g;
     const int m = g.m, n = g.n, S = a.S, St = a.St;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(1024) osd_kernel(OsdArgs<real> a) {
     uint16_t *order = reinterpret_cast<uint16_t *>(red_c + 32);                             // n
     uint16_t *prow = order + n;                                                             // n
     uint16_t *np = prow + n;                                                                // n
-    __shared__ int sh_found, sh_p, sh_t, sh_rank, sh_nnp, sh_best;
+    __shared__ int sh_found, sh_t, sh_rank, sh_nnp, sh_best;
 
     const int nfail = *a.fail_count;
     for (int f = blockIdx.x; f < nfail; f += gridDim.x) {

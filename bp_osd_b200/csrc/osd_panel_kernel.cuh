@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(1024) osd_panel_kernel(OsdPanelArgs<real> a) {
     uint8_t *s8 = reinterpret_cast<uint8_t *>(piv_pos + (size_t)nb * 32);                   // [m] transformed syndrome
     uint8_t *rowblk = s8 + m;                                                               // [m] block in which the check became a pivot
     uint8_t *linv_cnt = rowblk + m;                                                         // [nb] pivots Linv[b] was built for
-    __shared__ int sh_t, sh_rank, sh_nnp, sh_nblk, sh_cnt, sh_min[3], sh_best, sh_bestW;
+    __shared__ int sh_t, sh_rank, sh_nnp, sh_nblk, sh_cnt, sh_min[3], sh_best;
     __shared__ uint32_t Rk[32];
 
     // ---- replay every pivot block on the panel in P (block-wide; ends with a barrier) ----
