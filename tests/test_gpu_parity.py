@@ -581,3 +581,49 @@ def test_osd_kernel_variants(torch_cuda, oracle_mod, cfg_codes, variant, cfg, p,
     badw = np.flatnonzero((r.osdw_decoding.cpu().numpy() != ref["osdw"]).any(1))
     assert bad0.size == 0, f"osd0 differs for shots {bad0[:10]}"
     assert badw.size == 0, f"osdw differs for shots {badw[:10]}"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_parity_check_matrices(torch_cuda, oracle_mod, seed):
+    """Random sparse H with irregular degrees (empty rows and columns, weight up to 12 / 8), random channel,
+    random decoder settings: every BP kernel and both shared-memory OSD kernels against the oracle."""
+    from bp_osd_b200 import BpOsdDecoder
+    import scipy.sparse as sp
+    torch = torch_cuda
+    rng = np.random.default_rng(1000 + seed)
+    m, n = int(rng.integers(5, 60)), int(rng.integers(20, 140))
+    H = np.zeros((m, n), dtype=np.uint8)
+    for j in range(n):                                   # column weights 0..min(m, 6)
+        w = int(rng.integers(0, min(m, 6) + 1))
+        H[rng.choice(m, size=w, replace=False), j] = 1
+    heavy = np.flatnonzero(H.sum(1) > 12)                # keep rows within the specialised kernels' degree class
+    for i in heavy:
+        ones = np.flatnonzero(H[i])
+        H[i, rng.choice(ones, size=ones.size - 12, replace=False)] = 0
+    if seed % 2 == 0:
+        H[int(rng.integers(0, m))] = 0                   # an empty check
+    H = sp.csr_matrix(H)
+    probs = rng.uniform(0.01, 0.3, size=n)
+    if seed % 3 == 0:
+        probs[:] = 0.07
+    osd_method, osd_order = [("osd_cs", 5), ("osd_e", 4), ("osd0", 0)][seed % 3]
+    kw = dict(max_iter=int(rng.integers(1, 12)), bp_method="ms", ms_scaling_factor=[0, 0.625, 1.0][seed % 3],
+              osd_method=osd_method, osd_order=osd_order)
+    o = oracle_mod.OracleDecoder(H, channel_probs=probs, **kw)
+    if kw["osd_order"] > o.k:
+        kw["osd_order"] = o.k
+        o = oracle_mod.OracleDecoder(H, channel_probs=probs, **kw)
+    _, syn = random_syndromes(H, 0.1, 400, seed=seed)
+    ref = o.decode_batch(syn)
+    for kernel in (0, 1, 2, 3):
+        for variant in (1, 3):
+            d = BpOsdDecoder(H, channel_probs=probs, **kw)
+            d.set_tuning(bp_kernel=kernel)
+            d.set_osd_variant(variant)
+            r = d.decode_batch(torch.tensor(syn, device="cuda"))
+            out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
+                       llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
+            try:
+                assert_exact(out, ref)
+            except AssertionError as ex:
+                raise AssertionError(f"kernel {kernel} osd variant {variant} m={m} n={n}: {ex}")
