@@ -87,6 +87,8 @@ struct bposd_handle {
     unsigned long long *d_counters = nullptr; // 8 words
     int *d_minw = nullptr;
     double *d_cu_tab = nullptr; // channel-update tables [4, n]
+    uint8_t *h_stage = nullptr; // pinned staging of the small-batch host path (latency)
+    size_t stage_bytes = 1 << 20;
     bposd_stats_t stats{};
     std::string err;
 };
@@ -269,7 +271,7 @@ static int plan_geometry_t(bposd_handle *h) {
     h->osd_supported = osd_smem <= (size_t)h->smem_optin && n < 65535 && m < 65535;
     // HBM-resident OSD-0: used when T does not fit (or when forced), only for search depth 0
     h->osdl_npanels = (n + 31) / 32;
-    h->osdl_smem = (int)(4 * (size_t)m + 4096 + 256 + 2 * ((size_t)m + 2) + (size_t)m + 16);
+    h->osdl_smem = (int)(8 * (size_t)m + 4096 + 256 + 4 * ((size_t)h->osdl_npanels + 2) + 2 * ((size_t)m + 2) + (size_t)m + 16);
     const bool large_ok = h->osd_order == 0 && (size_t)h->osdl_smem <= (size_t)h->smem_optin && m < 65535;
     h->osd_large = large_ok && (h->osd_variant == 2 || (h->osd_variant == 0 && !h->osd_supported));
     if (h->osd_variant == 2 && !large_ok)
@@ -335,6 +337,7 @@ extern "C" void bposd_destroy(bposd_t *h) {
     cudaFree(h->d_osdl_mask); cudaFree(h->d_osdl_order); cudaFree(h->d_osdl_piv_row); cudaFree(h->d_osdl_piv_pos); cudaFree(h->d_osdl_pstart);
     cudaFree(h->d_t1); cudaFree(h->d_t2); cudaFree(h->d_t3); cudaFree(h->d_l_ptr); cudaFree(h->d_l_idx);
     cudaFree(h->d_counters); cudaFree(h->d_minw); cudaFree(h->d_cu_tab);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     delete h;
 }
 
@@ -755,6 +758,52 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
     if (need_ws) chunk = std::min(chunk, h->fail_cap);
     const int nslots = pipelined ? 2 : 1;
     h->stats = bposd_stats_t{};
+    // Small batches (single-shot decode() above all): pageable host buffers would make every copy a blocking
+    // call, so inputs and outputs go through one pinned staging block and the copies are truly asynchronous.
+    {
+        auto al = [](size_t x) { return (x + 15) / 16 * 16; };
+        const size_t o_synd = 0, o_osdw = o_synd + al((size_t)B * m), o_osd0 = o_osdw + (h_osdw ? al((size_t)B * n) : 0),
+                     o_bp = o_osd0 + (h_osd0 ? al((size_t)B * n) : 0), o_llr = o_bp + (h_bp ? al((size_t)B * n) : 0),
+                     o_conv = o_llr + (h_llr ? al((size_t)B * n * sizeof(real)) : 0), o_iter = o_conv + (h_conv ? al((size_t)B) : 0),
+                     total = o_iter + (h_iter ? al((size_t)B * 4) : 0);
+        if (!pipelined && chunk == B && total <= h->stage_bytes) {
+            if (!h->h_stage) CU_TRY(h, cudaMallocHost((void **)&h->h_stage, h->stage_bytes));
+            bposd_handle::Slot &sl = h->slot[0];
+            rc = collect_chunk(h, sl);
+            if (rc) return rc;
+            rc = ensure_buffers(h, sl, B, h_llr != nullptr, false);
+            if (rc) return rc;
+            cudaStream_t st = sl.stream;
+            uint8_t *sg = h->h_stage;
+            std::memcpy(sg + o_synd, h_synd, (size_t)B * m);
+            CU_TRY(h, cudaMemcpyAsync(sl.b_synd, sg + o_synd, (size_t)B * m, cudaMemcpyHostToDevice, st));
+            bposd_out_t o{};
+            o.d_osdw = h_osdw ? sl.b_osdw : nullptr;
+            o.d_osd0 = h_osd0 ? sl.b_osd0 : nullptr;
+            o.d_bp = h_bp ? sl.b_bp : nullptr;
+            o.d_llr = h_llr ? sl.b_llr : nullptr;
+            o.d_converge = h_conv ? sl.b_conv : nullptr;
+            o.d_iter = h_iter ? sl.b_iter : nullptr;
+            rc = launch_chunk<real>(h, sl, st, sl.b_synd, B, o, nullptr, nullptr);
+            if (rc) return rc;
+            if (h_osdw) CU_TRY(h, cudaMemcpyAsync(sg + o_osdw, sl.b_osdw, (size_t)B * n, cudaMemcpyDeviceToHost, st));
+            if (h_osd0) CU_TRY(h, cudaMemcpyAsync(sg + o_osd0, sl.b_osd0, (size_t)B * n, cudaMemcpyDeviceToHost, st));
+            if (h_bp) CU_TRY(h, cudaMemcpyAsync(sg + o_bp, sl.b_bp, (size_t)B * n, cudaMemcpyDeviceToHost, st));
+            if (h_llr) CU_TRY(h, cudaMemcpyAsync(sg + o_llr, sl.b_llr, (size_t)B * n * sizeof(real), cudaMemcpyDeviceToHost, st));
+            if (h_conv) CU_TRY(h, cudaMemcpyAsync(sg + o_conv, sl.b_conv, (size_t)B, cudaMemcpyDeviceToHost, st));
+            if (h_iter) CU_TRY(h, cudaMemcpyAsync(sg + o_iter, sl.b_iter, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(h, cudaEventRecord(sl.ev[3], st));
+            rc = collect_chunk(h, sl);
+            if (rc) return rc;
+            if (h_osdw) std::memcpy(h_osdw, sg + o_osdw, (size_t)B * n);
+            if (h_osd0) std::memcpy(h_osd0, sg + o_osd0, (size_t)B * n);
+            if (h_bp) std::memcpy(h_bp, sg + o_bp, (size_t)B * n);
+            if (h_llr) std::memcpy(h_llr, sg + o_llr, (size_t)B * n * sizeof(real));
+            if (h_conv) std::memcpy(h_conv, sg + o_conv, (size_t)B);
+            if (h_iter) std::memcpy(h_iter, sg + o_iter, (size_t)B * 4);
+            return BPOSD_OK;
+        }
+    }
     long long idx = 0;
     for (long long c0 = 0; c0 < B; c0 += chunk, idx++) {
         const long long Bc = std::min(chunk, B - c0);

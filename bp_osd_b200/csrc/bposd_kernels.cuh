@@ -612,7 +612,9 @@ __global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) 
     uint32_t *tab = P + m;                                                 // [4][256] XOR tables
     uint32_t *Rk = tab + 1024;                                             // [32] resolved pivot-row words
     int *red = reinterpret_cast<int *>(Rk + 32);                           // [32] block-reduce scratch
-    uint16_t *rowpanel = reinterpret_cast<uint16_t *>(red + 32);           // [m] panel in which the check became a pivot
+    uint32_t *Mloc = reinterpret_cast<uint32_t *>(red + 32);               // [m] multiplier masks of the panel being factorised
+    int *pstart_s = reinterpret_cast<int *>(Mloc + m);                     // [npanels + 1] first pivot of every panel
+    uint16_t *rowpanel = reinterpret_cast<uint16_t *>(pstart_s + a.npanels + 1 + ((a.npanels + 1) & 1)); // [m] panel in which the check became a pivot
     uint8_t *s8 = reinterpret_cast<uint8_t *>(rowpanel + ((m + 1) & ~1));  // [m] transformed syndrome
     __shared__ int sh_p, sh_rank, sh_cnt;
 
@@ -650,7 +652,7 @@ __global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) 
                 if (j0 + u * T < n) order[rk[u]] = j0 + u * T;
         }
         for (int i = tid; i < m; i += T) { rowpanel[i] = OSDL_UNUSED; s8[i] = synd[i] & 1; }
-        if (tid == 0) { sh_rank = 0; pstart[0] = 0; }
+        if (tid == 0) { sh_rank = 0; pstart_s[0] = 0; }
         __syncthreads();
 
         // ---- a10: elimination, one panel of 32 sorted columns at a time
@@ -658,7 +660,7 @@ __global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) 
         for (int w = 0; w < a.npanels; w++) {
             if (sh_rank >= a.maxrank) break;
             uint32_t *Mw = maskbase + (size_t)w * m;
-            for (int i = tid; i < m; i += T) { P[i] = 0; Mw[i] = 0; }
+            for (int i = tid; i < m; i += T) { P[i] = 0; Mloc[i] = 0; }
             __syncthreads();
             if (tid < 32) {
                 const int t = w * 32 + tid;
@@ -668,15 +670,25 @@ __global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) 
                 }
             }
             __syncthreads();
-            // replay the row operations of every earlier panel, in order
-            for (int q = 0; q < w; q++) {
-                const int ps = pstart[q], cnt = pstart[q + 1] - ps;
-                if (cnt == 0) continue;
+            // replay the row operations of every earlier panel that holds pivots, in order.  The pivot rows and
+            // their masks of the next such panel are fetched by warp 0 one step ahead (two dependent HBM/L2 loads).
+            int q = 0;
+            while (q < w && pstart_s[q + 1] == pstart_s[q]) q++;
+            int pf_pr = 0;
+            uint32_t pf_mj = 0;
+            if (warp == 0 && q < w) {
+                const int ps0 = pstart_s[q], cnt0 = pstart_s[q + 1] - ps0;
+                if (lane < cnt0) { pf_pr = piv_row[ps0 + lane]; pf_mj = (maskbase + (size_t)q * m)[pf_pr]; }
+            }
+            while (q < w) {
+                const int ps = pstart_s[q], cnt = pstart_s[q + 1] - ps;
+                int qn = q + 1;
+                while (qn < w && pstart_s[qn + 1] == pstart_s[qn]) qn++;
                 const uint32_t *Mq = maskbase + (size_t)q * m;
                 if (warp == 0) {
-                    int pr = 0;
-                    uint32_t cur = 0, mj = 0, R = 0;
-                    if (lane < cnt) { pr = piv_row[ps + lane]; cur = P[pr]; mj = Mq[pr]; }
+                    const int pr = pf_pr;
+                    const uint32_t mj = pf_mj;
+                    uint32_t cur = lane < cnt ? P[pr] : 0u, R = 0;
                     for (int k = 0; k < cnt; k++) {
                         const uint32_t rk = __shfl_sync(0xffffffffu, cur, k);
                         if (lane == k) R = cur;
@@ -686,30 +698,34 @@ __global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) 
                     __syncwarp();
                     // the parallel step below skips pivot rows of panel q, so their final words go in now
                     if (lane < cnt) P[pr] = cur;
-                }
-                __syncthreads();
-                {
-                    const int grp = tid >> 8, idx = tid & 255;
-                    if (tid < 1024) {
-                        uint32_t v = 0;
-#pragma unroll
-                        for (int b = 0; b < 8; b++) v ^= ((idx >> b) & 1) ? Rk[grp * 8 + b] : 0u;
-                        tab[grp * 256 + idx] = v;
+                    pf_pr = 0; pf_mj = 0;
+                    if (qn < w) {
+                        const int psn = pstart_s[qn], cntn = pstart_s[qn + 1] - psn;
+                        if (lane < cntn) { pf_pr = piv_row[psn + lane]; pf_mj = (maskbase + (size_t)qn * m)[pf_pr]; }
                     }
-                    if (T < 1024)
-                        for (int e = tid + T; e < 1024; e += T) {
-                            uint32_t v = 0;
-                            for (int b = 0; b < 8; b++) v ^= (((e & 255) >> b) & 1) ? Rk[(e >> 8) * 8 + b] : 0u;
-                            tab[e] = v;
-                        }
                 }
                 __syncthreads();
-                for (int i = tid; i < m; i += T) {
-                    const uint32_t mi = Mq[i];
-                    if (mi && rowpanel[i] != (uint16_t)q)
-                        P[i] ^= tab[mi & 255u] ^ tab[256 + ((mi >> 8) & 255u)] ^ tab[512 + ((mi >> 16) & 255u)] ^ tab[768 + (mi >> 24)];
+                for (int e = tid; e < 1024; e += T) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) v ^= (((e & 255) >> b) & 1) ? Rk[(e >> 8) * 8 + b] : 0u;
+                    tab[e] = v;
                 }
                 __syncthreads();
+                // masks are streamed eight rows per thread at a time so the loads overlap
+                for (int i0 = tid; i0 < m; i0 += 8 * T) {
+                    uint32_t mi[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int i = i0 + u * T; mi[u] = i < m ? __ldcs(Mq + i) : 0u; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = i0 + u * T;
+                        if (mi[u] && rowpanel[i] != (uint16_t)q)
+                            P[i] ^= tab[mi[u] & 255u] ^ tab[256 + ((mi[u] >> 8) & 255u)] ^ tab[512 + ((mi[u] >> 16) & 255u)] ^ tab[768 + (mi[u] >> 24)];
+                    }
+                }
+                __syncthreads();
+                q = qn;
             }
             // factorise this panel
             if (tid == 0) sh_cnt = 0;
@@ -736,7 +752,7 @@ __global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) 
                 const int k = sh_cnt;
                 __syncthreads(); // everyone has read sh_p / sh_cnt / P[p] before they change
                 for (int i = tid; i < m; i += T)
-                    if (i != p && ((P[i] >> c) & 1u)) { P[i] ^= Pp; s8[i] ^= sp; Mw[i] |= 1u << k; }
+                    if (i != p && ((P[i] >> c) & 1u)) { P[i] ^= Pp; s8[i] ^= sp; Mloc[i] |= 1u << k; }
                 if (tid == 0) {
                     const int r = sh_rank;
                     piv_row[r] = p; piv_pos[r] = t; rowpanel[p] = (uint16_t)w;
@@ -744,7 +760,9 @@ __global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) 
                 }
                 __syncthreads();
             }
-            if (tid == 0) pstart[w + 1] = sh_rank;
+            if (tid == 0) pstart_s[w + 1] = sh_rank;
+            if (sh_cnt > 0) // this panel's masks go to HBM once, coalesced
+                for (int i = tid; i < m; i += T) Mw[i] = Mloc[i];
             npan_done = w + 1;
             __syncthreads();
         }

@@ -145,6 +145,7 @@ class BpOsdDecoder:
         self.log_prob_ratios = np.zeros(self.n, dtype=np.float64)
         self.converge = False
         self.iter = 0
+        self._one = None
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -213,7 +214,19 @@ class BpOsdDecoder:
         if s.ndim != 1 or s.shape[0] != self.m:
             raise ValueError(f"syndrome must have length {self.m}")
         dtype = s.dtype if np.issubdtype(s.dtype, np.integer) else int
-        res = self._decode_host(np.ascontiguousarray((s.astype(np.int64) & 1).astype(np.uint8)).reshape(1, self.m))
+        if self._one is None:   # result buffers of the single-shot path are allocated once
+            self._one = {"osdw": np.empty((1, self.n), np.uint8), "osd0": np.empty((1, self.n), np.uint8),
+                         "bp": np.empty((1, self.n), np.uint8), "llr": np.empty((1, self.n), self._real),
+                         "converge": np.empty(1, np.uint8), "iter": np.empty(1, np.int32),
+                         "synd": np.empty((1, self.m), np.uint8)}
+        synd = self._one["synd"]
+        if s.dtype == np.bool_:
+            np.copyto(synd[0], s, casting="unsafe")
+        elif np.issubdtype(s.dtype, np.integer):
+            np.bitwise_and(s, 1, out=synd[0], casting="unsafe")
+        else:
+            synd[0] = s.astype(np.int64) & 1
+        res = self._decode_host(synd, out=self._one)
         self.osdw_decoding = res.osdw_decoding[0].astype(dtype)
         self.osd0_decoding = res.osd0_decoding[0].astype(dtype)
         self.bp_decoding = res.bp_decoding[0].astype(dtype)
