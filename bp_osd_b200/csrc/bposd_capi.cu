@@ -264,7 +264,14 @@ static int plan_geometry_t(bposd_handle *h) {
     // OSD kernel
     h->osd_S = (m + 31) / 32;
     h->osd_St = h->osd_S | 1;
-    h->osd_threads = std::min(1024, std::max(64, (m + 31) / 32 * 32));
+    // about one thread per two checks, at most 512: the elimination is a chain of short barrier-separated steps, so
+    // cheap barriers matter more than lanes (measured on B200, profiles/r01y_osd_threads.log: m = 192 -> 128 threads
+    // is 4.9x faster than 992 and 20 % faster than 192; m = 961 -> 512 threads is 5 % faster than 992)
+    h->osd_threads = std::min(512, std::max(64, (m / 2 + 31) / 32 * 32));
+    if (const char *ev = std::getenv("BPOSD_OSD_THREADS")) { // tuning experiments only
+        const int v = std::atoi(ev);
+        if (v >= 64 && v <= 1024 && v % 32 == 0) h->osd_threads = v;
+    }
     const int nw = h->osd_threads / 32;
     const size_t osd_smem = (size_t)n * 8 + 256 + ((size_t)m * h->osd_St + 3 * (size_t)h->osd_S + (size_t)nw * (h->osd_S + 64)) * 4 + 128 + 3 * (size_t)n * 2 + 16;
     h->osd_smem = (int)osd_smem;
