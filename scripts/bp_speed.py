@@ -16,6 +16,7 @@ ap.add_argument("--osd", default="osd_cs")
 ap.add_argument("--order", type=int, default=7)
 ap.add_argument("--max-iter", type=int, default=0)
 ap.add_argument("--method", default="ms")
+ap.add_argument("--osd-variant", type=int, default=None)
 ap.add_argument("--llr", action="store_true")
 a = ap.parse_args()
 code = codes.config_code(a.cfg, logicals=False) if a.cfg == 4 else codes.config_code(a.cfg)
@@ -24,6 +25,8 @@ d = BpOsdDecoder(H, error_rate=a.p, max_iter=a.max_iter, bp_method=a.method, ms_
                  osd_order=a.order, precision=a.prec)
 if a.kernel is not None or a.threads:
     d.set_tuning(bp_kernel=a.kernel, bp_threads=a.threads)
+if a.osd_variant is not None:
+    d.set_osd_variant(a.osd_variant)
 d.set_error_channel(px=a.p)
 _, syn = d.sample_syndromes(1, 0, a.shots, return_errors=False)
 info = d.info()
