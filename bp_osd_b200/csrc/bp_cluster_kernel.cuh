@@ -37,6 +37,7 @@ struct ClusterDev {
     const uint32_t *row_of;
     const uint32_t *bit_of;
     int rows_per_cta, bits_per_cta, CL;
+    int flip_table; // 1: per-edge parity-flip descriptors live in shared memory (bits_per_cta * DV words)
 };
 
 static inline void cluster_free(ClusterTables &t) {
@@ -46,11 +47,12 @@ static inline void cluster_free(ClusterTables &t) {
 }
 
 template <typename real>
-static inline size_t cluster_smem_bytes(int DC, int rows_per_cta, int bits_per_cta, bool with_priors) {
+static inline size_t cluster_smem_bytes(int DC, int rows_per_cta, int bits_per_cta, bool with_priors, int DV = 0) {
     size_t msgs = ((size_t)rows_per_cta * fast_row_stride(DC, (int)sizeof(real)) * sizeof(real) + 15) / 16 * 16;
     size_t meta = ((size_t)rows_per_cta + 15) / 16 * 16;
     size_t prior = with_priors ? ((size_t)bits_per_cta * sizeof(real) + 15) / 16 * 16 : 0;
-    return msgs + meta + prior + 16;
+    size_t flip = (size_t)bits_per_cta * DV * 4; // DV > 0: with the parity-flip descriptor table
+    return msgs + meta + prior + flip + 16;
 }
 
 // Host partition pass: alternate "every bit goes to the CTA that holds most of its checks" and "every check
@@ -191,18 +193,11 @@ __device__ __forceinline__ void cluster_check_row(real *row, unsigned mt, real a
     }
 }
 
-template <typename real>
-__device__ __forceinline__ real slot_load(unsigned char *smem, uint32_t off, bool is_remote) {
-    return is_remote ? ld_dsmem(off, (real)0) : *reinterpret_cast<const real *>(smem + off);
-}
-template <typename real>
-__device__ __forceinline__ void slot_store(unsigned char *smem, uint32_t off, bool is_remote, real v) {
-    if (is_remote) st_dsmem(off, v);
-    else *reinterpret_cast<real *>(smem + off) = v;
-}
-
-template <typename real, int DC, int DV, int VPT, bool REG>
-__global__ void __launch_bounds__(1024, 1) bp_cluster_kernel(BpArgs<real> a, ClusterDev t) {
+// MAXT (a multiple of 128 >= blockDim.x) sets the register budget: 65536 / MAXT per thread, so that the per-thread
+// slot addresses never spill -- a spill costs an L2 round trip per iteration here, because barrier.cluster
+// invalidates L1.
+template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
+__global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, ClusterDev t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = a.g.m, n = a.g.n;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -212,20 +207,34 @@ __global__ void __launch_bounds__(1024, 1) bp_cluster_kernel(BpArgs<real> a, Clu
     real *msg = reinterpret_cast<real *>(smem_raw);                                            // [rpc * RS] this CTA's rows
     uint8_t *meta = smem_raw + ((size_t)rpc * RS * sizeof(real) + 15) / 16 * 16;               // bit0 mismatch, bits1-5 degree, bit7 syndrome
     real *prior_s = reinterpret_cast<real *>(meta + ((size_t)rpc + 15) / 16 * 16);             // [bpc] priors by position (non-uniform only)
+    uint32_t *flip_desc = reinterpret_cast<uint32_t *>(prior_s + ((size_t)bpc * sizeof(real) + 15) / 16 * 16 / sizeof(real)); // [bpc * DV]
     __shared__ long long sh_shot;
     __shared__ int sh_slot;
     __shared__ unsigned sh_vote[2][16];
     const uint32_t msg_s = smem_u32(msg), meta_s = smem_u32(meta);
     const unsigned slots_per_cta = (unsigned)rpc * RS;
+    // A hard-decision flip toggles the parity-mismatch bit of every neighbouring check, wherever it lives.  The
+    // cluster address of that check's meta word (4-byte aligned) and its byte lane (low two bits) are resolved once
+    // per CTA; doing it at flip time costs a global load per edge that always misses L1 (barrier.cluster invalidates
+    // it), and flips are frequent on the shots that matter for the tail (BP that oscillates for thousands of passes).
+    if (t.flip_table)
+        for (int e = tid; e < bpc * DV; e += T) {
+            const uint32_t s = t.vslot[(size_t)rank * bpc * DV + e];
+            uint32_t d = 0;
+            if (s != BPC_NONE) {
+                const uint32_t prow = s / (unsigned)RS, lp = prow % (unsigned)rpc;
+                d = mapa_u32(meta_s + (lp & ~3u), prow / (unsigned)rpc) | (lp & 3u);
+            }
+            flip_desc[e] = d;
+        }
+    __syncthreads();
 
-    // slots of this thread's bits (shot independent): a byte offset into this CTA's array for a local slot, a
-    // cluster-window address for a slot that lives in another CTA (bit r*DV+k of `remote`).  Local slots use
-    // plain ld/st.shared: the shared::cluster path is several times narrower than the SM's own shared-memory
-    // pipe (measured: ~17 B/clk per SM), so only the edges that really cross CTAs should take it.
+    // cluster-window addresses of the slots of this thread's bits (shot independent).  Local and remote slots are
+    // addressed alike: splitting them (plain ld/st.shared for CTA-local slots) was measured and made no difference,
+    // the extra predicates and selects cost as much as the narrower path saves (profiles/r01k_cluster_probe.log).
     uint32_t off[VPT][DV];
     int dj[VPT];
     unsigned valid = 0;
-    unsigned long long remote = 0;
 #pragma unroll
     for (int r = 0; r < VPT; r++) {
         const int lq = tid + r * T;
@@ -238,9 +247,7 @@ __global__ void __launch_bounds__(1024, 1) bp_cluster_kernel(BpArgs<real> a, Clu
             const uint32_t s = have ? t.vslot[q * DV + k] : BPC_NONE;
             off[r][k] = 0;
             if (s != BPC_NONE) {
-                const uint32_t owner = s / slots_per_cta, byte_off = (s % slots_per_cta) * (unsigned)sizeof(real);
-                if (owner == rank) off[r][k] = byte_off;
-                else { off[r][k] = mapa_u32(msg_s + byte_off, owner); remote |= 1ull << (r * DV + k); }
+                off[r][k] = mapa_u32(msg_s + (s % slots_per_cta) * (unsigned)sizeof(real), s / slots_per_cta);
                 dj[r]++;
             }
         }
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(1024, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                 llr[r] = pj;
 #pragma unroll
                 for (int k = 0; k < DV; k++)
-                    if (REG || k < dj[r]) slot_store<real>(smem_raw, off[r][k], (remote >> (r * DV + k)) & 1ull, pj);
+                    if (REG || k < dj[r]) st_dsmem(off[r][k], pj);
             }
         }
         cluster_sync_all();
@@ -319,8 +326,7 @@ __global__ void __launch_bounds__(1024, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                     const int r = r0 + u;
 #pragma unroll
                     for (int k = 0; k < DV; k++)
-                        c[u][k] = (r < VPT && ((valid >> r) & 1u) && (REG || k < dj[r]))
-                                      ? slot_load<real>(smem_raw, off[r][k], (remote >> (r * DV + k)) & 1ull) : (real)0;
+                        c[u][k] = (r < VPT && ((valid >> r) & 1u) && (REG || k < dj[r])) ? ld_dsmem(off[r][k], (real)0) : (real)0;
                 }
 #pragma unroll
                 for (int u = 0; u < BATCH; u++) {
@@ -337,8 +343,7 @@ __global__ void __launch_bounds__(1024, 1) bp_cluster_kernel(BpArgs<real> a, Clu
 #pragma unroll
                         for (int k = DV - 1; k >= 0; k--)
                             if (REG || k < dj[r]) {
-                                slot_store<real>(smem_raw, off[r][k], (remote >> (r * DV + k)) & 1ull,
-                                                 (REG && k == DV - 1) ? pre[k] : pre[k] + sfx);
+                                st_dsmem(off[r][k], (REG && k == DV - 1) ? pre[k] : pre[k] + sfx);
                                 sfx = (REG && k == DV - 1) ? c[u][k] : sfx + c[u][k];
                             }
                     }
@@ -353,9 +358,14 @@ __global__ void __launch_bounds__(1024, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                     if ((flip >> r) & 1u) {
                         const size_t q = (size_t)rank * bpc + tid + r * T;
                         for (int k = 0; k < dj[r]; k++) {
-                            const uint32_t prow = t.vslot[q * DV + k] / (unsigned)RS;
-                            const uint32_t lp = prow % (unsigned)rpc;
-                            xor_dsmem_u32(mapa_u32(meta_s + (lp & ~3u), prow / (unsigned)rpc), 1u << ((lp & 3u) * 8u));
+                            if (t.flip_table) {
+                                const uint32_t d = flip_desc[(tid + r * T) * DV + k];
+                                xor_dsmem_u32(d & ~3u, 1u << ((d & 3u) * 8u));
+                            } else {
+                                const uint32_t prow = t.vslot[q * DV + k] / (unsigned)RS;
+                                const uint32_t lp = prow % (unsigned)rpc;
+                                xor_dsmem_u32(mapa_u32(meta_s + (lp & ~3u), prow / (unsigned)rpc), 1u << ((lp & 3u) * 8u));
+                            }
                         }
                     }
             }
@@ -402,7 +412,9 @@ __global__ void __launch_bounds__(1024, 1) bp_cluster_kernel(BpArgs<real> a, Clu
 // ---- dispatch ------------------------------------------------------------------------------------
 // bits per thread: the smallest of {1, 2, 3, 4, 6, 8} that lets a CTA of <= 1024 threads cover its bits
 static inline int cluster_vpt(int bits_per_cta) {
-    for (int v : {1, 2, 3, 4, 6, 8})
+    for (int v : {1, 2, 3, 4, 6, 8}) // prefer CTAs of <= 640 threads: 96+ registers per thread, no spills in fp64
+        if ((bits_per_cta + v - 1) / v <= 640) return v;
+    for (int v : {6, 8})
         if ((bits_per_cta + v - 1) / v <= 1024) return v;
     return 0;
 }
@@ -411,7 +423,15 @@ static inline int cluster_threads(int bits_per_cta) {
     return v ? std::max(32, ((bits_per_cta + v - 1) / v + 31) / 32 * 32) : 0;
 }
 
-#define BPOSD_CL_REG(EXPR) do { if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } while (0)
+#define BPOSD_CL_REG2(EXPR) do { if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } while (0)
+#define BPOSD_CL_REG(EXPR)                                                                       \
+    do {                                                                                         \
+        if (maxt__ <= 512) { constexpr int MAXT = 512; BPOSD_CL_REG2(EXPR); }                    \
+        else if (maxt__ <= 640) { constexpr int MAXT = 640; BPOSD_CL_REG2(EXPR); }               \
+        else if (maxt__ <= 768) { constexpr int MAXT = 768; BPOSD_CL_REG2(EXPR); }               \
+        else if (maxt__ <= 896) { constexpr int MAXT = 896; BPOSD_CL_REG2(EXPR); }               \
+        else { constexpr int MAXT = 1024; BPOSD_CL_REG2(EXPR); }                                 \
+    } while (0)
 #define BPOSD_CL_GEOM(DCv, DVv, EXPR)                                                            \
     do {                                                                                         \
         constexpr int DC = DCv, DV = DVv;                                                        \
@@ -425,6 +445,7 @@ static inline int cluster_threads(int bits_per_cta) {
 #define BPOSD_CL_DISPATCH(t, EXPR)                                                               \
     do {                                                                                         \
         const int vpt__ = cluster_vpt(t.bits_per_cta);                                           \
+        const int maxt__ = cluster_threads(t.bits_per_cta);                                      \
         const bool reg__ = t.regular != 0;                                                       \
         if (t.DC == 4) BPOSD_CL_GEOM(4, 2, EXPR);                                                \
         else if (t.DC == 6) BPOSD_CL_GEOM(6, 3, EXPR);                                           \
@@ -436,7 +457,7 @@ template <typename real>
 static inline cudaError_t cluster_prepare(const ClusterTables &t, int threads, size_t smem, int *max_clusters) {
     cudaError_t e = cudaSuccess;
     BPOSD_CL_DISPATCH(t, {
-        auto kern = (bp_cluster_kernel<real, DC, DV, VPT, REG>);
+        auto kern = (bp_cluster_kernel<real, DC, DV, VPT, MAXT, REG>);
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess && t.CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e == cudaSuccess) {
@@ -454,10 +475,11 @@ static inline cudaError_t cluster_prepare(const ClusterTables &t, int threads, s
 
 template <typename real>
 static inline cudaError_t cluster_launch(const ClusterTables &t, const BpArgs<real> &a, int nclusters, int threads, size_t smem,
-                                         cudaStream_t st) {
+                                         int flip_table, cudaStream_t st) {
     ClusterDev d;
     d.vslot = t.d_vslot; d.cdeg = t.d_cdeg; d.row_of = t.d_row_of; d.bit_of = t.d_bit_of;
     d.rows_per_cta = t.rows_per_cta; d.bits_per_cta = t.bits_per_cta; d.CL = t.CL;
+    d.flip_table = flip_table;
     cudaError_t e = cudaSuccess;
     BPOSD_CL_DISPATCH(t, {
         cudaLaunchConfig_t cfg = {};
@@ -466,7 +488,7 @@ static inline cudaError_t cluster_launch(const ClusterTables &t, const BpArgs<re
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = t.CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, bp_cluster_kernel<real, DC, DV, VPT, REG>, a, d);
+        e = cudaLaunchKernelEx(&cfg, bp_cluster_kernel<real, DC, DV, VPT, MAXT, REG>, a, d);
     });
     return e;
 }

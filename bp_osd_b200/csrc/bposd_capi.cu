@@ -37,7 +37,7 @@ struct bposd_handle {
     FastTables fast;
     // cluster-kernel tables (built on demand, when the messages exceed one SM's shared memory)
     ClusterTables clus;
-    int clus_nclusters = 0;
+    int clus_nclusters = 0, clus_flip_table = 0;
     // Two decode slots: each owns its control words, failed-shot workspace, staging buffers, events and
     // (for the host-buffer pipeline) a stream, so chunk i+1 can be copied in while chunk i decodes.
     struct Slot {
@@ -213,7 +213,12 @@ static int plan_geometry_t(bposd_handle *h) {
                 if (e != cudaSuccess) return fail(h, BPOSD_ECUDA, std::string("cluster_build: ") + cudaGetErrorString(e));
             }
             const int ct = cluster_threads(h->clus.bits_per_cta);
-            const size_t csmem = cluster_smem_bytes<real>(h->clus.DC, h->clus.rows_per_cta, h->clus.bits_per_cta, true);
+            size_t csmem = cluster_smem_bytes<real>(h->clus.DC, h->clus.rows_per_cta, h->clus.bits_per_cta, true, h->clus.DV);
+            h->clus_flip_table = 1; // parity-flip descriptors in shared memory when they fit
+            if (csmem > (size_t)h->smem_optin) {
+                csmem = cluster_smem_bytes<real>(h->clus.DC, h->clus.rows_per_cta, h->clus.bits_per_cta, true);
+                h->clus_flip_table = 0;
+            }
             int ncl = 0;
             cudaError_t e = (ct > 0 && ct <= 1024) ? cluster_prepare<real>(h->clus, ct, csmem, &ncl) : cudaErrorInvalidConfiguration;
             if (e == cudaSuccess && ncl >= 1) {
@@ -576,7 +581,7 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     CU_TRY(h, cudaEventRecord(sl.ev[0], st));
     if (h->bp_kernel == 3) {
         const int ncl = (int)std::min<long long>(Bc, h->clus_nclusters);
-        CU_TRY(h, cluster_launch<real>(h->clus, a, ncl, h->bp_threads, (size_t)h->bp_smem, st));
+        CU_TRY(h, cluster_launch<real>(h->clus, a, ncl, h->bp_threads, (size_t)h->bp_smem, h->clus_flip_table, st));
     } else if (h->bp_kernel == 2) fast_launch<real>(h->fast, a, grid, h->bp_threads, h->bp_smem, st);
     else if (h->bp_kernel == 1) bp_generic_kernel<real, true><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
     else bp_generic_kernel<real, false><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
