@@ -190,6 +190,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own messages (its version banner, NCCL_DEBUG output) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
