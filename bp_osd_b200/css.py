@@ -87,6 +87,15 @@ class css_code:
         self.lz = _logicals_of(self.hx, self.hz)
         return self.lx, self.lz
 
+    def canonical_logicals(self):
+        """Rescale lx so that lx @ lz.T = I (mod 2).  The reference's code generator calls this
+        (/root/reference/examples/codes/hgp_codes/generate_codes.py:11) and the lx files it ships are in
+        this form; lz is left as computed."""
+        pair = (self.lx @ self.lz.T).toarray() % 2
+        self.lx = sp.csr_matrix((mod2.inverse(pair).astype(np.int64) @ self.lx.toarray().astype(np.int64)) % 2,
+                                dtype=np.uint8)
+        return self.lx
+
     @property
     def h(self):
         zx = sp.csr_matrix(self.hz.shape, dtype=np.uint8)

@@ -98,3 +98,29 @@ def test_config5_shape():
     q = codes.config_code(5)
     assert q.hz.shape == (19200, 40000) and q.hz.nnz == 134400
     assert not ((q.hx @ q.hz.T).data % 2).any()
+
+
+@pytest.mark.parametrize("tag", ["400_16_6", "625_25_8", "900_36_10"])
+def test_reference_shipped_logicals(tag):
+    """Golden data FROM THE REFERENCE (not from the oracle): the lx/lz files it ships under
+    examples/codes/hgp_codes were written by the real ldpc.mod2 pipeline (generate_codes.py).  Our hgp() +
+    GF(2) toolkit must give the same lz bit for bit; lx is shipped in canonical form (lx lz^T = I) from an
+    older release, so it is pinned as a coset: canonical, commuting, and equal to ours modulo X stabilisers."""
+    import os
+    from bp_osd_b200.hgp import hgp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_hgp_logicals.npz"))
+    N, K, _ = (int(x) for x in tag.split("_"))
+    shape = tuple(g[f"seed_shape_{tag}"])
+    seed = np.unpackbits(g[f"seed_{tag}"], axis=1)[:, :shape[1]]
+    lx_ref = np.unpackbits(g[f"lx_{tag}"], axis=1)[:, :N].astype(np.int64)
+    lz_ref = np.unpackbits(g[f"lz_{tag}"], axis=1)[:, :N].astype(np.int64)
+    q = hgp(seed)
+    assert (q.N, q.K) == (N, K)
+    assert (q.lz.toarray() == lz_ref).all()
+    q.canonical_logicals()
+    lx = q.lx.toarray().astype(np.int64)
+    assert ((lx @ lz_ref.T) % 2 == np.eye(K, dtype=np.int64)).all()
+    assert ((lx_ref @ lz_ref.T) % 2 == np.eye(K, dtype=np.int64)).all()
+    hx = q.hx.toarray()
+    assert not ((q.hz.toarray().astype(np.int64) @ lx_ref.T) % 2).any()
+    assert mod2.rank(np.vstack([hx, (lx ^ lx_ref).astype(np.uint8)])) == mod2.rank(hx)
