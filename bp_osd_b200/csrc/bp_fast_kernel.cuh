@@ -90,18 +90,53 @@ constexpr int kCheckUnroll = BPOSD_CHECK_UNROLL; // rows of the check sweep inte
 #ifndef BPOSD_MID_MAXT
 #define BPOSD_MID_MAXT 256
 #endif
-static inline int fast_vpt(int n) { return n <= 256 ? 2 : (n <= 2048 ? BPOSD_MID_VPT : 8); }
-static inline int fast_maxt(int n) { return n <= 256 ? 128 : (n <= 2048 ? BPOSD_MID_MAXT : (n <= 4096 ? 512 : 1024)); }
+// latency geometry of the mid class: the whole CTA works on one shot, so what matters when only a few shots are in
+// flight (single-shot decode()) is the length of a pass, not shots per SM: few bits per thread, a full-size CTA
+// Measured on B200 (profiles/r03a_ab_probe.log, single-shot decode() p50 on the bench code): fp64 (4, 512) 95.6 us,
+// (3, 704) 102 us, (2, 1024) 104 us -- 1024 threads cap the kernel at 64 registers and the check update spills;
+// fp32 (2, 1024) 80 us, (4, 512) 90 us.
+#ifndef BPOSD_LAT_VPT64
+#define BPOSD_LAT_VPT64 4
+#endif
+#ifndef BPOSD_LAT_MAXT64
+#define BPOSD_LAT_MAXT64 512
+#endif
+#ifndef BPOSD_LAT_VPT32
+#define BPOSD_LAT_VPT32 2
+#endif
+#ifndef BPOSD_LAT_MAXT32
+#define BPOSD_LAT_MAXT32 1024
+#endif
+// geometry ids: 0 (2, 128) | 1 mid (throughput) | 2 (8, 512) | 3 (8, 1024) | 4 mid (latency)
+static inline int fast_geom(int n, bool latency) { return n <= 256 ? 0 : (n <= 2048 ? (latency ? 4 : 1) : (n <= 4096 ? 2 : 3)); }
+static inline int fast_vpt_g(int geom, int elem_bytes = 8) {
+    return geom == 0 ? 2 : (geom == 1 ? BPOSD_MID_VPT : (geom == 4 ? (elem_bytes == 8 ? BPOSD_LAT_VPT64 : BPOSD_LAT_VPT32) : 8));
+}
+static inline int fast_maxt_g(int geom, int elem_bytes = 8) {
+    return geom == 0 ? 128 : (geom == 1 ? BPOSD_MID_MAXT : (geom == 2 ? 512 : (geom == 4 ? (elem_bytes == 8 ? BPOSD_LAT_MAXT64 : BPOSD_LAT_MAXT32) : 1024)));
+}
+static inline int fast_vpt(int n) { return fast_vpt_g(fast_geom(n, false)); }
+static inline int fast_maxt(int n) { return fast_maxt_g(fast_geom(n, false)); }
 template <typename real, int MAXT> constexpr int fast_minb() {
     constexpr int cap = sizeof(real) == 8 ? BPOSD_REGCAP64 : BPOSD_REGCAP32;
     return (65536 / (MAXT * cap)) < 1 ? 1 : (65536 / (MAXT * cap));
 }
 
+// geometries whose check sweep takes two rows per thread at a time (fast_check_rows2): the fp64 latency geometry
+#ifndef BPOSD_PAIR_ROWS
+#define BPOSD_PAIR_ROWS 1
+#endif
+template <typename real, int VPT, int MAXT>
+constexpr bool kPairRows = BPOSD_PAIR_ROWS != 0 && BPOSD_TREE_MIN == 0 && sizeof(real) == 8 && VPT == BPOSD_LAT_VPT64 && MAXT == BPOSD_LAT_MAXT64 &&
+                           !(VPT == BPOSD_MID_VPT && MAXT == BPOSD_MID_MAXT) && MAXT >= 512;
+static inline int fast_default_threads_g(int n, int geom, int elem_bytes) {
+    const int vpt = fast_vpt_g(geom, elem_bytes);
+    int t = ((n + vpt - 1) / vpt + 31) / 32 * 32;
+    return std::min(fast_maxt_g(geom, elem_bytes), std::max(32, t));
+}
 static inline int fast_default_threads(int n, int m) {
     (void)m;
-    const int vpt = fast_vpt(n);
-    int t = ((n + vpt - 1) / vpt + 31) / 32 * 32;
-    return std::min(fast_maxt(n), std::max(32, t));
+    return fast_default_threads_g(n, fast_geom(n, false), 8);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -298,6 +333,20 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
     return cudaMemcpy(t.d_cdeg, cd.data(), cd.size(), cudaMemcpyHostToDevice);
 }
 
+// Bound behind the fp64 tree-min check update.  With P = max |prior| <= kFastPriorBound, B_t = max |bit->check
+// message| after pass t and g = max column degree - 1:  B_0 = P,  B_t <= P + g*B_{t-1}  (g also carries a scaling factor above 1)  (check->bit magnitudes never
+// exceed the bit->check ones),  so every partial sum of pass t is below P*DV*(t+1)*max(g,1)^t.  Up to the returned
+// pass that stays under 2^1023: no infinity and therefore no NaN can exist, and the order of the compares is free.
+constexpr double kFastPriorBound = 18446744073709551616.0; // 2^64
+static inline int fast_exact_after(int max_col_deg, int max_iter, double alpha) {
+    const double a1 = (alpha > 1.0) ? alpha : 1.0; // a scaling factor above 1 amplifies (never used by the reference)
+    if (!(a1 < 1e30)) return 0;
+    const double g = std::max(max_col_deg - 1, 1) * a1;
+    const double room = 1023.0 - 64.0 - std::log2((double)std::max(max_col_deg, 1) * a1) - std::log2((double)max_iter + 2.0);
+    if (g <= 1.0) return room > 0 ? 0x7fffffff : 0;
+    return (int)std::max(0.0, std::floor(room / std::log2(g)));
+}
+
 template <typename real>
 static inline size_t fast_smem_bytes(const FastTables &t, int n, int m) {
     if (t.DC == 0) return (size_t)1 << 40;
@@ -354,12 +403,13 @@ __device__ __forceinline__ float with_sign_word(float, uint32_t w) { return __ui
 template <typename real> __device__ __forceinline__ real lt_min(real a, real b) { return (a < b) ? a : b; } // `if (a < t) t = a`
 
 // One check of the min-sum check sweep (row a4), in place on its DC-slot row.  `mt` is the check's meta
-// byte (bit 7 syndrome, bits 1-5 degree).
+// byte (bit 7 syndrome, bits 1-5 degree).  Order-exact form: prefix/suffix running minima in the
+// reference's own order (`if (a < t) t = a`), which also reproduces its NaN propagation; used for shots
+// that carry an infinite or NaN value (fast_check_row_tree below handles the all-finite case).
 template <typename real, int DC, bool REG>
-__device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alpha, uint32_t alpha_w) {
-    real v[DC], suf[DC];
+__device__ __forceinline__ void fast_check_compute(real (&v)[DC], real (&out)[DC], unsigned mt, real alpha, uint32_t alpha_w) {
+    real suf[DC];
     uint32_t sw[DC];
-    RowIO<real, DC>::load(row, v);
     uint32_t X = (mt & 0x80u) << 24;
 #pragma unroll
     for (int k = 0; k < DC; k++) { sw[k] = sign_word(v[k]); X ^= sw[k]; v[k] = abs_bits(v[k]); }
@@ -367,7 +417,6 @@ __device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alph
     suf[DC - 1] = v[DC - 1];
 #pragma unroll
     for (int k = DC - 2; k >= 1; k--) suf[k] = lt_min(v[k], suf[k + 1]);
-    real out[DC];
     real run = v[0];
     out[0] = (DC > 1) ? suf[DC > 1 ? 1 : 0] : real_max<real>();
 #pragma unroll
@@ -396,7 +445,104 @@ __device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alph
 #pragma unroll
         for (int k = 0; k < DC; k++) out[k] = (k < deg) ? out[k] : real_max<real>();
     }
+}
+
+template <typename real, int DC, bool REG>
+__device__ __forceinline__ void fast_check_row_exact(real *row, unsigned mt, real alpha, uint32_t alpha_w) {
+    real v[DC], out[DC];
+    RowIO<real, DC>::load(row, v);
+    fast_check_compute<real, DC, REG>(v, out, mt, alpha, alpha_w);
     RowIO<real, DC>::store(row, out);
+}
+
+// Two rows at once: both rows are loaded before either is updated, so the two dependent compare/select chains
+// interleave.  Used by the latency geometry, where one CTA has the SM to itself and a pass is bound by those chains,
+// not by issue slots (throughput geometries have no registers to spare for it: profiles/r03a_ab_probe.log, E_unroll2).
+template <typename real, int DC, bool REG>
+__device__ __forceinline__ void fast_check_rows2(real *row_a, real *row_b, unsigned mt_a, unsigned mt_b, real alpha, uint32_t alpha_w) {
+    real va[DC], vb[DC], oa[DC], ob[DC];
+    RowIO<real, DC>::load(row_a, va);
+    RowIO<real, DC>::load(row_b, vb);
+    fast_check_compute<real, DC, REG>(va, oa, mt_a, alpha, alpha_w);
+    fast_check_compute<real, DC, REG>(vb, ob, mt_b, alpha, alpha_w);
+    RowIO<real, DC>::store(row_a, oa);
+    RowIO<real, DC>::store(row_b, ob);
+}
+
+// flip the IEEE sign bit of x where bit 31 of w is set
+__device__ __forceinline__ double xor_sign(double x, uint32_t w) { return __hiloint2double(__double2hiint(x) ^ (int)(w & 0x80000000u), __double2loint(x)); }
+__device__ __forceinline__ float xor_sign(float x, uint32_t w) { return __uint_as_float(__float_as_uint(x) ^ (w & 0x80000000u)); }
+
+// All-finite form of the same check update -- an evaluated alternative, compiled in with -DBPOSD_TREE_MIN=1 and off by
+// default: parity-green on B200 but not faster (profiles/r03a_ab_probe.log: fp64 111.3 vs 111.6 M shot-iterations/s,
+// fp32 172.5 vs 179.1), because ptxas emits the same ~95 instructions per row for both forms (one compare fewer,
+// the same register-pair moves) and the shallower dependence chain alone does not shorten the sweep.  With no NaN in the row the minimum over "the other edges"
+// does not depend on the order of the compares, so it is taken as a shallow tree: minima of the DC/2
+// pairs, the minimum of all pairs but one, and one compare per edge against its partner -- 13 compares
+// of depth 4 for a row of 6 against 15 of depth 6 for the running form, and the dependent
+// compare/select chain is what the sweep waits on (ncu: "wait" is the top stall).  The sign is applied
+// by flipping the operand's sign bit and multiplying by one +-alpha shared by the row (IEEE: the product's
+// magnitude does not depend on the signs, its sign is their XOR), which drops the per-edge +-alpha register pairs.
+// Results are bit-identical to fast_check_row_exact for finite inputs, including the +-0 slow path.
+template <typename real, int DC, bool REG>
+__device__ __forceinline__ void fast_check_row_tree(real *row, unsigned mt, real alpha, uint32_t alpha_w) {
+    static_assert(DC == 4 || DC == 6 || DC == 8, "tree form is written for rows of 4, 6 or 8 slots");
+    constexpr int NP = DC / 2;
+    real v[DC], out[DC], pm[NP], ex[NP];
+    uint32_t sw[DC];
+    RowIO<real, DC>::load(row, v);
+    uint32_t X = (mt & 0x80u) << 24;
+#pragma unroll
+    for (int k = 0; k < DC; k++) { sw[k] = sign_word(v[k]); X ^= sw[k]; v[k] = abs_bits(v[k]); }
+#pragma unroll
+    for (int i = 0; i < NP; i++) pm[i] = lt_min(v[2 * i], v[2 * i + 1]);
+    real all_min;
+    if constexpr (NP == 2) {
+        ex[0] = pm[1]; ex[1] = pm[0];
+        all_min = lt_min(pm[0], pm[1]);
+    } else if constexpr (NP == 3) {
+        ex[0] = lt_min(pm[1], pm[2]); ex[1] = lt_min(pm[0], pm[2]); ex[2] = lt_min(pm[0], pm[1]);
+        all_min = lt_min(ex[2], pm[2]);
+    } else {
+        const real lo = lt_min(pm[0], pm[1]), hi = lt_min(pm[2], pm[NP - 1]);
+        ex[0] = lt_min(pm[1], hi); ex[1] = lt_min(pm[0], hi); ex[2] = lt_min(lo, pm[NP - 1]); ex[NP - 1] = lt_min(lo, pm[2]);
+        all_min = lt_min(lo, hi);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; i++) { out[2 * i] = lt_min(v[2 * i + 1], ex[i]); out[2 * i + 1] = lt_min(v[2 * i], ex[i]); }
+    if (all_min == (real)0) {
+        int tot = (int)(mt >> 7);
+#pragma unroll
+        for (int k = 0; k < DC; k++) tot += ((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < DC; k++) {
+            const int sg = tot + (((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0);
+            out[k] = out[k] * ((sg & 1) ? -alpha : alpha);
+        }
+    } else {
+        const real a_row = with_sign_word(alpha, (X & 0x80000000u) ^ alpha_w); // alpha with sign = syndrome ^ parity of all signs
+#pragma unroll
+        for (int k = 0; k < DC; k++) out[k] = xor_sign(out[k], sw[k]) * a_row; // sign onto the operand: the product lands in the store registers
+    }
+    if (!REG) {
+        const int deg = (mt >> 1) & 0x1f;
+#pragma unroll
+        for (int k = 0; k < DC; k++) out[k] = (k < deg) ? out[k] : real_max<real>();
+    }
+    RowIO<real, DC>::store(row, out);
+}
+
+#ifndef BPOSD_TREE_MIN
+#define BPOSD_TREE_MIN 0 // measured on B200 (profiles/r03a_ab_probe.log): no gain in fp64 (111.3 vs 111.6 M it/s), -3.7 % in fp32
+#endif
+template <typename real, int DC, bool REG>
+__device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alpha, uint32_t alpha_w, bool exact) {
+    if constexpr (BPOSD_TREE_MIN != 0 && (DC == 4 || DC == 6 || DC == 8)) {
+        if (exact) fast_check_row_exact<real, DC, REG>(row, mt, alpha, alpha_w);
+        else fast_check_row_tree<real, DC, REG>(row, mt, alpha, alpha_w);
+    } else {
+        fast_check_row_exact<real, DC, REG>(row, mt, alpha, alpha_w);
+    }
 }
 
 template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
@@ -418,6 +564,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
     uint8_t *st_dec = reinterpret_cast<uint8_t *>(st_llr + n);
     __shared__ long long sh_shot;
     __shared__ int sh_slot;
+    __shared__ int sh_exact; // the shot carries an infinite or NaN value: check sweep in the reference's compare order
 
     // per-position registers: byte offsets of the edges' slots (shot independent).  Position q = tid + r*T
     // holds bit bit_of_tab[q]; only the prior look-up and the result staging need the bit index.
@@ -435,12 +582,17 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
         }
     }
     unsigned long long n_conv = 0, n_iter = 0;
+    long long next_static = blockIdx.x; // a.queue == nullptr (latency path): CTA b takes shots b, b + grid, ...
     const bool uniform = a.uniform_prior != 0;
     const real prior_u = a.prior[0];
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh_shot = (long long)atomicAdd(a.queue, 1ull);
+        if (tid == 0) {
+            if (a.queue) sh_shot = (long long)atomicAdd(a.queue, 1ull);
+            else { sh_shot = next_static; next_static += gridDim.x; }
+            sh_exact = 0;
+        }
         __syncthreads();
         const long long shot = sh_shot;
         if (shot >= a.B) break;
@@ -463,6 +615,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             if (j < n) {
                 const real pj = uniform ? prior_u : prior[bit_of_tab[j]];
                 if (!uniform) prior_s[j] = pj;
+                if (BPOSD_TREE_MIN != 0 && sizeof(real) == 8 && !(fabs(pj) < (real)kFastPriorBound)) sh_exact = 1; // +-inf (p = 0 or 1), NaN, absurd
                 llr[r] = pj;
 #pragma unroll
                 for (int k = 0; k < DV; k++)
@@ -480,13 +633,28 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             const real alpha = (a.alpha0 == (real)0) ? (real)1 - pow2 : a.alpha0;
             const uint32_t alpha_w = sign_word(alpha);
             bool ok = true;
+            // fp64: the tree form needs an all-finite shot.  Priors are checked when the shot is set up; sums cannot
+            // overflow before pass a.exact_after (fast_exact_after: magnitudes grow at most (DV-1)-fold per pass).
+            // fp32 has no bit-exactness contract and always takes the tree form.
+            const bool exact = BPOSD_TREE_MIN != 0 && sizeof(real) == 8 && (it > a.exact_after || *reinterpret_cast<volatile int *>(&sh_exact) != 0);
             // ---- check sweep (a4) + convergence vote for the previous pass (a7) ----
+            if constexpr (kPairRows<real, VPT, MAXT>) {
+                for (int p = tid; p < m; p += 2 * T) {
+                    const int p2 = p + T;
+                    const unsigned mt = meta[p], mt2 = p2 < m ? meta[p2] : 0u;
+                    if ((mt | mt2) & 1u) ok = false;
+                    if (last) continue;
+                    if (p2 < m) fast_check_rows2<real, DC, REG>(msg + (size_t)p * RS, msg + (size_t)p2 * RS, mt, mt2, alpha, alpha_w);
+                    else fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w, exact);
+                }
+            } else {
 #pragma unroll kCheckUnroll
-            for (int p = tid; p < m; p += T) {
-                const unsigned mt = meta[p];
-                if (mt & 1u) ok = false;
-                if (last) continue;
-                fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w);
+                for (int p = tid; p < m; p += T) {
+                    const unsigned mt = meta[p];
+                    if (mt & 1u) ok = false;
+                    if (last) continue;
+                    fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w, exact);
+                }
             }
             const int all_ok = __syncthreads_and(ok ? 1 : 0);
             if (it > 1 && all_ok) { conv = true; iters = it - 1; break; }
@@ -536,7 +704,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
 
         // ---- results ----
         const bool final_here = conv || a.osd_off;
-        if (!final_here) {
+        if (!final_here && a.fail_count) { // latency path: no list, the host reads the converge flags (LLRs go to a.llr)
             if (tid == 0) {
                 const int slot = atomicAdd(a.fail_count, 1);
                 a.fail_list[slot] = (int)shot;
@@ -584,37 +752,48 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
 #define BPOSD_FAST_GEOM(DCv, DVv, EXPR)                                                          \
     do {                                                                                         \
         constexpr int DC = DCv, DV = DVv;                                                        \
-        if (maxt__ == 128) { constexpr int VPT = 2, MAXT = 128; BPOSD_FAST_REG(EXPR); }          \
-        else if (maxt__ == BPOSD_MID_MAXT) { constexpr int VPT = BPOSD_MID_VPT, MAXT = BPOSD_MID_MAXT; BPOSD_FAST_REG(EXPR); } \
-        else if (maxt__ == 512) { constexpr int VPT = 8, MAXT = 512; BPOSD_FAST_REG(EXPR); }     \
+        if (geom__ == 0) { constexpr int VPT = 2, MAXT = 128; BPOSD_FAST_REG(EXPR); }            \
+        else if (geom__ == 1) { constexpr int VPT = BPOSD_MID_VPT, MAXT = BPOSD_MID_MAXT; BPOSD_FAST_REG(EXPR); } \
+        else if (geom__ == 4) { constexpr int VPT = sizeof(real) == 8 ? BPOSD_LAT_VPT64 : BPOSD_LAT_VPT32,               \
+                                              MAXT = sizeof(real) == 8 ? BPOSD_LAT_MAXT64 : BPOSD_LAT_MAXT32; BPOSD_FAST_REG(EXPR); } \
+        else if (geom__ == 2) { constexpr int VPT = 8, MAXT = 512; BPOSD_FAST_REG(EXPR); }       \
         else { constexpr int VPT = 8, MAXT = 1024; BPOSD_FAST_REG(EXPR); }                       \
     } while (0)
 
-#define BPOSD_FAST_DISPATCH(t, n, EXPR)                                                          \
+#ifdef BPOSD_DEV_DC6 // tuning builds only: instantiate the (6, 3) degree class alone (the bench code), 4x faster to compile
+#define BPOSD_FAST_DISPATCH(t, geom, EXPR)                                                       \
     do {                                                                                         \
-        const int maxt__ = fast_maxt(n);                                                         \
+        const int geom__ = (geom);                                                               \
+        const bool reg__ = t.regular != 0;                                                       \
+        BPOSD_FAST_GEOM(6, 3, EXPR);                                                             \
+    } while (0)
+#else
+#define BPOSD_FAST_DISPATCH(t, geom, EXPR)                                                       \
+    do {                                                                                         \
+        const int geom__ = (geom);                                                               \
         const bool reg__ = t.regular != 0;                                                       \
         if (t.DC == 4) BPOSD_FAST_GEOM(4, 2, EXPR);                                              \
         else if (t.DC == 6) BPOSD_FAST_GEOM(6, 3, EXPR);                                         \
         else if (t.DC == 8) BPOSD_FAST_GEOM(8, 4, EXPR);                                         \
         else BPOSD_FAST_GEOM(16, 8, EXPR);                                                       \
     } while (0)
+#endif
 
 template <typename real>
-static inline cudaError_t fast_set_smem_t(const FastTables &t, int n, size_t smem) {
+static inline cudaError_t fast_set_smem_t(const FastTables &t, int geom, size_t smem) {
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_DISPATCH(t, n, e = cudaFuncSetAttribute(bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BPOSD_FAST_DISPATCH(t, geom, e = cudaFuncSetAttribute(bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return e;
 }
 template <typename real>
-static inline cudaError_t fast_occupancy_t(const FastTables &t, int n, int threads, size_t smem, int *occ) {
+static inline cudaError_t fast_occupancy_t(const FastTables &t, int geom, int threads, size_t smem, int *occ) {
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_DISPATCH(t, n, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, threads, smem));
+    BPOSD_FAST_DISPATCH(t, geom, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, threads, smem));
     return e;
 }
 template <typename real>
-static inline void fast_launch(const FastTables &t, const BpArgs<real> &a, int grid, int threads, int smem, cudaStream_t st) {
-    BPOSD_FAST_DISPATCH(t, a.g.n, (bp_fast_kernel<real, DC, DV, VPT, MAXT, REG><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg, t.d_row_of, t.d_bit_of)));
+static inline void fast_launch(const FastTables &t, int geom, const BpArgs<real> &a, int grid, int threads, int smem, cudaStream_t st) {
+    BPOSD_FAST_DISPATCH(t, geom, (bp_fast_kernel<real, DC, DV, VPT, MAXT, REG><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg, t.d_row_of, t.d_bit_of)));
 }
 
 } // namespace bposd

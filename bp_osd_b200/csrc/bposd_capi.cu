@@ -65,6 +65,9 @@ struct bposd_handle {
     size_t scratch_bytes = 0;
     // launch geometry
     int bp_kernel = 1, bp_threads = 256, bp_ctas_per_sm = 1, bp_smem = 0, bp_grid = 0;
+    int bp_geom = 1;                    // fast kernel geometry id (bp_fast_kernel.cuh: fast_geom)
+    int lat_geom = -1, lat_threads = 0; // latency geometry of the fast kernel (-1: none; small host batches use it)
+    long long lat_max_shots = 0;        // host batches up to this size take the latency path (0: disabled)
     int osd_threads = 256, osd_smem = 0, osd_ctas_per_sm = 1, osd_S = 0, osd_St = 0;
     bool osd_supported = true;
     // large-H OSD-0 (T does not fit in shared memory): HBM workspace, one CTA per failed shot
@@ -87,8 +90,9 @@ struct bposd_handle {
     unsigned long long *d_counters = nullptr; // 8 words
     int *d_minw = nullptr;
     double *d_cu_tab = nullptr; // channel-update tables [4, n]
-    uint8_t *h_stage = nullptr; // pinned staging of the small-batch host path (latency)
-    size_t stage_bytes = 1 << 20;
+    uint8_t *h_stage = nullptr; // pinned, device-mapped staging of the small-batch host paths (latency)
+    uint8_t *d_stage = nullptr; // the same block as the device addresses it
+    size_t stage_bytes = 4 << 20;
     bposd_stats_t stats{};
     std::string err;
 };
@@ -233,13 +237,25 @@ static int plan_geometry_t(bposd_handle *h) {
         if (!done && want == 3) return fail(h, BPOSD_EUNSUP, "the cluster BP kernel cannot be launched for this matrix / cluster size");
     } else if (want == 3) return fail(h, BPOSD_EUNSUP, "the cluster BP kernel needs min-sum and row/column degrees up to 16/8");
     int occ = 0;
+    h->lat_geom = -1; h->lat_max_shots = 0;
     if (kernel == 3) {
         occ = 1;
     } else if (kernel == 2) {
+        h->bp_geom = fast_geom(n, false);
         threads = std::min(threads, fast_maxt(n));
         if (threads * fast_vpt(n) < n) threads = fast_default_threads(n, m);
-        CU_TRY(h, fast_set_smem_t<real>(h->fast, n, smem));
-        CU_TRY(h, fast_occupancy_t<real>(h->fast, n, threads, smem, &occ));
+        CU_TRY(h, fast_set_smem_t<real>(h->fast, h->bp_geom, smem));
+        CU_TRY(h, fast_occupancy_t<real>(h->fast, h->bp_geom, threads, smem, &occ));
+        // latency geometry: one shot per SM, as many threads on it as the code has work for
+        h->lat_geom = fast_geom(n, true);
+        h->lat_threads = fast_default_threads_g(n, h->lat_geom, (int)rs);
+        int occ_l = 0;
+        if (fast_set_smem_t<real>(h->fast, h->lat_geom, smem) != cudaSuccess ||
+            fast_occupancy_t<real>(h->fast, h->lat_geom, h->lat_threads, smem, &occ_l) != cudaSuccess || occ_l < 1) {
+            cudaGetLastError();
+            h->lat_geom = h->bp_geom; h->lat_threads = threads;
+        }
+        h->lat_max_shots = h->sm_count;
     } else if (kernel == 1) {
         CU_TRY(h, cudaFuncSetAttribute(bp_generic_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bp_generic_kernel<real, true>, threads, smem));
@@ -532,6 +548,85 @@ extern "C" int bposd_get_stats(const bposd_t *h, bposd_stats_t *stats) {
     return BPOSD_OK;
 }
 
+// OSD on the shots of a chunk that BP did not settle: `d_fail_list[0 .. *d_fail_count)` are their indices into the
+// chunk; `llr` is indexed by shot (llr_by_shot) or by position in the list.  All pointers are device-visible.
+template <typename real>
+static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const uint8_t *d_synd, const real *llr, int llr_by_shot,
+                      const int *d_fail_count, const int *d_fail_list, uint8_t *d_osd0, uint8_t *d_osdw,
+                      unsigned long long *d_stat, long long Bc, bool per_shot_priors, const double *d_weights, int *launches) {
+    const int n = h->n, m = h->m;
+    if (h->osd_large) {
+        const int ogrid = (int)std::min<long long>(Bc, h->osdl_grid);
+        if (h->osdl_alloc_grid < ogrid) {
+            cudaFree(h->d_osdl_mask); cudaFree(h->d_osdl_order); cudaFree(h->d_osdl_piv_row); cudaFree(h->d_osdl_piv_pos); cudaFree(h->d_osdl_pstart);
+            h->d_osdl_mask = nullptr; h->d_osdl_order = h->d_osdl_piv_row = h->d_osdl_piv_pos = h->d_osdl_pstart = nullptr;
+            h->osdl_alloc_grid = 0;
+            const size_t gsz = (size_t)ogrid, mn = (size_t)std::min(m, n);
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_mask, gsz * h->osdl_npanels * m * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_order, gsz * n * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_row, gsz * std::max<size_t>(mn, 1) * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_pos, gsz * std::max<size_t>(mn, 1) * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_pstart, gsz * ((size_t)h->osdl_npanels + 1) * 4));
+            h->osdl_alloc_grid = ogrid;
+        }
+        OsdLargeArgs<real> o;
+        o.g = g;
+        o.synd = d_synd;
+        o.llr = llr;
+        o.llr_by_shot = llr_by_shot;
+        o.fail_count = d_fail_count;
+        o.fail_list = d_fail_list;
+        o.osd0 = d_osd0; o.osdw = d_osdw;
+        o.stat = d_stat;
+        o.maxrank = h->rank;
+        o.npanels = h->osdl_npanels;
+        o.ws_mask = h->d_osdl_mask; o.ws_order = h->d_osdl_order;
+        o.ws_piv_row = h->d_osdl_piv_row; o.ws_piv_pos = h->d_osdl_piv_pos; o.ws_pstart = h->d_osdl_pstart;
+        osd0_large_kernel<real><<<ogrid, 1024, h->osdl_smem, st>>>(o);
+        CU_TRY(h, cudaGetLastError());
+        (*launches)++;
+    } else if (h->osd_panel) {
+        OsdPanelArgs<real> o;
+        o.g = g;
+        o.S = h->osd_S; o.nb = (std::min(m, n) + 31) / 32; o.maxrank = h->rank;
+        o.method = h->osd_method; o.order = h->osd_order;
+        o.uniform = (per_shot_priors || d_weights) ? 0 : h->uniform;
+        o.weight = d_weights ? d_weights : h->d_weight;
+        o.weight_stride = d_weights ? n : 0;
+        o.synd = d_synd;
+        o.llr = llr;
+        o.llr_by_shot = llr_by_shot;
+        o.fail_count = d_fail_count;
+        o.fail_list = d_fail_list;
+        o.osd0 = d_osd0; o.osdw = d_osdw;
+        o.stat = d_stat;
+        const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
+        osd_panel_kernel<real><<<ogrid, h->osd_threads, h->osdp_smem, st>>>(o);
+        CU_TRY(h, cudaGetLastError());
+        (*launches)++;
+    } else {
+        OsdArgs<real> o;
+        o.g = g;
+        o.S = h->osd_S; o.St = h->osd_St;
+        o.method = h->osd_method; o.order = h->osd_order;
+        o.uniform = (per_shot_priors || d_weights) ? 0 : h->uniform;
+        o.weight = d_weights ? d_weights : h->d_weight;
+        o.weight_stride = d_weights ? n : 0;
+        o.synd = d_synd;
+        o.llr = llr;
+        o.llr_by_shot = llr_by_shot;
+        o.fail_count = d_fail_count;
+        o.fail_list = d_fail_list;
+        o.osd0 = d_osd0; o.osdw = d_osdw;
+        o.stat = d_stat;
+        const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
+        osd_kernel<real><<<ogrid, h->osd_threads, h->osd_smem, st>>>(o);
+        CU_TRY(h, cudaGetLastError());
+        (*launches)++;
+    }
+    return BPOSD_OK;
+}
+
 // Enqueue one chunk (BP -> OSD -> control-word read-back) on `st`.  No host synchronisation.
 template <typename real>
 static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st, const uint8_t *d_synd, long long Bc,
@@ -561,6 +656,7 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     a.max_iter = h->max_iter;
     a.method = h->bp_method;
     a.alpha0 = (real)h->alpha;
+    a.exact_after = fast_exact_after(h->max_col_deg, h->max_iter, h->alpha);
     a.uniform_prior = d_priors ? 0 : h->uniform_prior;
     if (d_priors) { a.prior = static_cast<const real *>(d_priors); a.prior_stride = n; }
     else { a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32; a.prior_stride = 0; }
@@ -582,80 +678,18 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     if (h->bp_kernel == 3) {
         const int ncl = (int)std::min<long long>(Bc, h->clus_nclusters);
         CU_TRY(h, cluster_launch<real>(h->clus, a, ncl, h->bp_threads, (size_t)h->bp_smem, h->clus_flip_table, st));
-    } else if (h->bp_kernel == 2) fast_launch<real>(h->fast, a, grid, h->bp_threads, h->bp_smem, st);
+    } else if (h->bp_kernel == 2) fast_launch<real>(h->fast, h->bp_geom, a, grid, h->bp_threads, h->bp_smem, st);
     else if (h->bp_kernel == 1) bp_generic_kernel<real, true><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
     else bp_generic_kernel<real, false><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
     CU_TRY(h, cudaGetLastError());
     launches++;
     CU_TRY(h, cudaEventRecord(sl.ev[1], st));
-    if (osd_on && h->osd_large) {
-        const int ogrid = (int)std::min<long long>(Bc, h->osdl_grid);
-        if (h->osdl_alloc_grid < ogrid) {
-            cudaFree(h->d_osdl_mask); cudaFree(h->d_osdl_order); cudaFree(h->d_osdl_piv_row); cudaFree(h->d_osdl_piv_pos); cudaFree(h->d_osdl_pstart);
-            h->d_osdl_mask = nullptr; h->d_osdl_order = h->d_osdl_piv_row = h->d_osdl_piv_pos = h->d_osdl_pstart = nullptr;
-            h->osdl_alloc_grid = 0;
-            const size_t gsz = (size_t)ogrid, mn = (size_t)std::min(m, n);
-            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_mask, gsz * h->osdl_npanels * m * 4));
-            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_order, gsz * n * 4));
-            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_row, gsz * std::max<size_t>(mn, 1) * 4));
-            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_piv_pos, gsz * std::max<size_t>(mn, 1) * 4));
-            CU_TRY(h, cudaMalloc((void **)&h->d_osdl_pstart, gsz * ((size_t)h->osdl_npanels + 1) * 4));
-            h->osdl_alloc_grid = ogrid;
-        }
-        OsdLargeArgs<real> o;
-        o.g = a.g;
-        o.synd = a.synd;
-        o.llr = llr_out ? llr_out : static_cast<const real *>(sl.d_fail_llr);
-        o.llr_by_shot = llr_out ? 1 : 0;
-        o.fail_count = d_fail_count;
-        o.fail_list = sl.d_fail_list;
-        o.osd0 = a.osd0; o.osdw = a.osdw;
-        o.stat = sl.d_ctrl + 1;
-        o.maxrank = h->rank;
-        o.npanels = h->osdl_npanels;
-        o.ws_mask = h->d_osdl_mask; o.ws_order = h->d_osdl_order;
-        o.ws_piv_row = h->d_osdl_piv_row; o.ws_piv_pos = h->d_osdl_piv_pos; o.ws_pstart = h->d_osdl_pstart;
-        osd0_large_kernel<real><<<ogrid, 1024, h->osdl_smem, st>>>(o);
-        CU_TRY(h, cudaGetLastError());
-        launches++;
-    } else if (osd_on && h->osd_panel) {
-        OsdPanelArgs<real> o;
-        o.g = a.g;
-        o.S = h->osd_S; o.nb = (std::min(m, n) + 31) / 32; o.maxrank = h->rank;
-        o.method = h->osd_method; o.order = h->osd_order;
-        o.uniform = (d_priors || d_weights) ? 0 : h->uniform;
-        o.weight = d_weights ? d_weights : h->d_weight;
-        o.weight_stride = d_weights ? n : 0;
-        o.synd = a.synd;
-        o.llr = llr_out ? llr_out : static_cast<const real *>(sl.d_fail_llr);
-        o.llr_by_shot = llr_out ? 1 : 0;
-        o.fail_count = d_fail_count;
-        o.fail_list = sl.d_fail_list;
-        o.osd0 = a.osd0; o.osdw = a.osdw;
-        o.stat = sl.d_ctrl + 1;
-        const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
-        osd_panel_kernel<real><<<ogrid, h->osd_threads, h->osdp_smem, st>>>(o);
-        CU_TRY(h, cudaGetLastError());
-        launches++;
-    } else if (osd_on) {
-        OsdArgs<real> o;
-        o.g = a.g;
-        o.S = h->osd_S; o.St = h->osd_St;
-        o.method = h->osd_method; o.order = h->osd_order;
-        o.uniform = (d_priors || d_weights) ? 0 : h->uniform;
-        o.weight = d_weights ? d_weights : h->d_weight;
-        o.weight_stride = d_weights ? n : 0;
-        o.synd = a.synd;
-        o.llr = llr_out ? llr_out : static_cast<const real *>(sl.d_fail_llr);
-        o.llr_by_shot = llr_out ? 1 : 0;
-        o.fail_count = d_fail_count;
-        o.fail_list = sl.d_fail_list;
-        o.osd0 = a.osd0; o.osdw = a.osdw;
-        o.stat = sl.d_ctrl + 1;
-        const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
-        osd_kernel<real><<<ogrid, h->osd_threads, h->osd_smem, st>>>(o);
-        CU_TRY(h, cudaGetLastError());
-        launches++;
+    if (osd_on) {
+        int nl = 0;
+        const int rc = launch_osd<real>(h, st, a.g, a.synd, llr_out ? llr_out : static_cast<const real *>(sl.d_fail_llr), llr_out ? 1 : 0,
+                                        d_fail_count, sl.d_fail_list, a.osd0, a.osdw, sl.d_ctrl + 1, Bc, d_priors != nullptr, d_weights, &nl);
+        if (rc) return rc;
+        launches += nl;
     }
     CU_TRY(h, cudaEventRecord(sl.ev[2], st));
     CU_TRY(h, cudaMemcpyAsync(sl.h_ctrl, sl.d_ctrl, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -753,6 +787,107 @@ static int ensure_buffers(bposd_handle *h, bposd_handle::Slot &sl, long long B, 
     return BPOSD_OK;
 }
 
+static int ensure_stage(bposd_handle *h) {
+    if (h->h_stage) return BPOSD_OK;
+    CU_TRY(h, cudaHostAlloc((void **)&h->h_stage, h->stage_bytes, cudaHostAllocMapped));
+    CU_TRY(h, cudaHostGetDevicePointer((void **)&h->d_stage, h->h_stage, 0));
+    return BPOSD_OK;
+}
+
+// Latency path of the host-buffer decode: a handful of shots, single-shot decode() above all.  One kernel launch and
+// one synchronisation per call: the kernel reads the syndromes from, and writes every result to, pinned host memory
+// that the device addresses directly (no copy calls, no control words, no events), every shot has an SM to itself
+// (grid = B <= SM count, static assignment) and the CTA uses the latency geometry (bp_fast_kernel.cuh: few bits per
+// thread, so a pass is as short as one SM can make it).  The host reads the converge flags; only if a shot did not
+// converge (0.14 % on the bench code) does it hand the list to the OSD kernel and synchronise a second time.
+template <typename real>
+static int decode_latency_t(bposd_handle *h, const uint8_t *h_synd, long long B, uint8_t *h_osdw, uint8_t *h_osd0,
+                            uint8_t *h_bp, void *h_llr, uint8_t *h_conv, int32_t *h_iter, bool *taken) {
+    const int n = h->n, m = h->m;
+    *taken = false;
+    auto al = [](size_t x) { return (x + 15) / 16 * 16; };
+    const size_t o_synd = 0, o_osdw = o_synd + al((size_t)B * m), o_osd0 = o_osdw + al((size_t)B * n), o_bp = o_osd0 + al((size_t)B * n),
+                 o_llr = o_bp + al((size_t)B * n), o_conv = o_llr + (h_llr ? al((size_t)B * n * sizeof(real)) : 0),
+                 o_iter = o_conv + al((size_t)B), o_list = o_iter + al((size_t)B * 4), o_cnt = o_list + al((size_t)B * 4),
+                 total = o_cnt + 16;
+    if (total > h->stage_bytes) return BPOSD_OK;
+    *taken = true;
+    int rc = ensure_stage(h);
+    if (rc) return rc;
+    for (auto &s2 : h->slot) {
+        rc = collect_chunk(h, s2);
+        if (rc) return rc;
+    }
+    bposd_handle::Slot &sl = h->slot[0];
+    const bool osd_on = h->osd_method != BPOSD_OSD_OFF;
+    if (!h_llr) {
+        rc = ensure_buffers(h, sl, B, true, false);
+        if (rc) return rc;
+    }
+    cudaStream_t st = sl.stream;
+    uint8_t *sg = h->h_stage, *dg = h->d_stage;
+    std::memcpy(sg + o_synd, h_synd, (size_t)B * m);
+    BpArgs<real> a;
+    a.g = graph_of(h);
+    a.max_iter = h->max_iter;
+    a.method = h->bp_method;
+    a.alpha0 = (real)h->alpha;
+    a.exact_after = fast_exact_after(h->max_col_deg, h->max_iter, h->alpha);
+    a.uniform_prior = h->uniform_prior;
+    a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32;
+    a.prior_stride = 0;
+    a.synd = dg + o_synd;
+    a.B = B;
+    a.bp = h_bp ? dg + o_bp : nullptr;
+    a.osd0 = h_osd0 ? dg + o_osd0 : nullptr;
+    a.osdw = h_osdw ? dg + o_osdw : nullptr;
+    a.llr = h_llr ? reinterpret_cast<real *>(dg + o_llr) : static_cast<real *>(sl.b_llr);
+    a.converge = dg + o_conv;
+    a.iter = reinterpret_cast<int *>(dg + o_iter);
+    a.fail_count = nullptr; a.fail_list = nullptr; a.fail_llr = nullptr;
+    a.osd_off = osd_on ? 0 : 1;
+    a.queue = nullptr; a.stat = nullptr;
+    a.g_scratch = nullptr; a.g_dec = nullptr;
+    fast_launch<real>(h->fast, h->lat_geom, a, (int)B, h->lat_threads, h->bp_smem, st);
+    CU_TRY(h, cudaGetLastError());
+    // (polling a completion flag in pinned memory instead was measured: no gain over this, profiles/r03b_lat_probe.log)
+    CU_TRY(h, cudaStreamSynchronize(st));
+    int launches = 1;
+    const uint8_t *conv = sg + o_conv;
+    const int32_t *iters = reinterpret_cast<const int32_t *>(sg + o_iter);
+    int *list = reinterpret_cast<int *>(sg + o_list), *cnt = reinterpret_cast<int *>(sg + o_cnt);
+    long long nconv = 0, niter = 0;
+    int nfail = 0;
+    for (long long b = 0; b < B; b++) {
+        nconv += conv[b] ? 1 : 0;
+        niter += iters[b];
+        if (!conv[b]) list[nfail++] = (int)b;
+    }
+    if (osd_on && nfail > 0 && (a.osd0 || a.osdw)) {
+        *cnt = nfail;
+        int nl = 0;
+        rc = launch_osd<real>(h, st, a.g, a.synd, a.llr, 1, reinterpret_cast<const int *>(dg + o_cnt),
+                              reinterpret_cast<const int *>(dg + o_list), a.osd0, a.osdw, nullptr, nfail, false, nullptr, &nl);
+        if (rc) return rc;
+        CU_TRY(h, cudaStreamSynchronize(st));
+        launches += nl;
+    }
+    if (h_osdw) std::memcpy(h_osdw, sg + o_osdw, (size_t)B * n);
+    if (h_osd0) std::memcpy(h_osd0, sg + o_osd0, (size_t)B * n);
+    if (h_bp) std::memcpy(h_bp, sg + o_bp, (size_t)B * n);
+    if (h_llr) std::memcpy(h_llr, sg + o_llr, (size_t)B * n * sizeof(real));
+    if (h_conv) std::memcpy(h_conv, conv, (size_t)B);
+    if (h_iter) std::memcpy(h_iter, iters, (size_t)B * 4);
+    h->stats = bposd_stats_t{};
+    h->stats.shots = B;
+    h->stats.bp_converged = nconv;
+    h->stats.bp_iterations = niter;
+    h->stats.osd_invocations = osd_on ? nfail : 0;
+    h->stats.launches = launches;
+    h->stats.chunks = 1;
+    return BPOSD_OK;
+}
+
 // Host-buffer decode: the batch is cut into chunks that alternate between the two slots, each on its
 // own stream (H2D -> BP -> OSD -> D2H in stream order), so the copies of one chunk overlap the
 // kernels of the other.  Kernels that share a per-handle scratch (HBM-scratch BP, HBM OSD) run
@@ -763,6 +898,11 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
     const int n = h->n, m = h->m;
     int rc = check_osd_supported(h);
     if (rc) return rc;
+    if (h->bp_kernel == 2 && h->lat_geom >= 0 && B <= h->lat_max_shots) {
+        bool taken = false;
+        rc = decode_latency_t<real>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter, &taken);
+        if (rc || taken) return rc;
+    }
     const bool need_ws = h->osd_method != BPOSD_OSD_OFF && !h_llr;
     const bool pipelined = h->bp_kernel != 0 && !h->osd_large && B >= 2 * h->host_chunk_min;
     long long chunk = B;
@@ -779,7 +919,8 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
                      o_conv = o_llr + (h_llr ? al((size_t)B * n * sizeof(real)) : 0), o_iter = o_conv + (h_conv ? al((size_t)B) : 0),
                      total = o_iter + (h_iter ? al((size_t)B * 4) : 0);
         if (!pipelined && chunk == B && total <= h->stage_bytes) {
-            if (!h->h_stage) CU_TRY(h, cudaMallocHost((void **)&h->h_stage, h->stage_bytes));
+            rc = ensure_stage(h);
+            if (rc) return rc;
             bposd_handle::Slot &sl = h->slot[0];
             rc = collect_chunk(h, sl);
             if (rc) return rc;

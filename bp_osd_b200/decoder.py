@@ -140,6 +140,7 @@ class BpOsdDecoder:
         self.ms_scaling_factor = float(ms_scaling_factor)
         # result attributes, overwritten by every decode (reference semantics)
         self.osdw_decoding = np.zeros(self.n, dtype=int)
+        self._lazy = None
         self.osd0_decoding = np.zeros(self.n, dtype=int)
         self.bp_decoding = np.zeros(self.n, dtype=int)
         self.log_prob_ratios = np.zeros(self.n, dtype=np.float64)
@@ -209,31 +210,73 @@ class BpOsdDecoder:
 
     # ------------------------------------------------------------------ decode
     def decode(self, syndrome):
-        """Decode one syndrome; returns ``osdw_decoding`` and refreshes the result attributes."""
-        s = np.asarray(syndrome)
+        """Decode one syndrome; returns ``osdw_decoding`` and refreshes the result attributes.
+
+        The call is one ``bposd_decode_host`` with B = 1 (the library's latency path: one kernel launch, results
+        written straight to pinned host memory).  ``osd0_decoding``, ``bp_decoding`` and ``log_prob_ratios`` are
+        converted to the caller's dtype when they are first read, not here."""
+        s = syndrome if type(syndrome) is np.ndarray else np.asarray(syndrome)
         if s.ndim != 1 or s.shape[0] != self.m:
             raise ValueError(f"syndrome must have length {self.m}")
-        dtype = s.dtype if np.issubdtype(s.dtype, np.integer) else int
-        if self._one is None:   # result buffers of the single-shot path are allocated once
-            self._one = {"osdw": np.empty((1, self.n), np.uint8), "osd0": np.empty((1, self.n), np.uint8),
-                         "bp": np.empty((1, self.n), np.uint8), "llr": np.empty((1, self.n), self._real),
-                         "converge": np.empty(1, np.uint8), "iter": np.empty(1, np.int32),
-                         "synd": np.empty((1, self.m), np.uint8)}
-        synd = self._one["synd"]
-        if s.dtype == np.bool_:
-            np.copyto(synd[0], s, casting="unsafe")
-        elif np.issubdtype(s.dtype, np.integer):
-            np.bitwise_and(s, 1, out=synd[0], casting="unsafe")
+        kind = s.dtype.kind
+        dtype = s.dtype if kind in "iu" else int
+        one = self._one
+        if one is None:   # result buffers (and their raw addresses) of the single-shot path are set up once
+            one = self._one = {"osdw": np.empty((1, self.n), np.uint8), "osd0": np.empty((1, self.n), np.uint8),
+                               "bp": np.empty((1, self.n), np.uint8), "llr": np.empty((1, self.n), self._real),
+                               "converge": np.empty(1, np.uint8), "iter": np.empty(1, np.int32),
+                               "synd": np.empty((1, self.m), np.uint8)}
+            one["args"] = tuple(one[k].ctypes.data for k in ("synd", "osdw", "osd0", "bp", "llr", "converge", "iter"))
+            one["fn"] = _capi.load().bposd_decode_host
+            one["rows"] = tuple(one[k][0] for k in ("synd", "osdw", "osd0", "bp", "llr"))
+        synd0, osdw0 = one["rows"][0], one["rows"][1]
+        if kind == "b":
+            np.copyto(synd0, s, casting="unsafe")
+        elif kind in "iu":
+            np.bitwise_and(s, 1, out=synd0, casting="unsafe")
         else:
-            synd[0] = s.astype(np.int64) & 1
-        res = self._decode_host(synd, out=self._one)
-        self.osdw_decoding = res.osdw_decoding[0].astype(dtype)
-        self.osd0_decoding = res.osd0_decoding[0].astype(dtype)
-        self.bp_decoding = res.bp_decoding[0].astype(dtype)
-        self.log_prob_ratios = res.log_prob_ratios[0].astype(np.float64)
-        self.converge = bool(res.converge[0])
-        self.iter = int(res.iter[0])
+            synd0[:] = s.astype(np.int64) & 1
+        ptr = one["args"]
+        rc = one["fn"](self._h, ptr[0], 1, ptr[1], ptr[2], ptr[3], ptr[4], ptr[5], ptr[6])
+        if rc:
+            self._check(rc)
+        self._lazy = (one["rows"], dtype)
+        self._osd0 = self._bp = self._llr = None
+        self.osdw_decoding = osdw0.astype(dtype)
+        self.converge = bool(one["converge"][0])
+        self.iter = int(one["iter"][0])
         return self.osdw_decoding
+
+    # results of the last decode() that the caller may or may not look at: converted on first access
+    @property
+    def osd0_decoding(self):
+        if self._osd0 is None and self._lazy is not None:
+            self._osd0 = self._lazy[0][2].astype(self._lazy[1])
+        return self._osd0
+
+    @osd0_decoding.setter
+    def osd0_decoding(self, value):
+        self._osd0 = value
+
+    @property
+    def bp_decoding(self):
+        if self._bp is None and self._lazy is not None:
+            self._bp = self._lazy[0][3].astype(self._lazy[1])
+        return self._bp
+
+    @bp_decoding.setter
+    def bp_decoding(self, value):
+        self._bp = value
+
+    @property
+    def log_prob_ratios(self):
+        if self._llr is None and self._lazy is not None:
+            self._llr = self._lazy[0][4].astype(np.float64)
+        return self._llr
+
+    @log_prob_ratios.setter
+    def log_prob_ratios(self, value):
+        self._llr = value
 
     def _decode_host(self, synd_u8: np.ndarray, want_llr: bool = True, want_all: bool = True,
                      out: Optional[dict] = None) -> BatchResult:

@@ -112,7 +112,12 @@ int bposd_decode_batch(bposd_t *h, const uint8_t *d_syndromes, int64_t B, const 
  * requested outputs back (NULL = not wanted).  This is what the reference-facing
  * `decode()` / `decode_batch(numpy)` call goes through.  Large batches are cut into chunks that are
  * double-buffered over two internal streams, so the copies overlap the kernels; pass pinned host
- * memory for the copies to be asynchronous. */
+ * memory for the copies to be asynchronous.
+ * Batches of at most one shot per SM (single-shot decode() above all) take a latency path: one kernel
+ * launch and one synchronisation, syndromes read from and results written to pinned host memory that the
+ * device addresses directly, one SM per shot with few bits per thread; the OSD kernel is launched only if
+ * the converge flags the host reads back say a shot needs it.  bposd_stats_t then carries no event times
+ * (ms_bp = ms_osd = 0). */
 int bposd_decode_host(bposd_t *h, const uint8_t *h_syndromes, int64_t B, uint8_t *h_osdw,
                       uint8_t *h_osd0, uint8_t *h_bp, void *h_llr, uint8_t *h_converge,
                       int32_t *h_iter);

@@ -17,7 +17,9 @@ def load_golden(name):
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    """Decoder goldens only (ref_*.npz are code-construction data from the reference, see make_code_golden.py)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                  if not os.path.basename(p).startswith("ref_"))
 
 
 def random_syndromes(H, p, B, seed):

@@ -627,3 +627,48 @@ def test_random_parity_check_matrices(torch_cuda, oracle_mod, seed):
                 assert_exact(out, ref)
             except AssertionError as ex:
                 raise AssertionError(f"kernel {kernel} osd variant {variant} m={m} n={n}: {ex}")
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("cfg,p,kw", [
+    (1, 0.10, dict(max_iter=3, bp_method="ms", ms_scaling_factor=0.625, osd_method="osd_e", osd_order=6)),
+    (2, 0.06, dict(MS_CS7, max_iter=20)),
+    (3, 0.05, MS_CS7),
+    (3, 0.06, dict(MS_CS7, max_iter=30)),
+])
+def test_latency_path_small_host_batches(torch_cuda, oracle_mod, cfg_codes, cfg, p, kw, precision):
+    """Host batches of at most one shot per SM take the latency path of bposd_decode_host (one launch, results written
+    straight to pinned host memory, latency geometry): same bits as the oracle, shot by shot
+    through decode() and as small batches, including shots that need the OSD stage."""
+    from bp_osd_b200 import BpOsdDecoder
+    H = cfg_codes(cfg).hz
+    _, syn = random_syndromes(H, p, 48, seed=300 + cfg)
+    ref = oracle_mod.OracleDecoder(H, error_rate=p, **kw).decode_batch(syn)
+    d = BpOsdDecoder(H, error_rate=p, precision=precision, **kw)
+    if precision == 64:
+        assert (ref["converge"] == 0).any() or cfg == 3, "the case should exercise the OSD stage"
+    for B in (1, 5, 48):
+        r = d.decode_batch(syn[:B])
+        st = d.stats()
+        assert st["shots"] == B and st["chunks"] == 1
+        assert H.shape[1] > 2048 or d.info()["bp_kernel"] != 2 or st["launches"] <= 2   # BP (+ OSD), no copies, no sampler
+        if precision == 64:
+            out = dict(osdw=r.osdw_decoding, osd0=r.osd0_decoding, bp=r.bp_decoding, llr=r.log_prob_ratios,
+                       converge=r.converge, iter=r.iter)
+            assert_exact(out, {k: v[:B] for k, v in ref.items()})
+            assert st["bp_converged"] == int(ref["converge"][:B].sum())
+            assert st["bp_iterations"] == int(ref["iter"][:B].sum())
+            assert st["osd_invocations"] == int((ref["converge"][:B] == 0).sum())
+        else:
+            assert not ((H @ r.osdw_decoding.T) % 2 != syn[:B].T).any(), "fp32 osdw must still satisfy the syndrome"
+    for i in range(12):
+        s = syn[i].astype(np.int64)
+        out = d.decode(s)
+        assert out.dtype == np.int64 and out is d.osdw_decoding
+        if precision == 64:
+            assert (out == ref["osdw"][i]).all() and (d.osd0_decoding == ref["osd0"][i]).all()
+            assert (d.bp_decoding == ref["bp"][i]).all() and d.bp_decoding.dtype == np.int64
+            assert (d.log_prob_ratios == ref["llr"][i]).all()
+            assert d.converge == bool(ref["converge"][i]) and d.iter == int(ref["iter"][i])
+        else:
+            assert not ((H @ out) % 2 != syn[i]).any()
