@@ -122,13 +122,6 @@ template <typename real, int MAXT> constexpr int fast_minb() {
     return (65536 / (MAXT * cap)) < 1 ? 1 : (65536 / (MAXT * cap));
 }
 
-// geometries whose check sweep takes two rows per thread at a time (fast_check_rows2): the fp64 latency geometry
-#ifndef BPOSD_PAIR_ROWS
-#define BPOSD_PAIR_ROWS 1
-#endif
-template <typename real, int VPT, int MAXT>
-constexpr bool kPairRows = BPOSD_PAIR_ROWS != 0 && BPOSD_TREE_MIN == 0 && sizeof(real) == 8 && VPT == BPOSD_LAT_VPT64 && MAXT == BPOSD_LAT_MAXT64 &&
-                           !(VPT == BPOSD_MID_VPT && MAXT == BPOSD_MID_MAXT) && MAXT >= 512;
 static inline int fast_default_threads_g(int n, int geom, int elem_bytes) {
     const int vpt = fast_vpt_g(geom, elem_bytes);
     int t = ((n + vpt - 1) / vpt + 31) / 32 * 32;
@@ -333,25 +326,15 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
     return cudaMemcpy(t.d_cdeg, cd.data(), cd.size(), cudaMemcpyHostToDevice);
 }
 
-// Bound behind the fp64 tree-min check update.  With P = max |prior| <= kFastPriorBound, B_t = max |bit->check
-// message| after pass t and g = max column degree - 1:  B_0 = P,  B_t <= P + g*B_{t-1}  (g also carries a scaling factor above 1)  (check->bit magnitudes never
-// exceed the bit->check ones),  so every partial sum of pass t is below P*DV*(t+1)*max(g,1)^t.  Up to the returned
-// pass that stays under 2^1023: no infinity and therefore no NaN can exist, and the order of the compares is free.
-constexpr double kFastPriorBound = 18446744073709551616.0; // 2^64
-static inline int fast_exact_after(int max_col_deg, int max_iter, double alpha) {
-    const double a1 = (alpha > 1.0) ? alpha : 1.0; // a scaling factor above 1 amplifies (never used by the reference)
-    if (!(a1 < 1e30)) return 0;
-    const double g = std::max(max_col_deg - 1, 1) * a1;
-    const double room = 1023.0 - 64.0 - std::log2((double)std::max(max_col_deg, 1) * a1) - std::log2((double)max_iter + 2.0);
-    if (g <= 1.0) return room > 0 ? 0x7fffffff : 0;
-    return (int)std::max(0.0, std::floor(room / std::log2(g)));
-}
+// slots after the last row that thread positions beyond the last bit read and write (regular codes: the bit sweep
+// then needs no "is this position a bit" guard); never read by a check
+constexpr int kFastDummySlots = 8;
 
 template <typename real>
 static inline size_t fast_smem_bytes(const FastTables &t, int n, int m) {
     if (t.DC == 0) return (size_t)1 << 40;
     // the message array doubles as the staging area of the per-shot results ([n] reals + [n] bytes)
-    size_t msgs = (std::max((size_t)m * fast_row_stride(t.DC, (int)sizeof(real)) * sizeof(real), (size_t)n * (sizeof(real) + 1)) + 15) / 16 * 16;
+    size_t msgs = (std::max(((size_t)m * fast_row_stride(t.DC, (int)sizeof(real)) + kFastDummySlots) * sizeof(real), (size_t)n * (sizeof(real) + 1)) + 15) / 16 * 16;
     size_t meta = ((size_t)m + 15) / 16 * 16;
     size_t prior = ((size_t)n * sizeof(real) + 15) / 16 * 16; // copy of the priors when they are not uniform
     return msgs + meta + prior + 16;
@@ -401,44 +384,48 @@ __device__ __forceinline__ float abs_bits(float x) { return __uint_as_float(__fl
 __device__ __forceinline__ double with_sign_word(double x, uint32_t w) { return __hiloint2double((int)w, __double2loint(x)); }
 __device__ __forceinline__ float with_sign_word(float, uint32_t w) { return __uint_as_float(w); }
 template <typename real> __device__ __forceinline__ real lt_min(real a, real b) { return (a < b) ? a : b; } // `if (a < t) t = a`
+// the same on magnitudes, carrying the raw value: `if (|a| < |t|) t = a`
+template <typename real> __device__ __forceinline__ real mag_min(real a, real b) { return (fabs(a) < fabs(b)) ? a : b; }
 
 // One check of the min-sum check sweep (row a4), in place on its DC-slot row.  `mt` is the check's meta
-// byte (bit 7 syndrome, bits 1-5 degree).  Order-exact form: prefix/suffix running minima in the
-// reference's own order (`if (a < t) t = a`), which also reproduces its NaN propagation; used for shots
-// that carry an infinite or NaN value (fast_check_row_tree below handles the all-finite case).
+// byte (bit 7 syndrome, bits 1-5 degree).  Prefix/suffix running minima in the reference's own compare order
+// (`if (a < t) t = a`), which also reproduces its NaN propagation on shots whose sums overflowed.
+// (A shallower tree of compares for all-finite shots and two rows interleaved per thread were both built, verified
+// bit-exact and measured not faster: profiles/r03a_ab_probe.log, r03d_ab_probe.log.)
 template <typename real, int DC, bool REG>
 __device__ __forceinline__ void fast_check_compute(real (&v)[DC], real (&out)[DC], unsigned mt, real alpha, uint32_t alpha_w) {
+    // Magnitudes are never materialised: the compares take |a| < |b| and select the raw values, the final multiply
+    // takes |min|, and sm_100a folds both into operand modifiers of DSETP / DMUL (FSETP / FMUL) -- 12 instructions
+    // fewer per row of 6 than clearing the sign bits first.  Compare order and tie behaviour are the reference's.
     real suf[DC];
-    uint32_t sw[DC];
     uint32_t X = (mt & 0x80u) << 24;
 #pragma unroll
-    for (int k = 0; k < DC; k++) { sw[k] = sign_word(v[k]); X ^= sw[k]; v[k] = abs_bits(v[k]); }
+    for (int k = 0; k < DC; k++) X ^= sign_word(v[k]);
     // suffix minima first, then one running prefix minimum: out[k] = min(prefix before k, suffix after k)
     suf[DC - 1] = v[DC - 1];
 #pragma unroll
-    for (int k = DC - 2; k >= 1; k--) suf[k] = lt_min(v[k], suf[k + 1]);
+    for (int k = DC - 2; k >= 1; k--) suf[k] = mag_min(v[k], suf[k + 1]);
     real run = v[0];
     out[0] = (DC > 1) ? suf[DC > 1 ? 1 : 0] : real_max<real>();
 #pragma unroll
-    for (int k = 1; k < DC - 1; k++) { out[k] = lt_min(suf[k + 1], run); run = lt_min(v[k], run); }
+    for (int k = 1; k < DC - 1; k++) { out[k] = mag_min(suf[k + 1], run); run = mag_min(v[k], run); }
     if (DC > 1) out[DC - 1] = run;
-    const real all_min = (DC > 1) ? lt_min(v[DC - 1], run) : v[0];
-    if (all_min == (real)0) {
+    const real all_min = (DC > 1) ? mag_min(v[DC - 1], run) : v[0];
+    if (fabs(all_min) == (real)0) {
         // some message is +-0: "<= 0" counts +0 as negative, the sign bit does not -> exact path
-        // (the magnitudes are already in v; a zero magnitude with a clear sign bit is the +0 case)
         int tot = (int)(mt >> 7);
 #pragma unroll
-        for (int k = 0; k < DC; k++) tot += ((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0;
+        for (int k = 0; k < DC; k++) tot += ((sign_word(v[k]) >> 31) | (fabs(v[k]) == (real)0 ? 1u : 0u)) ? 1 : 0;
 #pragma unroll
         for (int k = 0; k < DC; k++) {
-            const int sg = tot + (((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0);
-            out[k] = out[k] * ((sg & 1) ? -alpha : alpha);
+            const int sg = tot + (((sign_word(v[k]) >> 31) | (fabs(v[k]) == (real)0 ? 1u : 0u)) ? 1 : 0);
+            out[k] = fabs(out[k]) * ((sg & 1) ? -alpha : alpha);
         }
     } else {
         // sign of edge k = syndrome ^ (parity of all sign bits) ^ own sign bit; fold it into alpha
         const uint32_t XA = (X & 0x80000000u) ^ alpha_w;
 #pragma unroll
-        for (int k = 0; k < DC; k++) out[k] = out[k] * with_sign_word(alpha, XA ^ (sw[k] & 0x80000000u));
+        for (int k = 0; k < DC; k++) out[k] = fabs(out[k]) * with_sign_word(alpha, XA ^ (sign_word(v[k]) & 0x80000000u));
     }
     if (!REG) {
         const int deg = (mt >> 1) & 0x1f;
@@ -448,101 +435,50 @@ __device__ __forceinline__ void fast_check_compute(real (&v)[DC], real (&out)[DC
 }
 
 template <typename real, int DC, bool REG>
-__device__ __forceinline__ void fast_check_row_exact(real *row, unsigned mt, real alpha, uint32_t alpha_w) {
+__device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alpha, uint32_t alpha_w) {
     real v[DC], out[DC];
     RowIO<real, DC>::load(row, v);
     fast_check_compute<real, DC, REG>(v, out, mt, alpha, alpha_w);
     RowIO<real, DC>::store(row, out);
 }
 
-// Two rows at once: both rows are loaded before either is updated, so the two dependent compare/select chains
-// interleave.  Used by the latency geometry, where one CTA has the SM to itself and a pass is bound by those chains,
-// not by issue slots (throughput geometries have no registers to spare for it: profiles/r03a_ab_probe.log, E_unroll2).
-template <typename real, int DC, bool REG>
-__device__ __forceinline__ void fast_check_rows2(real *row_a, real *row_b, unsigned mt_a, unsigned mt_b, real alpha, uint32_t alpha_w) {
-    real va[DC], vb[DC], oa[DC], ob[DC];
-    RowIO<real, DC>::load(row_a, va);
-    RowIO<real, DC>::load(row_b, vb);
-    fast_check_compute<real, DC, REG>(va, oa, mt_a, alpha, alpha_w);
-    fast_check_compute<real, DC, REG>(vb, ob, mt_b, alpha, alpha_w);
-    RowIO<real, DC>::store(row_a, oa);
-    RowIO<real, DC>::store(row_b, ob);
-}
-
-// flip the IEEE sign bit of x where bit 31 of w is set
-__device__ __forceinline__ double xor_sign(double x, uint32_t w) { return __hiloint2double(__double2hiint(x) ^ (int)(w & 0x80000000u), __double2loint(x)); }
-__device__ __forceinline__ float xor_sign(float x, uint32_t w) { return __uint_as_float(__float_as_uint(x) ^ (w & 0x80000000u)); }
-
-// All-finite form of the same check update -- an evaluated alternative, compiled in with -DBPOSD_TREE_MIN=1 and off by
-// default: parity-green on B200 but not faster (profiles/r03a_ab_probe.log: fp64 111.3 vs 111.6 M shot-iterations/s,
-// fp32 172.5 vs 179.1), because ptxas emits the same ~95 instructions per row for both forms (one compare fewer,
-// the same register-pair moves) and the shallower dependence chain alone does not shorten the sweep.  With no NaN in the row the minimum over "the other edges"
-// does not depend on the order of the compares, so it is taken as a shallow tree: minima of the DC/2
-// pairs, the minimum of all pairs but one, and one compare per edge against its partner -- 13 compares
-// of depth 4 for a row of 6 against 15 of depth 6 for the running form, and the dependent
-// compare/select chain is what the sweep waits on (ncu: "wait" is the top stall).  The sign is applied
-// by flipping the operand's sign bit and multiplying by one +-alpha shared by the row (IEEE: the product's
-// magnitude does not depend on the signs, its sign is their XOR), which drops the per-edge +-alpha register pairs.
-// Results are bit-identical to fast_check_row_exact for finite inputs, including the +-0 slow path.
-template <typename real, int DC, bool REG>
-__device__ __forceinline__ void fast_check_row_tree(real *row, unsigned mt, real alpha, uint32_t alpha_w) {
-    static_assert(DC == 4 || DC == 6 || DC == 8, "tree form is written for rows of 4, 6 or 8 slots");
-    constexpr int NP = DC / 2;
-    real v[DC], out[DC], pm[NP], ex[NP];
-    uint32_t sw[DC];
-    RowIO<real, DC>::load(row, v);
-    uint32_t X = (mt & 0x80u) << 24;
-#pragma unroll
-    for (int k = 0; k < DC; k++) { sw[k] = sign_word(v[k]); X ^= sw[k]; v[k] = abs_bits(v[k]); }
-#pragma unroll
-    for (int i = 0; i < NP; i++) pm[i] = lt_min(v[2 * i], v[2 * i + 1]);
-    real all_min;
-    if constexpr (NP == 2) {
-        ex[0] = pm[1]; ex[1] = pm[0];
-        all_min = lt_min(pm[0], pm[1]);
-    } else if constexpr (NP == 3) {
-        ex[0] = lt_min(pm[1], pm[2]); ex[1] = lt_min(pm[0], pm[2]); ex[2] = lt_min(pm[0], pm[1]);
-        all_min = lt_min(ex[2], pm[2]);
-    } else {
-        const real lo = lt_min(pm[0], pm[1]), hi = lt_min(pm[2], pm[NP - 1]);
-        ex[0] = lt_min(pm[1], hi); ex[1] = lt_min(pm[0], hi); ex[2] = lt_min(lo, pm[NP - 1]); ex[NP - 1] = lt_min(lo, pm[2]);
-        all_min = lt_min(lo, hi);
-    }
-#pragma unroll
-    for (int i = 0; i < NP; i++) { out[2 * i] = lt_min(v[2 * i + 1], ex[i]); out[2 * i + 1] = lt_min(v[2 * i], ex[i]); }
-    if (all_min == (real)0) {
-        int tot = (int)(mt >> 7);
-#pragma unroll
-        for (int k = 0; k < DC; k++) tot += ((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0;
-#pragma unroll
-        for (int k = 0; k < DC; k++) {
-            const int sg = tot + (((sw[k] >> 31) | (v[k] == (real)0 ? 1u : 0u)) ? 1 : 0);
-            out[k] = out[k] * ((sg & 1) ? -alpha : alpha);
-        }
-    } else {
-        const real a_row = with_sign_word(alpha, (X & 0x80000000u) ^ alpha_w); // alpha with sign = syndrome ^ parity of all signs
-#pragma unroll
-        for (int k = 0; k < DC; k++) out[k] = xor_sign(out[k], sw[k]) * a_row; // sign onto the operand: the product lands in the store registers
-    }
-    if (!REG) {
-        const int deg = (mt >> 1) & 0x1f;
-#pragma unroll
-        for (int k = 0; k < DC; k++) out[k] = (k < deg) ? out[k] : real_max<real>();
-    }
-    RowIO<real, DC>::store(row, out);
-}
-
-#ifndef BPOSD_TREE_MIN
-#define BPOSD_TREE_MIN 0 // measured on B200 (profiles/r03a_ab_probe.log): no gain in fp64 (111.3 vs 111.6 M it/s), -3.7 % in fp32
+// Bit sweep (rows a6 + a8) of one thread: VPT positions, each a bit with <= DV edges.  Sums run in the reference's
+// order (prior + c_1 + ... left to right for the LLR and the prefix; the suffix from the last edge backwards).
+// Returns the hard decisions, bit r = position tid + r*T (garbage for positions past the last bit: the caller masks).
+// UNI: every bit has the same prior (a register), else priors come from shared memory by position.
+// Regular codes (REG) run without any per-position branch: positions past the last bit own dummy slots.
+#ifndef BPOSD_BIT_GUARDS
+#define BPOSD_BIT_GUARDS 0 // 1: the older guarded form for every code (A/B)
 #endif
-template <typename real, int DC, bool REG>
-__device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alpha, uint32_t alpha_w, bool exact) {
-    if constexpr (BPOSD_TREE_MIN != 0 && (DC == 4 || DC == 6 || DC == 8)) {
-        if (exact) fast_check_row_exact<real, DC, REG>(row, mt, alpha, alpha_w);
-        else fast_check_row_tree<real, DC, REG>(row, mt, alpha, alpha_w);
-    } else {
-        fast_check_row_exact<real, DC, REG>(row, mt, alpha, alpha_w);
+template <typename real, int DV, int VPT, bool REG, bool UNI>
+__device__ __forceinline__ unsigned fast_bit_sweep(unsigned char *smem_raw, const unsigned (&off)[VPT][DV], const int (&dj)[VPT],
+                                                   real (&llr)[VPT], real prior_u, const real *prior_s, int tid, int T, int n) {
+    constexpr bool FREE = REG && BPOSD_BIT_GUARDS == 0;
+    unsigned dnow = 0;
+#pragma unroll
+    for (int r = 0; r < VPT; r++) {
+        const int j = tid + r * T;
+        if (FREE || j < n) {
+            real c[DV], pre[DV];
+#pragma unroll
+            for (int k = 0; k < DV; k++) c[k] = (REG || k < dj[r]) ? *reinterpret_cast<const real *>(smem_raw + off[r][k]) : (real)0;
+            real t = UNI ? prior_u : prior_s[FREE ? min(j, n - 1) : j];
+#pragma unroll
+            for (int k = 0; k < DV; k++)
+                if (REG || k < dj[r]) { pre[k] = t; t += c[k]; }
+            llr[r] = t;
+            dnow |= ((t <= 0) ? 1u : 0u) << r;
+            real sfx = 0;
+#pragma unroll
+            for (int k = DV - 1; k >= 0; k--)
+                if (REG || k < dj[r]) {
+                    // the last edge gets pre + 0, which is pre itself (sign of zero is immaterial downstream)
+                    *reinterpret_cast<real *>(smem_raw + off[r][k]) = (REG && k == DV - 1) ? pre[k] : pre[k] + sfx;
+                    sfx = (REG && k == DV - 1) ? c[k] : sfx + c[k];
+                }
+        }
     }
+    return dnow;
 }
 
 template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
@@ -555,7 +491,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
     const int tid = threadIdx.x, T = blockDim.x;
     real *msg = reinterpret_cast<real *>(smem_raw);
     constexpr int RS = fast_row_stride(DC, (int)sizeof(real)); // row stride in elements (>= DC, see fast_row_stride)
-    const size_t msg_bytes = ((size_t)m * RS * sizeof(real) > (size_t)n * (sizeof(real) + 1) ? (size_t)m * RS * sizeof(real)
+    const size_t msg_bytes = (((size_t)m * RS + kFastDummySlots) * sizeof(real) > (size_t)n * (sizeof(real) + 1) ? ((size_t)m * RS + kFastDummySlots) * sizeof(real)
                                                                                              : (size_t)n * (sizeof(real) + 1));
     uint8_t *meta = smem_raw + (msg_bytes + 15) / 16 * 16; // bit0 mismatch, bits1-5 degree, bit7 syndrome
     unsigned *meta32 = reinterpret_cast<unsigned *>(meta);
@@ -564,12 +500,12 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
     uint8_t *st_dec = reinterpret_cast<uint8_t *>(st_llr + n);
     __shared__ long long sh_shot;
     __shared__ int sh_slot;
-    __shared__ int sh_exact; // the shot carries an infinite or NaN value: check sweep in the reference's compare order
 
     // per-position registers: byte offsets of the edges' slots (shot independent).  Position q = tid + r*T
     // holds bit bit_of_tab[q]; only the prior look-up and the result staging need the bit index.
     unsigned off[VPT][DV];
     int dj[VPT];
+    unsigned valid = 0; // bit r: position tid + r*T holds a bit
 #pragma unroll
     for (int r = 0; r < VPT; r++) {
         const int j = tid + r * T;
@@ -579,7 +515,10 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             const unsigned s = (j < n) ? vslot_tab[(size_t)j * DV + k] : 0xFFFFu;
             off[r][k] = s * (unsigned)sizeof(real);
             dj[r] += (s != 0xFFFFu) ? 1 : 0;
+            // regular codes: a position past the last bit works on dummy slots instead of being branched around
+            if (REG && BPOSD_BIT_GUARDS == 0 && j >= n) off[r][k] = (unsigned)((m * RS + k) * (int)sizeof(real));
         }
+        valid |= (j < n ? 1u : 0u) << r;
     }
     unsigned long long n_conv = 0, n_iter = 0;
     long long next_static = blockIdx.x; // a.queue == nullptr (latency path): CTA b takes shots b, b + grid, ...
@@ -591,7 +530,6 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
         if (tid == 0) {
             if (a.queue) sh_shot = (long long)atomicAdd(a.queue, 1ull);
             else { sh_shot = next_static; next_static += gridDim.x; }
-            sh_exact = 0;
         }
         __syncthreads();
         const long long shot = sh_shot;
@@ -615,7 +553,6 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             if (j < n) {
                 const real pj = uniform ? prior_u : prior[bit_of_tab[j]];
                 if (!uniform) prior_s[j] = pj;
-                if (BPOSD_TREE_MIN != 0 && sizeof(real) == 8 && !(fabs(pj) < (real)kFastPriorBound)) sh_exact = 1; // +-inf (p = 0 or 1), NaN, absurd
                 llr[r] = pj;
 #pragma unroll
                 for (int k = 0; k < DV; k++)
@@ -633,57 +570,20 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             const real alpha = (a.alpha0 == (real)0) ? (real)1 - pow2 : a.alpha0;
             const uint32_t alpha_w = sign_word(alpha);
             bool ok = true;
-            // fp64: the tree form needs an all-finite shot.  Priors are checked when the shot is set up; sums cannot
-            // overflow before pass a.exact_after (fast_exact_after: magnitudes grow at most (DV-1)-fold per pass).
-            // fp32 has no bit-exactness contract and always takes the tree form.
-            const bool exact = BPOSD_TREE_MIN != 0 && sizeof(real) == 8 && (it > a.exact_after || *reinterpret_cast<volatile int *>(&sh_exact) != 0);
             // ---- check sweep (a4) + convergence vote for the previous pass (a7) ----
-            if constexpr (kPairRows<real, VPT, MAXT>) {
-                for (int p = tid; p < m; p += 2 * T) {
-                    const int p2 = p + T;
-                    const unsigned mt = meta[p], mt2 = p2 < m ? meta[p2] : 0u;
-                    if ((mt | mt2) & 1u) ok = false;
-                    if (last) continue;
-                    if (p2 < m) fast_check_rows2<real, DC, REG>(msg + (size_t)p * RS, msg + (size_t)p2 * RS, mt, mt2, alpha, alpha_w);
-                    else fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w, exact);
-                }
-            } else {
 #pragma unroll kCheckUnroll
-                for (int p = tid; p < m; p += T) {
-                    const unsigned mt = meta[p];
-                    if (mt & 1u) ok = false;
-                    if (last) continue;
-                    fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w, exact);
-                }
+            for (int p = tid; p < m; p += T) {
+                const unsigned mt = meta[p];
+                if (mt & 1u) ok = false;
+                if (last) continue;
+                fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w);
             }
             const int all_ok = __syncthreads_and(ok ? 1 : 0);
             if (it > 1 && all_ok) { conv = true; iters = it - 1; break; }
             if (last) { iters = a.max_iter; break; }
             // ---- bit sweep (a6 + a8) ----
-            unsigned dnow = 0;
-#pragma unroll
-            for (int r = 0; r < VPT; r++) {
-                const int j = tid + r * T;
-                if (j < n) {
-                    real c[DV], pre[DV];
-#pragma unroll
-                    for (int k = 0; k < DV; k++) c[k] = (REG || k < dj[r]) ? *reinterpret_cast<const real *>(smem_raw + off[r][k]) : (real)0;
-                    real t = uniform ? prior_u : prior_s[j];
-#pragma unroll
-                    for (int k = 0; k < DV; k++)
-                        if (REG || k < dj[r]) { pre[k] = t; t += c[k]; }
-                    llr[r] = t;
-                    dnow |= ((t <= 0) ? 1u : 0u) << r;
-                    real sfx = 0;
-#pragma unroll
-                    for (int k = DV - 1; k >= 0; k--)
-                        if (REG || k < dj[r]) {
-                            // the last edge gets pre + 0, which is pre itself (sign of zero is immaterial downstream)
-                            *reinterpret_cast<real *>(smem_raw + off[r][k]) = (REG && k == DV - 1) ? pre[k] : pre[k] + sfx;
-                            sfx = (REG && k == DV - 1) ? c[k] : sfx + c[k];
-                        }
-                }
-            }
+            const unsigned dnow = valid & (uniform ? fast_bit_sweep<real, DV, VPT, REG, true>(smem_raw, off, dj, llr, prior_u, prior_s, tid, T, n)
+                                                   : fast_bit_sweep<real, DV, VPT, REG, false>(smem_raw, off, dj, llr, prior_u, prior_s, tid, T, n));
             if (dnow != dprev) {
                 // a hard decision flipped (rare): toggle the parity-mismatch bit of every neighbouring check
                 unsigned flip = dnow ^ dprev;

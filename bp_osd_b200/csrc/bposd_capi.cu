@@ -656,7 +656,6 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     a.max_iter = h->max_iter;
     a.method = h->bp_method;
     a.alpha0 = (real)h->alpha;
-    a.exact_after = fast_exact_after(h->max_col_deg, h->max_iter, h->alpha);
     a.uniform_prior = d_priors ? 0 : h->uniform_prior;
     if (d_priors) { a.prior = static_cast<const real *>(d_priors); a.prior_stride = n; }
     else { a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32; a.prior_stride = 0; }
@@ -832,7 +831,6 @@ static int decode_latency_t(bposd_handle *h, const uint8_t *h_synd, long long B,
     a.max_iter = h->max_iter;
     a.method = h->bp_method;
     a.alpha0 = (real)h->alpha;
-    a.exact_after = fast_exact_after(h->max_col_deg, h->max_iter, h->alpha);
     a.uniform_prior = h->uniform_prior;
     a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32;
     a.prior_stride = 0;

@@ -34,7 +34,6 @@ struct BpArgs {
     GraphDev g;
     int max_iter;
     int method;   // 0 product-sum, 1 min-sum
-    int exact_after = 0; // fast kernel, fp64: last pass whose sums provably stay finite (bp_fast_kernel.cuh: fast_exact_after)
     real alpha0;  // 0 => 1 - 2^-it
     const real *prior;
     long long prior_stride; // 0: one prior vector for all shots, n: per-shot rows
