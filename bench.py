@@ -343,7 +343,9 @@ def run_gpu(args):
         for i in range(300):
             t = time.perf_counter(); dec.decode(s1[i]); ts.append(time.perf_counter() - t)
         ts = np.array(ts[50:]) * 1e6
-        lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "samples": int(ts.size)}
+        lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "samples": int(ts.size),
+               "path": "decoder.decode(syndrome) -> bposd_decode_host B=1: one kernel launch + one stream synchronise, syndrome "
+                       "read from and results written to pinned host memory by the kernel, one SM per shot (latency geometry)"}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as _o
             _o.build()

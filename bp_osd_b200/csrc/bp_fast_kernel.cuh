@@ -329,6 +329,7 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
 // slots after the last row that thread positions beyond the last bit read and write (regular codes: the bit sweep
 // then needs no "is this position a bit" guard); never read by a check
 constexpr int kFastDummySlots = 8;
+constexpr int kFastZeroSlot = kFastDummySlots - 1; // irregular codes: the slot absent edges read, always 0.0
 
 template <typename real>
 static inline size_t fast_smem_bytes(const FastTables &t, int n, int m) {
@@ -450,32 +451,90 @@ __device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alph
 #ifndef BPOSD_BIT_GUARDS
 #define BPOSD_BIT_GUARDS 0 // 1: the older guarded form for every code (A/B)
 #endif
+#ifndef BPOSD_T_REG
+#define BPOSD_T_REG 0
+#endif
+#ifndef BPOSD_BIT_GROUP
+#define BPOSD_BIT_GROUP 4 // positions whose messages are loaded together before the first store (regular codes)
+#endif
 template <typename real, int DV, int VPT, bool REG, bool UNI>
 __device__ __forceinline__ unsigned fast_bit_sweep(unsigned char *smem_raw, const unsigned (&off)[VPT][DV], const int (&dj)[VPT],
                                                    real (&llr)[VPT], real prior_u, const real *prior_s, int tid, int T, int n) {
-    constexpr bool FREE = REG && BPOSD_BIT_GUARDS == 0;
     unsigned dnow = 0;
+    if constexpr (BPOSD_BIT_GUARDS == 0 && REG) {
+        // regular code: every position has DV slots (real ones or its dummies), nothing is conditional.  The messages of
+        // G positions are loaded before any of them is stored: the compiler cannot move a shared-memory load above a
+        // store on its own (it does not know that slots never alias), and with one position at a time every LDS latency
+        // is exposed (ncu source view: the DADD after each load triple held 14 % of the kernel's stall samples).
+        constexpr int G = (VPT % BPOSD_BIT_GROUP == 0) ? BPOSD_BIT_GROUP : 1;
 #pragma unroll
-    for (int r = 0; r < VPT; r++) {
-        const int j = tid + r * T;
-        if (FREE || j < n) {
+        for (int r0 = 0; r0 < VPT; r0 += G) {
+            real c[G][DV];
+#pragma unroll
+            for (int g = 0; g < G; g++)
+#pragma unroll
+                for (int k = 0; k < DV; k++) c[g][k] = *reinterpret_cast<const real *>(smem_raw + off[r0 + g][k]);
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int r = r0 + g;
+                real pre[DV];
+                real t = UNI ? prior_u : prior_s[min(tid + r * T, n - 1)];
+#pragma unroll
+                for (int k = 0; k < DV; k++) { pre[k] = t; t += c[g][k]; }
+                llr[r] = t;
+                dnow |= ((t <= 0) ? 1u : 0u) << r;
+                real sfx = 0;
+#pragma unroll
+                for (int k = DV - 1; k >= 0; k--) {
+                    // the last edge gets pre + 0, which is pre itself (sign of zero is immaterial downstream)
+                    *reinterpret_cast<real *>(smem_raw + off[r][k]) = (k == DV - 1) ? pre[k] : pre[k] + sfx;
+                    sfx = (k == DV - 1) ? c[g][k] : sfx + c[g][k];
+                }
+            }
+        }
+    } else if constexpr (BPOSD_BIT_GUARDS == 0) {
+        // irregular code: an absent edge (k >= degree, or a position past the last bit) reads the constant-zero slot, so
+        // the sums need no guard (x + 0 is x, and 0 + 0 is the +0 the running suffix starts from); only the stores are
+        // predicated.  Same values as the guarded form below.
+#pragma unroll
+        for (int r = 0; r < VPT; r++) {
             real c[DV], pre[DV];
 #pragma unroll
-            for (int k = 0; k < DV; k++) c[k] = (REG || k < dj[r]) ? *reinterpret_cast<const real *>(smem_raw + off[r][k]) : (real)0;
-            real t = UNI ? prior_u : prior_s[FREE ? min(j, n - 1) : j];
+            for (int k = 0; k < DV; k++) c[k] = *reinterpret_cast<const real *>(smem_raw + off[r][k]);
+            real t = UNI ? prior_u : prior_s[min(tid + r * T, n - 1)];
 #pragma unroll
-            for (int k = 0; k < DV; k++)
-                if (REG || k < dj[r]) { pre[k] = t; t += c[k]; }
+            for (int k = 0; k < DV; k++) { pre[k] = t; t += c[k]; }
             llr[r] = t;
             dnow |= ((t <= 0) ? 1u : 0u) << r;
             real sfx = 0;
 #pragma unroll
-            for (int k = DV - 1; k >= 0; k--)
-                if (REG || k < dj[r]) {
-                    // the last edge gets pre + 0, which is pre itself (sign of zero is immaterial downstream)
-                    *reinterpret_cast<real *>(smem_raw + off[r][k]) = (REG && k == DV - 1) ? pre[k] : pre[k] + sfx;
-                    sfx = (REG && k == DV - 1) ? c[k] : sfx + c[k];
-                }
+            for (int k = DV - 1; k >= 0; k--) {
+                if (k < dj[r]) *reinterpret_cast<real *>(smem_raw + off[r][k]) = pre[k] + sfx;
+                sfx = sfx + c[k];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < VPT; r++) {
+            const int j = tid + r * T;
+            if (j < n) {
+                real c[DV], pre[DV];
+#pragma unroll
+                for (int k = 0; k < DV; k++) c[k] = (REG || k < dj[r]) ? *reinterpret_cast<const real *>(smem_raw + off[r][k]) : (real)0;
+                real t = UNI ? prior_u : prior_s[j];
+#pragma unroll
+                for (int k = 0; k < DV; k++)
+                    if (REG || k < dj[r]) { pre[k] = t; t += c[k]; }
+                llr[r] = t;
+                dnow |= ((t <= 0) ? 1u : 0u) << r;
+                real sfx = 0;
+#pragma unroll
+                for (int k = DV - 1; k >= 0; k--)
+                    if (REG || k < dj[r]) {
+                        *reinterpret_cast<real *>(smem_raw + off[r][k]) = (REG && k == DV - 1) ? pre[k] : pre[k] + sfx;
+                        sfx = (REG && k == DV - 1) ? c[k] : sfx + c[k];
+                    }
+            }
         }
     }
     return dnow;
@@ -488,7 +547,15 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
                                                        const uint16_t *__restrict__ bit_of_tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = a.g.m, n = a.g.n;
-    const int tid = threadIdx.x, T = blockDim.x;
+    const int tid = threadIdx.x;
+#if BPOSD_T_REG
+    // the CTA size pinned in a register: left to itself the compiler re-reads it from the constant bank at the end of
+    // every check row and the next row's address waits for that load (ncu source view: 5 % of the stall samples)
+    int T;
+    asm volatile("mov.u32 %0, %%ntid.x;" : "=r"(T));
+#else
+    const int T = blockDim.x;
+#endif
     real *msg = reinterpret_cast<real *>(smem_raw);
     constexpr int RS = fast_row_stride(DC, (int)sizeof(real)); // row stride in elements (>= DC, see fast_row_stride)
     const size_t msg_bytes = (((size_t)m * RS + kFastDummySlots) * sizeof(real) > (size_t)n * (sizeof(real) + 1) ? ((size_t)m * RS + kFastDummySlots) * sizeof(real)
@@ -515,8 +582,10 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             const unsigned s = (j < n) ? vslot_tab[(size_t)j * DV + k] : 0xFFFFu;
             off[r][k] = s * (unsigned)sizeof(real);
             dj[r] += (s != 0xFFFFu) ? 1 : 0;
-            // regular codes: a position past the last bit works on dummy slots instead of being branched around
-            if (REG && BPOSD_BIT_GUARDS == 0 && j >= n) off[r][k] = (unsigned)((m * RS + k) * (int)sizeof(real));
+            // regular codes: a position past the last bit works on dummy slots instead of being branched around;
+            // irregular codes: every absent edge reads the constant-zero slot (and is never stored)
+            if (BPOSD_BIT_GUARDS == 0 && REG && j >= n) off[r][k] = (unsigned)((m * RS + k) * (int)sizeof(real));
+            if (BPOSD_BIT_GUARDS == 0 && !REG && s == 0xFFFFu) off[r][k] = (unsigned)((m * RS + kFastZeroSlot) * (int)sizeof(real));
         }
         valid |= (j < n ? 1u : 0u) << r;
     }
@@ -544,6 +613,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
                       // of the previous shot overwrote the array, so they are set again for every shot)
                 for (int k = (int)deg; k < DC; k++) msg[p * RS + k] = real_max<real>();
         }
+        if (!REG && tid == 0) msg[m * RS + kFastZeroSlot] = (real)0; // (the previous shot's result staging may have covered it)
         real llr[VPT];
         unsigned dprev = 0;
 #pragma unroll

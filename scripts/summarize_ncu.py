@@ -55,7 +55,9 @@ def launches(path, out):
 
 
 def rep(path, out):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # path: the .ncu-rep, or the raw-page CSV scripts/profile.sh exports on the box when the report is too big to travel
+    raw = open(path).read() if path.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     res = []
@@ -81,5 +83,7 @@ if __name__ == "__main__":
     rp = a.rep or os.path.join(ROOT, "gpurun_out", a.tag + "_bp.ncu-rep")
     if os.path.exists(lp):
         launches(lp, os.path.join(ROOT, "profiles", a.tag + "_launches_summary.csv"))
+    if not os.path.exists(rp) and os.path.exists(os.path.join(ROOT, "gpurun_out", a.tag + "_bp_raw.csv")):
+        rp = os.path.join(ROOT, "gpurun_out", a.tag + "_bp_raw.csv")
     if os.path.exists(rp):
         rep(rp, os.path.join(ROOT, "profiles", a.tag + "_ncu_full_summary.json"))
