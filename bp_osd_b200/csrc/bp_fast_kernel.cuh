@@ -452,10 +452,11 @@ __device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alph
 #define BPOSD_BIT_GUARDS 0 // 1: the older guarded form for every code (A/B)
 #endif
 #ifndef BPOSD_T_REG
-#define BPOSD_T_REG 0
+#define BPOSD_T_REG 1 // profiles/r03h_ab_probe.log: fp64 128.4 -> 129.7, fp32 192.0 -> 195.0 M shot-iterations/s
 #endif
 #ifndef BPOSD_BIT_GROUP
-#define BPOSD_BIT_GROUP 4 // positions whose messages are loaded together before the first store (regular codes)
+#define BPOSD_BIT_GROUP 1 // positions whose messages are loaded together before the first store (regular codes); measured on
+                          // B200 (profiles/r03h_ab_probe.log): 1 -> 128.4, 2 -> 128.1, 4 -> 127.4, 8 -> 127.1 M shot-iterations/s
 #endif
 template <typename real, int DV, int VPT, bool REG, bool UNI>
 __device__ __forceinline__ unsigned fast_bit_sweep(unsigned char *smem_raw, const unsigned (&off)[VPT][DV], const int (&dj)[VPT],
@@ -463,9 +464,10 @@ __device__ __forceinline__ unsigned fast_bit_sweep(unsigned char *smem_raw, cons
     unsigned dnow = 0;
     if constexpr (BPOSD_BIT_GUARDS == 0 && REG) {
         // regular code: every position has DV slots (real ones or its dummies), nothing is conditional.  The messages of
-        // G positions are loaded before any of them is stored: the compiler cannot move a shared-memory load above a
-        // store on its own (it does not know that slots never alias), and with one position at a time every LDS latency
-        // is exposed (ncu source view: the DADD after each load triple held 14 % of the kernel's stall samples).
+        // G positions can be loaded before any of them is stored (the compiler cannot move a shared-memory load above a
+        // store on its own: it does not know that slots never alias).  The ncu source view shows the DADD after each
+        // load triple holding 14 % of the stall samples, but batching the loads buys nothing (see BPOSD_BIT_GROUP): the
+        // other warps already cover that latency and the shared-memory pipe, not the wait, sets the pace.
         constexpr int G = (VPT % BPOSD_BIT_GROUP == 0) ? BPOSD_BIT_GROUP : 1;
 #pragma unroll
         for (int r0 = 0; r0 < VPT; r0 += G) {
@@ -641,6 +643,8 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
             const uint32_t alpha_w = sign_word(alpha);
             bool ok = true;
             // ---- check sweep (a4) + convergence vote for the previous pass (a7) ----
+            // (prefetching the thread's next row into a second register set before updating the current one was measured:
+            // 111 vs 128 M shot-iterations/s -- the second set spills at the 128-register cap; profiles/r03i_ab_probe.log)
 #pragma unroll kCheckUnroll
             for (int p = tid; p < m; p += T) {
                 const unsigned mt = meta[p];
