@@ -451,6 +451,9 @@ __device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alph
 #ifndef BPOSD_BIT_GUARDS
 #define BPOSD_BIT_GUARDS 0 // 1: the older guarded form for every code (A/B)
 #endif
+#ifndef BPOSD_FLIP_NOHOIST
+#define BPOSD_FLIP_NOHOIST 1
+#endif
 #ifndef BPOSD_T_REG
 #define BPOSD_T_REG 1 // profiles/r03h_ab_probe.log: fp64 128.4 -> 129.7, fp32 192.0 -> 195.0 M shot-iterations/s
 #endif
@@ -668,7 +671,13 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
 #pragma unroll
                         for (int k = 0; k < DV; k++)
                             if (REG || k < dj[r]) {
-                                const unsigned p = off[r][k] / (unsigned)(RS * sizeof(real));
+                                unsigned o = off[r][k];
+#if BPOSD_FLIP_NOHOIST
+                                // keep the row / word / mask arithmetic inside this (rare) branch: left alone, the compiler hoists
+                                // it out of the pass loop for all VPT*DV edges and parks the results in 2 registers per edge
+                                asm volatile("" : "+r"(o));
+#endif
+                                const unsigned p = o / (unsigned)(RS * sizeof(real));
                                 atomicXor(&meta32[p >> 2], 1u << ((p & 3u) * 8u));
                             }
                     }
