@@ -117,8 +117,17 @@ static inline int fast_maxt_g(int geom, int elem_bytes = 8) {
 }
 static inline int fast_vpt(int n) { return fast_vpt_g(fast_geom(n, false)); }
 static inline int fast_maxt(int n) { return fast_maxt_g(fast_geom(n, false)); }
-template <typename real, int MAXT> constexpr int fast_minb() {
-    constexpr int cap = sizeof(real) == 8 ? BPOSD_REGCAP64 : BPOSD_REGCAP32;
+// fp64, throughput geometry of the mid class, rows of <= 6 / bits of <= 3 edges (the bench code): 80 registers, i.e.
+// 3 CTAs of 256 threads per SM instead of 2 -- possible once the parity-flip arithmetic stays inside its branch
+// (kFlipInBranch).  Measured on B200 (profiles/r03l_ab_probe.log): 136.3 vs 129.7 M shot-iterations/s.
+#ifndef BPOSD_REGCAP64_SMALL
+#define BPOSD_REGCAP64_SMALL 80
+#endif
+template <typename real, int MAXT, int DC, int DV, int VPT>
+constexpr bool kFastSmallClass = sizeof(real) == 8 && MAXT == BPOSD_MID_MAXT && VPT == BPOSD_MID_VPT && MAXT == 256 && DC <= 6 && DV <= 3 &&
+                                 BPOSD_REGCAP64_SMALL < BPOSD_REGCAP64;
+template <typename real, int MAXT, int DC = 16, int DV = 8, int VPT = 0> constexpr int fast_minb() {
+    constexpr int cap = sizeof(real) == 8 ? (kFastSmallClass<real, MAXT, DC, DV, VPT> ? BPOSD_REGCAP64_SMALL : BPOSD_REGCAP64) : BPOSD_REGCAP32;
     return (65536 / (MAXT * cap)) < 1 ? 1 : (65536 / (MAXT * cap));
 }
 
@@ -336,7 +345,7 @@ static inline size_t fast_smem_bytes(const FastTables &t, int n, int m) {
     if (t.DC == 0) return (size_t)1 << 40;
     // the message array doubles as the staging area of the per-shot results ([n] reals + [n] bytes)
     size_t msgs = (std::max(((size_t)m * fast_row_stride(t.DC, (int)sizeof(real)) + kFastDummySlots) * sizeof(real), (size_t)n * (sizeof(real) + 1)) + 15) / 16 * 16;
-    size_t meta = ((size_t)m + 15) / 16 * 16;
+    size_t meta = ((size_t)m * 4 + 15) / 16 * 16; // one 32-bit word per check (see the kernel)
     size_t prior = ((size_t)n * sizeof(real) + 15) / 16 * 16; // copy of the priors when they are not uniform
     return msgs + meta + prior + 16;
 }
@@ -546,7 +555,7 @@ __device__ __forceinline__ unsigned fast_bit_sweep(unsigned char *smem_raw, cons
 }
 
 template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
-__global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
+__global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT>())) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
                                                        const uint8_t *__restrict__ cdeg_tab,
                                                        const uint16_t *__restrict__ row_of_tab,
                                                        const uint16_t *__restrict__ bit_of_tab) {
@@ -565,9 +574,11 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
     constexpr int RS = fast_row_stride(DC, (int)sizeof(real)); // row stride in elements (>= DC, see fast_row_stride)
     const size_t msg_bytes = (((size_t)m * RS + kFastDummySlots) * sizeof(real) > (size_t)n * (sizeof(real) + 1) ? ((size_t)m * RS + kFastDummySlots) * sizeof(real)
                                                                                              : (size_t)n * (sizeof(real) + 1));
-    uint8_t *meta = smem_raw + (msg_bytes + 15) / 16 * 16; // bit0 mismatch, bits1-5 degree, bit7 syndrome
-    unsigned *meta32 = reinterpret_cast<unsigned *>(meta);
-    real *prior_s = reinterpret_cast<real *>(meta + ((size_t)m + 15) / 16 * 16); // [n] priors by position when they are not uniform
+    // one word per check: bit0 parity mismatch, bits1-5 degree, bit7 syndrome.  A word, not a byte, so that toggling the
+    // mismatch bit is `atomicXor(word, 1)`: one address per edge, where byte-packed flags needed an address and a shifted
+    // mask per edge (the compiler keeps those loop invariants in registers: 48 of them for 8 bits x 3 edges)
+    unsigned *meta = reinterpret_cast<unsigned *>(smem_raw + (msg_bytes + 15) / 16 * 16);
+    real *prior_s = reinterpret_cast<real *>(reinterpret_cast<unsigned char *>(meta) + ((size_t)m * 4 + 15) / 16 * 16); // [n] priors by position when they are not uniform
     real *st_llr = msg;                                         // per-shot result staging (after the last pass)
     uint8_t *st_dec = reinterpret_cast<uint8_t *>(st_llr + n);
     __shared__ long long sh_shot;
@@ -613,7 +624,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
         for (int p = tid; p < m; p += T) {
             const unsigned s = a.synd[shot * m + row_of_tab[p]] & 1u;
             const unsigned deg = cdeg_tab[p];
-            meta[p] = (uint8_t)(s | (deg << 1) | (s << 7));
+            meta[p] = s | (deg << 1) | (s << 7);
             if (!REG) // absent slots of short rows hold +max: neutral for min and sign (the result staging
                       // of the previous shot overwrote the array, so they are set again for every shot)
                 for (int k = (int)deg; k < DC; k++) msg[p * RS + k] = real_max<real>();
@@ -672,13 +683,11 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT>())) bp_fast_kerne
                         for (int k = 0; k < DV; k++)
                             if (REG || k < dj[r]) {
                                 unsigned o = off[r][k];
-#if BPOSD_FLIP_NOHOIST
-                                // keep the row / word / mask arithmetic inside this (rare) branch: left alone, the compiler hoists
-                                // it out of the pass loop for all VPT*DV edges and parks the results in 2 registers per edge
-                                asm volatile("" : "+r"(o));
-#endif
+                                // register-capped class: keep the slot -> row arithmetic inside this branch (left alone, the
+                                // compiler hoists it out of the pass loop and parks one address per edge in a register)
+                                if constexpr (kFastSmallClass<real, MAXT, DC, DV, VPT> && BPOSD_FLIP_NOHOIST != 0) asm volatile("" : "+r"(o));
                                 const unsigned p = o / (unsigned)(RS * sizeof(real));
-                                atomicXor(&meta32[p >> 2], 1u << ((p & 3u) * 8u));
+                                atomicXor(&meta[p], 1u);
                             }
                     }
             }
