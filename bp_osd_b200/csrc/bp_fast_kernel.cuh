@@ -123,11 +123,11 @@ static inline int fast_maxt(int n) { return fast_maxt_g(fast_geom(n, false)); }
 #ifndef BPOSD_REGCAP64_SMALL
 #define BPOSD_REGCAP64_SMALL 80
 #endif
-template <typename real, int MAXT, int DC, int DV, int VPT>
-constexpr bool kFastSmallClass = sizeof(real) == 8 && MAXT == BPOSD_MID_MAXT && VPT == BPOSD_MID_VPT && MAXT == 256 && DC <= 6 && DV <= 3 &&
-                                 BPOSD_REGCAP64_SMALL < BPOSD_REGCAP64;
-template <typename real, int MAXT, int DC = 16, int DV = 8, int VPT = 0> constexpr int fast_minb() {
-    constexpr int cap = sizeof(real) == 8 ? (kFastSmallClass<real, MAXT, DC, DV, VPT> ? BPOSD_REGCAP64_SMALL : BPOSD_REGCAP64) : BPOSD_REGCAP32;
+template <typename real, int MAXT, int DC, int DV, int VPT, bool REG>
+constexpr bool kFastSmallClass = sizeof(real) == 8 && MAXT == BPOSD_MID_MAXT && VPT == BPOSD_MID_VPT && MAXT == 256 && DC <= 6 && DV <= 3 && REG &&
+                                 BPOSD_REGCAP64_SMALL < BPOSD_REGCAP64; // regular codes only: the irregular form spills twice as much (unmeasured)
+template <typename real, int MAXT, int DC = 16, int DV = 8, int VPT = 0, bool REG = false> constexpr int fast_minb() {
+    constexpr int cap = sizeof(real) == 8 ? (kFastSmallClass<real, MAXT, DC, DV, VPT, REG> ? BPOSD_REGCAP64_SMALL : BPOSD_REGCAP64) : BPOSD_REGCAP32;
     return (65536 / (MAXT * cap)) < 1 ? 1 : (65536 / (MAXT * cap));
 }
 
@@ -555,7 +555,7 @@ __device__ __forceinline__ unsigned fast_bit_sweep(unsigned char *smem_raw, cons
 }
 
 template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
-__global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT>())) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
+__global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG>())) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
                                                        const uint8_t *__restrict__ cdeg_tab,
                                                        const uint16_t *__restrict__ row_of_tab,
                                                        const uint16_t *__restrict__ bit_of_tab) {
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT>())) 
                                 unsigned o = off[r][k];
                                 // register-capped class: keep the slot -> row arithmetic inside this branch (left alone, the
                                 // compiler hoists it out of the pass loop and parks one address per edge in a register)
-                                if constexpr (kFastSmallClass<real, MAXT, DC, DV, VPT> && BPOSD_FLIP_NOHOIST != 0) asm volatile("" : "+r"(o));
+                                if constexpr (kFastSmallClass<real, MAXT, DC, DV, VPT, REG> && BPOSD_FLIP_NOHOIST != 0) asm volatile("" : "+r"(o));
                                 const unsigned p = o / (unsigned)(RS * sizeof(real));
                                 atomicXor(&meta[p], 1u);
                             }
