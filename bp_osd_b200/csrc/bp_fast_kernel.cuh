@@ -14,8 +14,9 @@
 //                the reference's order (prior + c_1 + ... left to right; suffix from the last edge
 //                backwards) and overwrites them with the new bit->check messages.
 // Convergence (H*decoding == syndrome) is tracked incrementally: every check keeps one parity-mismatch
-// bit, initialised to its syndrome bit; a bit whose hard decision flips toggles the mismatch bits of
-// its checks with a shared-memory atomicXor (rare), and the next check sweep only votes on that bit.
+// bit (in a 32-bit flag word of its own), initialised to its syndrome bit; a bit whose hard decision flips
+// toggles the mismatch bits of its checks with a shared-memory atomicXor (frequent in the first passes,
+// rare later), and the next check sweep only votes on that bit.
 // Per-bit state that must survive to the end of the shot (LLR of the last executed pass, edge
 // offsets, last hard decisions) lives in registers; nothing but the syndrome and the results
 // touches HBM.  Persistent CTAs pull shots from an atomic queue (iteration counts are heavy tailed).
