@@ -423,8 +423,23 @@ static inline int cluster_threads(int bits_per_cta) {
     return v ? std::max(32, ((bits_per_cta + v - 1) / v + 31) / 32 * 32) : 0;
 }
 
+// Instantiated per (precision, degree class) in its own translation unit (bp_cluster_inst.cu); see FastInst.
+template <typename real, int DC, int DV>
+struct ClusterInst {
+    static cudaError_t prepare(const ClusterTables &t, int threads, size_t smem, int *max_clusters);
+    static cudaError_t launch(const ClusterTables &t, const BpArgs<real> &a, const ClusterDev &d, int nclusters, int threads, size_t smem, cudaStream_t st);
+};
+
+#ifdef BPOSD_CLUSTER_INSTANTIATE
 #define BPOSD_CL_REG2(EXPR) do { if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } while (0)
+// (bits per thread, CTA size class) pairs that cluster_vpt / cluster_threads can produce: up to 640 threads for every
+// VPT, more only for VPT 6 (896, 1024) and 8 (768, 896, 1024)
 #define BPOSD_CL_REG(EXPR)                                                                       \
+    do {                                                                                         \
+        if (maxt__ <= 512) { constexpr int MAXT = 512; BPOSD_CL_REG2(EXPR); }                    \
+        else { constexpr int MAXT = 640; BPOSD_CL_REG2(EXPR); }                                  \
+    } while (0)
+#define BPOSD_CL_REG_BIG(EXPR)                                                                   \
     do {                                                                                         \
         if (maxt__ <= 512) { constexpr int MAXT = 512; BPOSD_CL_REG2(EXPR); }                    \
         else if (maxt__ <= 640) { constexpr int MAXT = 640; BPOSD_CL_REG2(EXPR); }               \
@@ -432,31 +447,23 @@ static inline int cluster_threads(int bits_per_cta) {
         else if (maxt__ <= 896) { constexpr int MAXT = 896; BPOSD_CL_REG2(EXPR); }               \
         else { constexpr int MAXT = 1024; BPOSD_CL_REG2(EXPR); }                                 \
     } while (0)
-#define BPOSD_CL_GEOM(DCv, DVv, EXPR)                                                            \
-    do {                                                                                         \
-        constexpr int DC = DCv, DV = DVv;                                                        \
-        if (vpt__ == 1) { constexpr int VPT = 1; BPOSD_CL_REG(EXPR); }                           \
-        else if (vpt__ == 2) { constexpr int VPT = 2; BPOSD_CL_REG(EXPR); }                      \
-        else if (vpt__ == 3) { constexpr int VPT = 3; BPOSD_CL_REG(EXPR); }                      \
-        else if (vpt__ == 4) { constexpr int VPT = 4; BPOSD_CL_REG(EXPR); }                      \
-        else if (vpt__ == 6) { constexpr int VPT = 6; BPOSD_CL_REG(EXPR); }                      \
-        else { constexpr int VPT = 8; BPOSD_CL_REG(EXPR); }                                      \
-    } while (0)
-#define BPOSD_CL_DISPATCH(t, EXPR)                                                               \
+#define BPOSD_CL_GEOM(t, EXPR)                                                                   \
     do {                                                                                         \
         const int vpt__ = cluster_vpt(t.bits_per_cta);                                           \
         const int maxt__ = cluster_threads(t.bits_per_cta);                                      \
         const bool reg__ = t.regular != 0;                                                       \
-        if (t.DC == 4) BPOSD_CL_GEOM(4, 2, EXPR);                                                \
-        else if (t.DC == 6) BPOSD_CL_GEOM(6, 3, EXPR);                                           \
-        else if (t.DC == 8) BPOSD_CL_GEOM(8, 4, EXPR);                                           \
-        else BPOSD_CL_GEOM(16, 8, EXPR);                                                         \
+        if (vpt__ == 1) { constexpr int VPT = 1; BPOSD_CL_REG(EXPR); }                           \
+        else if (vpt__ == 2) { constexpr int VPT = 2; BPOSD_CL_REG(EXPR); }                      \
+        else if (vpt__ == 3) { constexpr int VPT = 3; BPOSD_CL_REG(EXPR); }                      \
+        else if (vpt__ == 4) { constexpr int VPT = 4; BPOSD_CL_REG(EXPR); }                      \
+        else if (vpt__ == 6) { constexpr int VPT = 6; BPOSD_CL_REG_BIG(EXPR); }                  \
+        else { constexpr int VPT = 8; BPOSD_CL_REG_BIG(EXPR); }                                  \
     } while (0)
 
-template <typename real>
-static inline cudaError_t cluster_prepare(const ClusterTables &t, int threads, size_t smem, int *max_clusters) {
+template <typename real, int DC, int DV>
+cudaError_t ClusterInst<real, DC, DV>::prepare(const ClusterTables &t, int threads, size_t smem, int *max_clusters) {
     cudaError_t e = cudaSuccess;
-    BPOSD_CL_DISPATCH(t, {
+    BPOSD_CL_GEOM(t, {
         auto kern = (bp_cluster_kernel<real, DC, DV, VPT, MAXT, REG>);
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess && t.CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -473,15 +480,11 @@ static inline cudaError_t cluster_prepare(const ClusterTables &t, int threads, s
     return e;
 }
 
-template <typename real>
-static inline cudaError_t cluster_launch(const ClusterTables &t, const BpArgs<real> &a, int nclusters, int threads, size_t smem,
-                                         int flip_table, cudaStream_t st) {
-    ClusterDev d;
-    d.vslot = t.d_vslot; d.cdeg = t.d_cdeg; d.row_of = t.d_row_of; d.bit_of = t.d_bit_of;
-    d.rows_per_cta = t.rows_per_cta; d.bits_per_cta = t.bits_per_cta; d.CL = t.CL;
-    d.flip_table = flip_table;
+template <typename real, int DC, int DV>
+cudaError_t ClusterInst<real, DC, DV>::launch(const ClusterTables &t, const BpArgs<real> &a, const ClusterDev &d, int nclusters, int threads,
+                                              size_t smem, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
-    BPOSD_CL_DISPATCH(t, {
+    BPOSD_CL_GEOM(t, {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(nclusters * t.CL, 1, 1); cfg.blockDim = dim3(threads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1];
@@ -490,6 +493,26 @@ static inline cudaError_t cluster_launch(const ClusterTables &t, const BpArgs<re
         cfg.attrs = at; cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, bp_cluster_kernel<real, DC, DV, VPT, MAXT, REG>, a, d);
     });
+    return e;
+}
+#endif // BPOSD_CLUSTER_INSTANTIATE
+
+template <typename real>
+static inline cudaError_t cluster_prepare(const ClusterTables &t, int threads, size_t smem, int *max_clusters) {
+    cudaError_t e = cudaSuccess;
+    BPOSD_FAST_CLASS(t, (e = ClusterInst<real, DC, DV>::prepare(t, threads, smem, max_clusters)));
+    return e;
+}
+
+template <typename real>
+static inline cudaError_t cluster_launch(const ClusterTables &t, const BpArgs<real> &a, int nclusters, int threads, size_t smem,
+                                         int flip_table, cudaStream_t st) {
+    ClusterDev d;
+    d.vslot = t.d_vslot; d.cdeg = t.d_cdeg; d.row_of = t.d_row_of; d.bit_of = t.d_bit_of;
+    d.rows_per_cta = t.rows_per_cta; d.bits_per_cta = t.bits_per_cta; d.CL = t.CL;
+    d.flip_table = flip_table;
+    cudaError_t e = cudaSuccess;
+    BPOSD_FAST_CLASS(t, (e = ClusterInst<real, DC, DV>::launch(t, a, d, nclusters, threads, smem, st)));
     return e;
 }
 

@@ -741,10 +741,22 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG>
 }
 
 // ---- dispatch over the degree classes ---------------------------------------------------------
+// Every (precision, degree class) pair is its own translation unit (bp_fast_inst.cu, compiled once per pair by
+// bp_osd_b200/build.py with -DBPOSD_INST_REAL / _DC / _DV): FastInst<real, DC, DV> is declared here for every
+// includer and defined (which is what instantiates the kernels) only where BPOSD_FAST_INSTANTIATE is set.
+template <typename real, int DC, int DV>
+struct FastInst {
+    static cudaError_t set_smem(const FastTables &t, int geom, size_t smem);
+    static cudaError_t occupancy(const FastTables &t, int geom, int threads, size_t smem, int *occ);
+    static void launch(const FastTables &t, int geom, const BpArgs<real> &a, int grid, int threads, int smem, cudaStream_t st);
+};
+
+#ifdef BPOSD_FAST_INSTANTIATE
 #define BPOSD_FAST_REG(EXPR) do { if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } while (0)
-#define BPOSD_FAST_GEOM(DCv, DVv, EXPR)                                                          \
+#define BPOSD_FAST_GEOM(t, geom, EXPR)                                                           \
     do {                                                                                         \
-        constexpr int DC = DCv, DV = DVv;                                                        \
+        const int geom__ = (geom);                                                               \
+        const bool reg__ = t.regular != 0;                                                       \
         if (geom__ == 0) { constexpr int VPT = 2, MAXT = 128; BPOSD_FAST_REG(EXPR); }            \
         else if (geom__ == 1) { constexpr int VPT = BPOSD_MID_VPT, MAXT = BPOSD_MID_MAXT; BPOSD_FAST_REG(EXPR); } \
         else if (geom__ == 4) { constexpr int VPT = sizeof(real) == 8 ? BPOSD_LAT_VPT64 : BPOSD_LAT_VPT32,               \
@@ -753,40 +765,51 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG>
         else { constexpr int VPT = 8, MAXT = 1024; BPOSD_FAST_REG(EXPR); }                       \
     } while (0)
 
-#ifdef BPOSD_DEV_DC6 // tuning builds only: instantiate the (6, 3) degree class alone (the bench code), 4x faster to compile
-#define BPOSD_FAST_DISPATCH(t, geom, EXPR)                                                       \
-    do {                                                                                         \
-        const int geom__ = (geom);                                                               \
-        const bool reg__ = t.regular != 0;                                                       \
-        BPOSD_FAST_GEOM(6, 3, EXPR);                                                             \
-    } while (0)
+template <typename real, int DC, int DV>
+cudaError_t FastInst<real, DC, DV>::set_smem(const FastTables &t, int geom, size_t smem) {
+    cudaError_t e = cudaSuccess;
+    BPOSD_FAST_GEOM(t, geom, e = cudaFuncSetAttribute(bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return e;
+}
+template <typename real, int DC, int DV>
+cudaError_t FastInst<real, DC, DV>::occupancy(const FastTables &t, int geom, int threads, size_t smem, int *occ) {
+    cudaError_t e = cudaSuccess;
+    BPOSD_FAST_GEOM(t, geom, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, threads, smem));
+    return e;
+}
+template <typename real, int DC, int DV>
+void FastInst<real, DC, DV>::launch(const FastTables &t, int geom, const BpArgs<real> &a, int grid, int threads, int smem, cudaStream_t st) {
+    BPOSD_FAST_GEOM(t, geom, (bp_fast_kernel<real, DC, DV, VPT, MAXT, REG><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg, t.d_row_of, t.d_bit_of)));
+}
+#endif // BPOSD_FAST_INSTANTIATE
+
+#ifdef BPOSD_DEV_CLASS_ONLY // tuning builds (BPOSD_DEV_CLASS=6,3 python -m bp_osd_b200.build): one degree class alone
+#define BPOSD_FAST_CLASS(t, EXPR) do { constexpr int DC = BPOSD_DEV_DC, DV = BPOSD_DEV_DC / 2; EXPR; } while (0)
 #else
-#define BPOSD_FAST_DISPATCH(t, geom, EXPR)                                                       \
+#define BPOSD_FAST_CLASS(t, EXPR)                                                                \
     do {                                                                                         \
-        const int geom__ = (geom);                                                               \
-        const bool reg__ = t.regular != 0;                                                       \
-        if (t.DC == 4) BPOSD_FAST_GEOM(4, 2, EXPR);                                              \
-        else if (t.DC == 6) BPOSD_FAST_GEOM(6, 3, EXPR);                                         \
-        else if (t.DC == 8) BPOSD_FAST_GEOM(8, 4, EXPR);                                         \
-        else BPOSD_FAST_GEOM(16, 8, EXPR);                                                       \
+        if (t.DC == 4) { constexpr int DC = 4, DV = 2; EXPR; }                                   \
+        else if (t.DC == 6) { constexpr int DC = 6, DV = 3; EXPR; }                              \
+        else if (t.DC == 8) { constexpr int DC = 8, DV = 4; EXPR; }                              \
+        else { constexpr int DC = 16, DV = 8; EXPR; }                                            \
     } while (0)
 #endif
 
 template <typename real>
 static inline cudaError_t fast_set_smem_t(const FastTables &t, int geom, size_t smem) {
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_DISPATCH(t, geom, e = cudaFuncSetAttribute(bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BPOSD_FAST_CLASS(t, (e = FastInst<real, DC, DV>::set_smem(t, geom, smem)));
     return e;
 }
 template <typename real>
 static inline cudaError_t fast_occupancy_t(const FastTables &t, int geom, int threads, size_t smem, int *occ) {
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_DISPATCH(t, geom, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, threads, smem));
+    BPOSD_FAST_CLASS(t, (e = FastInst<real, DC, DV>::occupancy(t, geom, threads, smem, occ)));
     return e;
 }
 template <typename real>
 static inline void fast_launch(const FastTables &t, int geom, const BpArgs<real> &a, int grid, int threads, int smem, cudaStream_t st) {
-    BPOSD_FAST_DISPATCH(t, geom, (bp_fast_kernel<real, DC, DV, VPT, MAXT, REG><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg, t.d_row_of, t.d_bit_of)));
+    BPOSD_FAST_CLASS(t, (FastInst<real, DC, DV>::launch(t, geom, a, grid, threads, smem, st)));
 }
 
 } // namespace bposd

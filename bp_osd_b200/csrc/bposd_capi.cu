@@ -8,7 +8,6 @@
 #include "bposd_kernels.cuh"
 #include "bp_fast_kernel.cuh"
 #include "bp_cluster_kernel.cuh"
-#include "osd_panel_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -72,9 +71,7 @@ struct bposd_handle {
     bool osd_supported = true;
     // large-H OSD-0 (T does not fit in shared memory): HBM workspace, one CTA per failed shot
     bool osd_large = false;
-    int osd_variant = 0; // 0 auto, 1 T-matrix shared-memory kernel, 2 HBM-resident kernel, 3 panel shared-memory kernel
-    bool osd_panel = false;
-    int osdp_smem = 0;
+    int osd_variant = 0; // 0 auto, 1 T-matrix shared-memory kernel, 2 HBM-resident kernel
     int osdl_smem = 0, osdl_grid = 0, osdl_npanels = 0;
     long long osdl_ws_cap = 16ll << 30;
     uint32_t *d_osdl_mask = nullptr;
@@ -310,22 +307,7 @@ static int plan_geometry_t(bposd_handle *h) {
         h->osdl_grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, h->osdl_ws_cap / (long long)std::max<size_t>(per_cta, 1)));
         h->osd_supported = true;
     }
-    // panel kernel (default when it fits): same m^2/8-byte footprint as the T-matrix kernel, ~20x less traffic
-    h->osdp_smem = (int)osd_panel_smem_bytes(m, n, h->osd_threads);
-    const bool panel_ok = (size_t)h->osdp_smem <= (size_t)h->smem_optin && n < 65535 && m < 65535 && (std::min(m, n) + 31) / 32 <= 254 && m > 0;
-    if (h->osd_variant == 3 && !panel_ok) return fail(h, BPOSD_EUNSUP, "the panel OSD kernel does not fit this matrix in shared memory");
-    // measured on B200 (profiles/r01o_speed.log): although it moves ~20x fewer shared-memory words, the panel kernel's
-    // ~8 000 short barrier-separated steps per shot make it 1.6-2.5x slower than the T-matrix kernel's ~1 900
-    // bulk sweeps, so it is only used on request or when the T-matrix kernel does not fit
-    h->osd_panel = !h->osd_large && panel_ok && (h->osd_variant == 3 || (h->osd_variant == 0 && !h->osd_supported));
-    if (h->osd_panel) {
-        CU_TRY(h, cudaFuncSetAttribute(osd_panel_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->osdp_smem));
-        int occ3 = 0;
-        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, osd_panel_kernel<real>, h->osd_threads, h->osdp_smem));
-        h->osd_ctas_per_sm = std::max(1, occ3);
-        h->osd_supported = true;
-    }
-    if (h->osd_supported && !h->osd_large && !h->osd_panel) {
+    if (h->osd_supported && !h->osd_large) {
         CU_TRY(h, cudaFuncSetAttribute(osd_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osd_smem));
         int occ2 = 0;
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, osd_kernel<real>, h->osd_threads, osd_smem));
@@ -516,7 +498,7 @@ extern "C" int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size) {
 
 extern "C" int bposd_set_osd_variant(bposd_t *h, int32_t variant, int64_t workspace_bytes) {
     if (!h) return BPOSD_EINVAL;
-    if (variant < 0 || variant > 3) return fail(h, BPOSD_EINVAL, "osd variant must be 0 (auto), 1 (T matrix in shared memory), 2 (HBM resident) or 3 (panels in shared memory)");
+    if (variant < 0 || variant > 2) return fail(h, BPOSD_EINVAL, "osd variant must be 0 (auto), 1 (T matrix in shared memory) or 2 (HBM resident)");
     CU_TRY(h, cudaSetDevice(h->device));
     const int old = h->osd_variant;
     h->osd_variant = variant;
@@ -534,8 +516,7 @@ extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
     info->bp_kernel = h->bp_kernel; info->bp_threads = h->bp_threads; info->bp_ctas_per_sm = h->bp_ctas_per_sm;
     info->bp_smem_bytes = h->bp_smem; info->osd_threads = h->osd_threads; info->osd_smem_bytes = h->osd_smem;
     info->sm_count = h->sm_count; info->ms_scaling_factor = h->alpha;
-    info->osd_variant = !h->osd_supported ? 0 : (h->osd_large ? 2 : (h->osd_panel ? 3 : 1));
-    if (h->osd_panel) info->osd_smem_bytes = h->osdp_smem;
+    info->osd_variant = !h->osd_supported ? 0 : (h->osd_large ? 2 : 1);
     info->bp_layout_excess = h->bp_kernel == 3 ? (int32_t)(1000 * h->clus.remote_edges / std::max<long long>(h->clus.total_edges, 1))
                                                : (int32_t)h->fast.conflicts_after;
     info->bp_cluster_size = h->bp_kernel == 3 ? h->clus.CL : 1;
@@ -583,25 +564,6 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
         o.ws_mask = h->d_osdl_mask; o.ws_order = h->d_osdl_order;
         o.ws_piv_row = h->d_osdl_piv_row; o.ws_piv_pos = h->d_osdl_piv_pos; o.ws_pstart = h->d_osdl_pstart;
         osd0_large_kernel<real><<<ogrid, 1024, h->osdl_smem, st>>>(o);
-        CU_TRY(h, cudaGetLastError());
-        (*launches)++;
-    } else if (h->osd_panel) {
-        OsdPanelArgs<real> o;
-        o.g = g;
-        o.S = h->osd_S; o.nb = (std::min(m, n) + 31) / 32; o.maxrank = h->rank;
-        o.method = h->osd_method; o.order = h->osd_order;
-        o.uniform = (per_shot_priors || d_weights) ? 0 : h->uniform;
-        o.weight = d_weights ? d_weights : h->d_weight;
-        o.weight_stride = d_weights ? n : 0;
-        o.synd = d_synd;
-        o.llr = llr;
-        o.llr_by_shot = llr_by_shot;
-        o.fail_count = d_fail_count;
-        o.fail_list = d_fail_list;
-        o.osd0 = d_osd0; o.osdw = d_osdw;
-        o.stat = d_stat;
-        const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
-        osd_panel_kernel<real><<<ogrid, h->osd_threads, h->osdp_smem, st>>>(o);
         CU_TRY(h, cudaGetLastError());
         (*launches)++;
     } else {

@@ -111,6 +111,7 @@ __device__ __forceinline__ void bp_write_shot(const BpArgs<real> &a, long long s
     }
 }
 
+#ifndef BPOSD_KERNELS_COMMON_ONLY // the specialised-BP translation units need only the declarations above
 // ---------------------------------------------------------------------------------------------
 // Generic BP kernel (rows a3-a8).  Literal flooding schedule with separate bit->check and
 // check->bit arrays, any row/column degree.  SMEM=true: state carved from dynamic shared
@@ -961,5 +962,7 @@ __global__ void __launch_bounds__(256) css_counters_kernel(long long B, CssSecto
     for (int o = 16; o > 0; o >>= 1) minw = min(minw, __shfl_xor_sync(0xffffffffu, minw, o));
     if ((threadIdx.x & 31) == 0 && minw != 0x7fffffff) atomicMin(min_weight, minw);
 }
+
+#endif // BPOSD_KERNELS_COMMON_ONLY
 
 } // namespace bposd
