@@ -16,8 +16,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libbposd_b200.so")
-HEADERS = ["bposd_kernels.cuh", "bp_fast_kernel.cuh", "bp_cluster_kernel.cuh", "osd_reg_kernel.cuh", "bposd_math.h",
-           os.path.join("..", "..", "include", "bposd_b200.h")]
+_INC = os.path.join("..", "..", "include")
+HEADERS = ["bposd_kernels.cuh", "bp_fast_kernel.cuh", "bp_cluster_kernel.cuh", "osd_reg_kernel.cuh",
+           os.path.join(_INC, "bposd_math.h"), os.path.join(_INC, "bposd_b200.h")]
+# headers each source actually includes (the object cache is keyed by their contents)
+DEPS = {"bposd_capi.cu": HEADERS,
+        "bp_fast_inst.cu": ["bposd_kernels.cuh", "bp_fast_kernel.cuh", os.path.join(_INC, "bposd_math.h")],
+        "bp_cluster_inst.cu": ["bposd_kernels.cuh", "bp_fast_kernel.cuh", "bp_cluster_kernel.cuh", os.path.join(_INC, "bposd_math.h")]}
 CLASSES = [(4, 2), (6, 3), (8, 4), (16, 8)]  # (max row degree, max column degree) classes of the specialised BP kernels
 
 NVCC_FLAGS = [
@@ -44,7 +49,7 @@ def units(only_class=None):
 def _digest(src, flags):
     h = hashlib.sha256()
     h.update(" ".join(flags).encode())
-    for f in [src] + HEADERS:
+    for f in [src] + DEPS[src]:
         p = os.path.join(CSRC, f)
         if os.path.exists(p):
             with open(p, "rb") as fh:

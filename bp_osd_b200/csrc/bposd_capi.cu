@@ -8,6 +8,7 @@
 #include "bposd_kernels.cuh"
 #include "bp_fast_kernel.cuh"
 #include "bp_cluster_kernel.cuh"
+#include "osd_reg_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -71,7 +72,9 @@ struct bposd_handle {
     bool osd_supported = true;
     // large-H OSD-0 (T does not fit in shared memory): HBM workspace, one CTA per failed shot
     bool osd_large = false;
-    int osd_variant = 0; // 0 auto, 1 T-matrix shared-memory kernel, 2 HBM-resident kernel
+    int osd_variant = 0; // 0 auto, 1 T-matrix shared-memory kernel, 2 HBM-resident kernel, 3 T-matrix register kernel
+    bool osd_reg = false; // the register kernel is selected (m <= 1024)
+    int osdr_W = 0, osdr_threads = 0, osdr_smem = 0;
     int osdl_smem = 0, osdl_grid = 0, osdl_npanels = 0;
     long long osdl_ws_cap = 16ll << 30;
     uint32_t *d_osdl_mask = nullptr;
@@ -307,7 +310,43 @@ static int plan_geometry_t(bposd_handle *h) {
         h->osdl_grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, h->osdl_ws_cap / (long long)std::max<size_t>(per_cta, 1)));
         h->osd_supported = true;
     }
-    if (h->osd_supported && !h->osd_large) {
+    // register kernel (default whenever it applies): T in registers, two barriers per 16 sorted columns
+    {
+        const int Sw = (m + 31) / 32;
+        h->osdr_W = Sw <= 4 ? 4 : (Sw <= 8 ? 8 : (Sw <= 16 ? 16 : 32));
+        h->osdr_threads = std::max(64, ((m + kOsdRegCPT - 1) / kOsdRegCPT + 31) / 32 * 32);
+        size_t rs_ = 0;
+        switch (h->osdr_W) {
+            case 4: rs_ = osd_reg_smem_bytes<4>(m, n, h->osdr_threads, std::max(h->max_col_deg, 1)); break;
+            case 8: rs_ = osd_reg_smem_bytes<8>(m, n, h->osdr_threads, std::max(h->max_col_deg, 1)); break;
+            case 16: rs_ = osd_reg_smem_bytes<16>(m, n, h->osdr_threads, std::max(h->max_col_deg, 1)); break;
+            default: rs_ = osd_reg_smem_bytes<32>(m, n, h->osdr_threads, std::max(h->max_col_deg, 1)); break;
+        }
+        h->osdr_smem = (int)rs_;
+        const bool reg_ok = m >= 1 && m <= 1024 && n < 65535 && h->max_col_deg <= 64 && rs_ <= (size_t)h->smem_optin;
+        if (h->osd_variant == 3 && !reg_ok)
+            return fail(h, BPOSD_EUNSUP, "the register OSD kernel needs m <= 1024, n < 65535 and column degrees up to 64");
+        h->osd_reg = reg_ok && (h->osd_variant == 3 || h->osd_variant == 0);
+        if (h->osd_reg) {
+            h->osd_large = false;
+            h->osd_supported = true;
+            int occ4 = 0;
+#define BPOSD_OSDR_SETUP(Wv)                                                                                                         \
+    do {                                                                                                                             \
+        CU_TRY(h, cudaFuncSetAttribute(osd_reg_kernel<real, Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->osdr_smem));         \
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, osd_reg_kernel<real, Wv>, h->osdr_threads, h->osdr_smem));      \
+    } while (0)
+            switch (h->osdr_W) {
+                case 4: BPOSD_OSDR_SETUP(4); break;
+                case 8: BPOSD_OSDR_SETUP(8); break;
+                case 16: BPOSD_OSDR_SETUP(16); break;
+                default: BPOSD_OSDR_SETUP(32); break;
+            }
+#undef BPOSD_OSDR_SETUP
+            h->osd_ctas_per_sm = std::max(1, occ4);
+        }
+    }
+    if (h->osd_supported && !h->osd_large && !h->osd_reg) {
         CU_TRY(h, cudaFuncSetAttribute(osd_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osd_smem));
         int occ2 = 0;
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, osd_kernel<real>, h->osd_threads, osd_smem));
@@ -498,7 +537,7 @@ extern "C" int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size) {
 
 extern "C" int bposd_set_osd_variant(bposd_t *h, int32_t variant, int64_t workspace_bytes) {
     if (!h) return BPOSD_EINVAL;
-    if (variant < 0 || variant > 2) return fail(h, BPOSD_EINVAL, "osd variant must be 0 (auto), 1 (T matrix in shared memory) or 2 (HBM resident)");
+    if (variant < 0 || variant > 3) return fail(h, BPOSD_EINVAL, "osd variant must be 0 (auto), 1 (T matrix in shared memory), 2 (HBM resident) or 3 (T matrix in registers)");
     CU_TRY(h, cudaSetDevice(h->device));
     const int old = h->osd_variant;
     h->osd_variant = variant;
@@ -516,7 +555,8 @@ extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
     info->bp_kernel = h->bp_kernel; info->bp_threads = h->bp_threads; info->bp_ctas_per_sm = h->bp_ctas_per_sm;
     info->bp_smem_bytes = h->bp_smem; info->osd_threads = h->osd_threads; info->osd_smem_bytes = h->osd_smem;
     info->sm_count = h->sm_count; info->ms_scaling_factor = h->alpha;
-    info->osd_variant = !h->osd_supported ? 0 : (h->osd_large ? 2 : 1);
+    info->osd_variant = !h->osd_supported ? 0 : (h->osd_large ? 2 : (h->osd_reg ? 3 : 1));
+    if (h->osd_reg) { info->osd_threads = h->osdr_threads; info->osd_smem_bytes = h->osdr_smem; }
     info->bp_layout_excess = h->bp_kernel == 3 ? (int32_t)(1000 * h->clus.remote_edges / std::max<long long>(h->clus.total_edges, 1))
                                                : (int32_t)h->fast.conflicts_after;
     info->bp_cluster_size = h->bp_kernel == 3 ? h->clus.CL : 1;
@@ -570,6 +610,7 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
         OsdArgs<real> o;
         o.g = g;
         o.S = h->osd_S; o.St = h->osd_St;
+        o.maxrank = h->rank; o.maxdeg = std::max(h->max_col_deg, 1);
         o.method = h->osd_method; o.order = h->osd_order;
         o.uniform = (per_shot_priors || d_weights) ? 0 : h->uniform;
         o.weight = d_weights ? d_weights : h->d_weight;
@@ -582,6 +623,14 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
         o.osd0 = d_osd0; o.osdw = d_osdw;
         o.stat = d_stat;
         const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
+        if (h->osd_reg) {
+            switch (h->osdr_W) {
+                case 4: osd_reg_kernel<real, 4><<<ogrid, h->osdr_threads, h->osdr_smem, st>>>(o); break;
+                case 8: osd_reg_kernel<real, 8><<<ogrid, h->osdr_threads, h->osdr_smem, st>>>(o); break;
+                case 16: osd_reg_kernel<real, 16><<<ogrid, h->osdr_threads, h->osdr_smem, st>>>(o); break;
+                default: osd_reg_kernel<real, 32><<<ogrid, h->osdr_threads, h->osdr_smem, st>>>(o); break;
+            }
+        } else
         osd_kernel<real><<<ogrid, h->osd_threads, h->osd_smem, st>>>(o);
         CU_TRY(h, cudaGetLastError());
         (*launches)++;

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <float.h>
+#include "../../include/bposd_math.h"
 
 namespace bposd {
 
@@ -70,9 +71,10 @@ __device__ __forceinline__ float ms_alpha(float alpha0, int it) {
 // mode applies no clipping, exactly like the reference (row a5).
 __device__ __forceinline__ double ps_clamp(double x) { return x; }
 __device__ __forceinline__ float ps_clamp(float x) { return fminf(fmaxf(x, -0.99999994f), 0.99999994f); }
-__device__ __forceinline__ double r_tanh(double x) { return tanh(x); }
+// fp64: the portable FMA-free functions the oracle also compiles (include/bposd_math.h) -- same bits on both sides
+__device__ __forceinline__ double r_tanh(double x) { return bpm_tanh(x); }
 __device__ __forceinline__ float r_tanh(float x) { return tanhf(x); }
-__device__ __forceinline__ double r_log(double x) { return log(x); }
+__device__ __forceinline__ double r_log(double x) { return bpm_log(x); }
 __device__ __forceinline__ float r_log(float x) { return logf(x); }
 __device__ __forceinline__ double r_abs(double x) { return fabs(x); }
 __device__ __forceinline__ float r_abs(float x) { return fabsf(x); }
@@ -275,6 +277,8 @@ struct OsdArgs {
     const int *fail_list;
     uint8_t *osd0, *osdw;
     unsigned long long *stat; // [2] osd invocations
+    int maxrank;  // rank(H): no pivot can follow the maxrank-th (osd_reg_kernel stops its scan there)
+    int maxdeg;   // largest column degree of H (osd_reg_kernel: capacity of a candidate's row list)
 };
 
 __device__ __forceinline__ unsigned long long sort_key(double x) {
@@ -295,6 +299,144 @@ __device__ __forceinline__ uint32_t reduced_col_word(const GraphDev &g, const ui
     uint32_t v = 0;
     for (int q = g.col_ptr[c]; q < g.col_ptr[c + 1]; q++) v ^= Tc[g.row_idx[q] * St + w];
     return v;
+}
+
+// a11 read-out + a12-a14 candidate search + result write of one failed shot, shared by the OSD kernels.  On entry the
+// elimination is finished: Tc holds the m x m row-operation matrix (column r at Tc + r*St, S words), `used` the pivot
+// rows, `sprime` = (T s) & used, order/prow/np/nnp the column order, pivot row of every pivot column and the non-pivot
+// positions in sorted order; the caller has synchronised the CTA.  wscr: nwarps * (S + 64) words of scratch.
+template <typename real>
+__device__ __forceinline__ void osd_readout_and_search(const OsdArgs<real> &a, long long shot, const double *weight, const uint32_t *Tc,
+                                                       int St, const uint32_t *used, const uint32_t *sprime, uint32_t *wscr, double *red_w,
+                                                       int *red_c, const uint16_t *order, const uint16_t *prow, const uint16_t *np, int nnp,
+                                                       int *sh_best, int *sh_found) {
+    const GraphDev &g = a.g;
+    const int n = g.n, S = a.S;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const long long base = shot * (long long)n;
+    for (int j = tid; j < n; j += T) {
+        const unsigned pr = prow[j];
+        uint8_t x = (pr != OSD_NONE) ? (uint8_t)((sprime[pr >> 5] >> (pr & 31)) & 1u) : 0;
+        if (a.osd0) a.osd0[base + j] = x;
+        if (a.osdw) a.osdw[base + j] = x; // overwritten below if a candidate wins
+    }
+    if (tid == 0 && a.stat) atomicAdd(&a.stat[2], 1ull);
+
+    const int wd = a.order;
+    if (a.method == 0 || wd <= 0 || !a.osdw) return;
+
+    // ---- a12-a14: candidate search.  Candidate -1 is OSD-0 itself. ----
+    long long ncand = (a.method == 1) ? ((1ll << wd) - 1) : ((long long)nnp + (long long)wd * (wd - 1) / 2);
+    uint32_t *s2 = wscr + (size_t)warp * (S + 64);
+    int *selcol = reinterpret_cast<int *>(s2 + S);
+    double bestW = 0;
+    long long bestC = -2; // nothing yet
+    for (long long c = -1 + warp; c < ncand; c += nwarps) {
+        // decode the selection of non-pivot positions
+        int nsel = 0;
+        __syncwarp();
+        if (c >= 0) {
+            if (a.method == 1) {
+                long long v = c + 1;
+                for (int b = 0; b < wd; b++)
+                    if ((v >> b) & 1) { if (lane == 0) selcol[nsel] = order[np[b]]; nsel++; }
+            } else if (c < nnp) {
+                if (lane == 0) selcol[0] = order[np[c]];
+                nsel = 1;
+            } else {
+                int idx = (int)(c - nnp), i = 0;
+                while (idx >= wd - 1 - i) { idx -= wd - 1 - i; i++; }
+                if (lane == 0) { selcol[0] = order[np[i]]; selcol[1] = order[np[i + 1 + idx]]; }
+                nsel = 2;
+            }
+        }
+        __syncwarp();
+        // s'' = s' + reduced images of the selected columns
+        int pc = 0;
+        for (int w = lane; w < S; w += 32) {
+            uint32_t v = sprime[w];
+            for (int q = 0; q < nsel; q++) v ^= reduced_col_word(g, Tc, St, selcol[q], w);
+            v &= used[w];
+            s2[w] = v;
+            pc += __popc(v);
+        }
+        double W;
+        if (a.uniform) {
+            for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+            W = (double)(pc + nsel);
+        } else {
+            __syncwarp();
+            W = 0;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                int x = 0;
+                if (j < n) {
+                    const unsigned pr = prow[j];
+                    if (pr != OSD_NONE) x = (s2[pr >> 5] >> (pr & 31)) & 1u;
+                    else
+                        for (int q = 0; q < nsel; q++) x |= (selcol[q] == j) ? 1 : 0;
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, x);
+                while (mask) { // ascending j, sequential fp64 accumulation (row a14)
+                    const int b = __ffs(mask) - 1;
+                    W += weight[j0 + b];
+                    mask &= mask - 1;
+                }
+            }
+        }
+        if (bestC == -2 || W < bestW) { bestW = W; bestC = c; }
+    }
+    if (lane == 0) { red_w[warp] = bestW; red_c[warp] = (int)bestC; }
+    __syncthreads();
+    if (tid == 0) {
+        double bw = 0; int bc = -2;
+        for (int k = 0; k < nwarps; k++) {
+            if (red_c[k] == -2) continue;
+            if (bc == -2 || red_w[k] < bw || (red_w[k] == bw && red_c[k] < bc)) { bw = red_w[k]; bc = red_c[k]; }
+        }
+        *sh_best = bc;
+    }
+    __syncthreads();
+    const int bc = *sh_best;
+    if (bc < 0) return; // OSD-0 stands (strict '<' in the reference: ties keep the earlier)
+    // rebuild the winner and write it
+    if (warp == 0) {
+        int nsel = 0;
+        if (a.method == 1) {
+            long long v = (long long)bc + 1;
+            for (int b = 0; b < wd; b++)
+                if ((v >> b) & 1) { if (lane == 0) selcol[nsel] = order[np[b]]; nsel++; }
+        } else if (bc < nnp) {
+            if (lane == 0) selcol[0] = order[np[bc]];
+            nsel = 1;
+        } else {
+            int idx = bc - nnp, i = 0;
+            while (idx >= wd - 1 - i) { idx -= wd - 1 - i; i++; }
+            if (lane == 0) { selcol[0] = order[np[i]]; selcol[1] = order[np[i + 1 + idx]]; }
+            nsel = 2;
+        }
+        __syncwarp();
+        for (int w = lane; w < S; w += 32) {
+            uint32_t v = sprime[w];
+            for (int q = 0; q < nsel; q++) v ^= reduced_col_word(g, Tc, St, selcol[q], w);
+            s2[w] = v & used[w];
+        }
+        if (lane == 0) *sh_found = nsel;
+    }
+    __syncthreads();
+    {
+        const int nsel = *sh_found;
+        const uint32_t *w0 = wscr;
+        const int *sel0 = reinterpret_cast<const int *>(w0 + S);
+        for (int j = tid; j < n; j += T) {
+            const unsigned pr = prow[j];
+            int x = 0;
+            if (pr != OSD_NONE) x = (w0[pr >> 5] >> (pr & 31)) & 1u;
+            else
+                for (int q = 0; q < nsel; q++) x |= (sel0[q] == j) ? 1 : 0;
+            a.osdw[base + j] = (uint8_t)x;
+        }
+    }
 }
 
 template <typename real>
@@ -434,130 +576,7 @@ __global__ void __launch_bounds__(1024, 1) osd_kernel(OsdArgs<real> a) {
             }
             __syncthreads();
         }
-        const long long base = shot * (long long)n;
-        for (int j = tid; j < n; j += T) {
-            const unsigned pr = prow[j];
-            uint8_t x = (pr != OSD_NONE) ? (uint8_t)((sprime[pr >> 5] >> (pr & 31)) & 1u) : 0;
-            if (a.osd0) a.osd0[base + j] = x;
-            if (a.osdw) a.osdw[base + j] = x; // overwritten below if a candidate wins
-        }
-        if (tid == 0 && a.stat) atomicAdd(&a.stat[2], 1ull);
-
-        const int wd = a.order;
-        if (a.method == 0 || wd <= 0 || !a.osdw) continue;
-
-        // ---- a12-a14: candidate search.  Candidate -1 is OSD-0 itself. ----
-        long long ncand = (a.method == 1) ? ((1ll << wd) - 1) : ((long long)nnp + (long long)wd * (wd - 1) / 2);
-        uint32_t *s2 = wscr + (size_t)warp * (S + 64);
-        int *selcol = reinterpret_cast<int *>(s2 + S);
-        double bestW = 0;
-        long long bestC = -2; // nothing yet
-        for (long long c = -1 + warp; c < ncand; c += nwarps) {
-            // decode the selection of non-pivot positions
-            int nsel = 0;
-            __syncwarp();
-            if (c >= 0) {
-                if (a.method == 1) {
-                    long long v = c + 1;
-                    for (int b = 0; b < wd; b++)
-                        if ((v >> b) & 1) { if (lane == 0) selcol[nsel] = order[np[b]]; nsel++; }
-                } else if (c < nnp) {
-                    if (lane == 0) selcol[0] = order[np[c]];
-                    nsel = 1;
-                } else {
-                    int idx = (int)(c - nnp), i = 0;
-                    while (idx >= wd - 1 - i) { idx -= wd - 1 - i; i++; }
-                    if (lane == 0) { selcol[0] = order[np[i]]; selcol[1] = order[np[i + 1 + idx]]; }
-                    nsel = 2;
-                }
-            }
-            __syncwarp();
-            // s'' = s' + reduced images of the selected columns
-            int pc = 0;
-            for (int w = lane; w < S; w += 32) {
-                uint32_t v = sprime[w];
-                for (int q = 0; q < nsel; q++) v ^= reduced_col_word(g, Tc, St, selcol[q], w);
-                v &= used[w];
-                s2[w] = v;
-                pc += __popc(v);
-            }
-            double W;
-            if (a.uniform) {
-                for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
-                W = (double)(pc + nsel);
-            } else {
-                __syncwarp();
-                W = 0;
-                for (int j0 = 0; j0 < n; j0 += 32) {
-                    const int j = j0 + lane;
-                    int x = 0;
-                    if (j < n) {
-                        const unsigned pr = prow[j];
-                        if (pr != OSD_NONE) x = (s2[pr >> 5] >> (pr & 31)) & 1u;
-                        else
-                            for (int q = 0; q < nsel; q++) x |= (selcol[q] == j) ? 1 : 0;
-                    }
-                    unsigned mask = __ballot_sync(0xffffffffu, x);
-                    while (mask) { // ascending j, sequential fp64 accumulation (row a14)
-                        const int b = __ffs(mask) - 1;
-                        W += weight[j0 + b];
-                        mask &= mask - 1;
-                    }
-                }
-            }
-            if (bestC == -2 || W < bestW) { bestW = W; bestC = c; }
-        }
-        if (lane == 0) { red_w[warp] = bestW; red_c[warp] = (int)bestC; }
-        __syncthreads();
-        if (tid == 0) {
-            double bw = 0; int bc = -2;
-            for (int k = 0; k < nwarps; k++) {
-                if (red_c[k] == -2) continue;
-                if (bc == -2 || red_w[k] < bw || (red_w[k] == bw && red_c[k] < bc)) { bw = red_w[k]; bc = red_c[k]; }
-            }
-            sh_best = bc;
-        }
-        __syncthreads();
-        const int bc = sh_best;
-        if (bc < 0) continue; // OSD-0 stands (strict '<' in the reference: ties keep the earlier)
-        // rebuild the winner and write it
-        if (warp == 0) {
-            int nsel = 0;
-            if (a.method == 1) {
-                long long v = (long long)bc + 1;
-                for (int b = 0; b < wd; b++)
-                    if ((v >> b) & 1) { if (lane == 0) selcol[nsel] = order[np[b]]; nsel++; }
-            } else if (bc < nnp) {
-                if (lane == 0) selcol[0] = order[np[bc]];
-                nsel = 1;
-            } else {
-                int idx = bc - nnp, i = 0;
-                while (idx >= wd - 1 - i) { idx -= wd - 1 - i; i++; }
-                if (lane == 0) { selcol[0] = order[np[i]]; selcol[1] = order[np[i + 1 + idx]]; }
-                nsel = 2;
-            }
-            __syncwarp();
-            for (int w = lane; w < S; w += 32) {
-                uint32_t v = sprime[w];
-                for (int q = 0; q < nsel; q++) v ^= reduced_col_word(g, Tc, St, selcol[q], w);
-                s2[w] = v & used[w];
-            }
-            if (lane == 0) sh_found = nsel;
-        }
-        __syncthreads();
-        {
-            const int nsel = sh_found;
-            const uint32_t *w0 = wscr;
-            const int *sel0 = reinterpret_cast<const int *>(w0 + S);
-            for (int j = tid; j < n; j += T) {
-                const unsigned pr = prow[j];
-                int x = 0;
-                if (pr != OSD_NONE) x = (w0[pr >> 5] >> (pr & 31)) & 1u;
-                else
-                    for (int q = 0; q < nsel; q++) x |= (sel0[q] == j) ? 1 : 0;
-                a.osdw[base + j] = (uint8_t)x;
-            }
-        }
+        osd_readout_and_search<real>(a, shot, weight, Tc, St, used, sprime, wscr, red_w, red_c, order, prow, np, nnp, &sh_best, &sh_found);
     }
 }
 

@@ -28,6 +28,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* tanh / log of the product-sum update: the portable, FMA-free implementations shared with the CUDA
+ * kernels (include/bposd_math.h) so that fp64 product-sum can be compared bit for bit, or the host libm
+ * (what ldpc itself calls; its last bits depend on the glibc build and CPU). */
+#include "../include/bposd_math.h"
+#define ORACLE_MATH_SHARED 0
+#define ORACLE_MATH_LIBM 1
+
 #define BP_PRODUCT_SUM 0
 #define BP_MINIMUM_SUM 1
 #define OSD_0 0
@@ -51,7 +58,15 @@ typedef struct {
     uint64_t *work;
     long stat_elim_wordxors;
     long total_elim_wordxors, total_osd; /* accumulated over decodes (algorithmic-op count of SURVEY.md 8d) */
+    int math_mode;                       /* ORACLE_MATH_SHARED (default) or ORACLE_MATH_LIBM */
 } oracle_t;
+
+static double o_tanh(const oracle_t *o, double x) { return o->math_mode == ORACLE_MATH_LIBM ? tanh(x) : bpm_tanh(x); }
+static double o_log(const oracle_t *o, double x) { return o->math_mode == ORACLE_MATH_LIBM ? log(x) : bpm_log(x); }
+void oracle_set_math(oracle_t *o, int mode) { o->math_mode = mode; }
+double oracle_math_tanh(double x) { return bpm_tanh(x); }
+double oracle_math_log(double x) { return bpm_log(x); }
+double oracle_math_expm1(double x) { return bpm_expm1(x); }
 
 /* ------------------------------------------------------------------ helpers */
 
@@ -182,14 +197,14 @@ static void bp_decode(oracle_t *o, const uint8_t *synd) {
                 double t = 1.0;
                 for (int e = o->row_ptr[i]; e < o->row_ptr[i + 1]; e++) {
                     c2b[e] = t;
-                    t *= tanh(b2c[e] / 2);
+                    t *= o_tanh(o, b2c[e] / 2);
                 }
                 t = 1.0;
                 for (int e = o->row_ptr[i + 1] - 1; e >= o->row_ptr[i]; e--) {
                     c2b[e] *= t;
                     double sgn = synd[i] ? -1.0 : 1.0;
-                    c2b[e] = sgn * log((1 + c2b[e]) / (1 - c2b[e]));
-                    t *= tanh(b2c[e] / 2);
+                    c2b[e] = sgn * o_log(o, (1 + c2b[e]) / (1 - c2b[e]));
+                    t *= o_tanh(o, b2c[e] / 2);
                 }
             }
         } else {

@@ -22,8 +22,8 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "bposd_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "bposd_oracle.c"), os.path.join(_HERE, "..", "include", "bposd_math.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libbposd_oracle.so"])
     return _LIB_PATH
 
@@ -49,6 +49,10 @@ def lib():
         for name in ("llr", "bp_decoding", "osd0_decoding", "osdw_decoding"):
             f = getattr(L, "oracle_" + name)
             f.restype, f.argtypes = P, [P]
+        L.oracle_set_math.argtypes = [P, C.c_int]
+        for name in ("tanh", "log", "expm1"):
+            f = getattr(L, "oracle_math_" + name)
+            f.restype, f.argtypes = C.c_double, [C.c_double]
         L.oracle_philox.argtypes = [P, P, P]
         L.oracle_sample_errors.argtypes = [C.c_uint64, C.c_uint64, C.c_long, C.c_int, P, P, P, P, P]
         L.oracle_syndrome.argtypes = [P, P, C.c_long, P]
@@ -77,7 +81,9 @@ def csr_of(h):
 
 class OracleDecoder:
     def __init__(self, parity_check_matrix, error_rate=None, channel_probs=None, max_iter=0,
-                 bp_method="ms", ms_scaling_factor=1.0, osd_method="osd0", osd_order=0):
+                 bp_method="ms", ms_scaling_factor=1.0, osd_method="osd0", osd_order=0, math="shared"):
+        """math: "shared" = the portable tanh/log of include/bposd_math.h (the functions the CUDA kernels use, so
+        product-sum compares bit for bit), "libm" = the host libm, as ldpc itself calls (last bits machine dependent)."""
         h = csr_of(parity_check_matrix)
         self.m, self.n = h.shape
         cp = None
@@ -95,6 +101,9 @@ class OracleDecoder:
         om = _OSD[str(osd_method).lower()]
         self._h = lib().oracle_create(_ptr(self._ip), _ptr(self._ix), self.m, self.n, _ptr(cp),
                                       int(max_iter), bm, float(ms_scaling_factor), om, int(osd_order))
+        if math not in ("shared", "libm"):
+            raise ValueError("math must be 'shared' or 'libm'")
+        lib().oracle_set_math(self._h, 1 if math == "libm" else 0)
         self.rank = lib().oracle_rank(self._h)
         self.k = lib().oracle_k(self._h)
         if om != 0 and int(osd_order) > self.k:

@@ -18,10 +18,11 @@ ap.add_argument("--max-iter", type=int, default=0)
 ap.add_argument("--method", default="ms")
 ap.add_argument("--osd-variant", type=int, default=None)
 ap.add_argument("--llr", action="store_true")
+ap.add_argument("--alpha", type=float, default=0.0)
 a = ap.parse_args()
 code = codes.config_code(a.cfg, logicals=False) if a.cfg == 4 else codes.config_code(a.cfg)
 H = code.hz
-d = BpOsdDecoder(H, error_rate=a.p, max_iter=a.max_iter, bp_method=a.method, ms_scaling_factor=0, osd_method=a.osd,
+d = BpOsdDecoder(H, error_rate=a.p, max_iter=a.max_iter, bp_method=a.method, ms_scaling_factor=a.alpha, osd_method=a.osd,
                  osd_order=a.order, precision=a.prec)
 if a.kernel is not None or a.threads:
     d.set_tuning(bp_kernel=a.kernel, bp_threads=a.threads)

@@ -106,26 +106,20 @@ def test_thread_counts_do_not_change_results(torch_cuda, oracle_mod, cfg_codes, 
 
 
 def test_product_sum_lifted_product(torch_cuda, oracle_mod, cfg_codes):
-    """Config 4: product-sum BP + OSD-E 10.  tanh/log come from CUDA's libm, so LLRs carry a tolerance:
-    1e-9 relative for shots that stop within 20 iterations (error grows with the iteration count)."""
+    """Config 4: product-sum BP + OSD-E 10 at max_iter = n.  tanh / log are the portable FMA-free functions of
+    include/bposd_math.h on BOTH sides (the oracle's default `math="shared"`), so everything is compared exactly:
+    decodings, converge flags, iteration counts and every bit of the LLRs (NaN where the reference arithmetic itself
+    produces inf - inf)."""
     H = cfg_codes(4).hz
     kw = dict(max_iter=0, bp_method="ps", ms_scaling_factor=0, osd_method="osd_e", osd_order=10)
     _, syn = random_syndromes(H, 0.05, 300, seed=12345)
     ref = oracle_mod.OracleDecoder(H, error_rate=0.05, **kw).decode_batch(syn)
+    assert (ref["iter"] > 100).sum() >= 20  # long-running shots are part of the comparison
     for kernel in (0, 1):
         _, out = gpu_decode(torch_cuda, H, syn, kernel=kernel, error_rate=0.05, **kw)
-        same = (out["converge"] == ref["converge"].astype(bool)) & (out["iter"] == ref["iter"])
-        assert same.mean() > 0.97
-        assert ((out["bp"] == ref["bp"]).all(1) | ~same).mean() > 0.97
-        assert (out["osdw"] == ref["osdw"]).all(1).mean() > 0.95
-        quick = same & (ref["iter"] <= 20)
-        assert quick.sum() > 50
-        a, b = out["llr"][quick], ref["llr"][quick]
-        fin = np.isfinite(b)  # product-sum is unclipped upstream: tanh saturates to +-1 and the LLR to +-inf
-        assert (a[~fin] == b[~fin]).all()
-        assert (np.abs(a[fin] - b[fin]) / np.abs(b[fin])).max() < 1e-9
-        Hd = H.toarray()
-        assert ((out["osdw"] @ Hd.T % 2) == syn).all()
+        assert_exact(out, ref, llr_exact=False)
+        # NaN payloads are the one thing that legitimately differs (x86 and sm_100a generate different quiet NaNs)
+        assert np.array_equal(out["llr"], ref["llr"], equal_nan=True), "log_prob_ratios not bit-exact"
 
 
 def test_nonuniform_and_zero_probabilities(torch_cuda, oracle_mod, cfg_codes):

@@ -75,7 +75,8 @@ def test_oracle_vs_second_restatement(oracle_mod, cfg_codes, case):
     H = cfg_codes(case["cfg"]).hz
     n = H.shape[1]
     kw = case["kw"]
-    o = oracle_mod.OracleDecoder(H, error_rate=case["p"], **kw)
+    # the second restatement calls the host libm for tanh/log, so the C oracle is put in the same mode for product-sum
+    o = oracle_mod.OracleDecoder(H, error_rate=case["p"], math="libm" if kw["bp_method"] == "ps" else "shared", **kw)
     s = SlowDecoder(H, [case["p"]] * n, kw["max_iter"], kw["bp_method"], kw["ms_scaling_factor"], kw["osd_method"], kw["osd_order"])
     _, syn = random_syndromes(H, case["p"], case["shots"], seed=3)
     for b in range(case["shots"]):
@@ -152,3 +153,62 @@ def test_zero_probability_entries_do_not_nan(oracle_mod, cfg_codes):
         _, syn = random_syndromes(H, 0.05, 30, seed=4)
         out = o.decode_batch(syn)
     assert not np.isnan(out["llr"]).any()
+
+
+def _ulps(got, want):
+    """|got - want| in units of the last place of `want` (finite, non-zero values)."""
+    import math
+    return abs(got - want) / math.ulp(want)
+
+
+def test_shared_math_is_pinned_to_glibc(oracle_mod):
+    """include/bposd_math.h (compiled into the oracle AND the CUDA kernels) against the host libm: the portable tanh / log
+    stay within 3 / 1 ulp of glibc's on the ranges product-sum BP visits (both are fdlibm-class algorithms with a
+    < 2.5 ulp / < 1 ulp error bound, measured against long double: 2.17 vs 2.15 and 0.89 vs 0.52 ulp), and agree on
+    every special value."""
+    import math
+    L = oracle_mod.lib()
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.uniform(-25, 25, 40000), rng.uniform(-1, 1, 40000), rng.uniform(-1e-3, 1e-3, 5000),
+                         np.ldexp(rng.uniform(-1, 1, 5000), rng.integers(-70, 5, 5000))])
+    worst_t = worst_l = 0.0
+    for x in xs:
+        x = float(x)
+        t, tw = L.oracle_math_tanh(x), math.tanh(x)
+        if tw != 0.0:
+            worst_t = max(worst_t, _ulps(t, tw))
+        else:
+            assert t == tw
+        if abs(tw) < 1.0:
+            y = (1 + tw) / (1 - tw)        # the argument product-sum feeds to log (row a5)
+            worst_l = max(worst_l, _ulps(L.oracle_math_log(y), math.log(y)) if math.log(y) != 0 else 0.0)
+    for y in np.concatenate([rng.uniform(1e-6, 1e6, 20000), 1 + rng.uniform(-1e-3, 1e-3, 5000),
+                             np.ldexp(rng.uniform(0.5, 1, 5000), rng.integers(-1000, 1000, 5000))]):
+        y = float(y)
+        lw = math.log(y)
+        if lw != 0.0:
+            worst_l = max(worst_l, _ulps(L.oracle_math_log(y), lw))
+    assert worst_t <= 3.0, worst_t
+    assert worst_l <= 1.0, worst_l
+    inf, nan = float("inf"), float("nan")
+    assert L.oracle_math_tanh(inf) == 1.0 and L.oracle_math_tanh(-inf) == -1.0 and math.isnan(L.oracle_math_tanh(nan))
+    assert L.oracle_math_tanh(40.0) == 1.0 and L.oracle_math_tanh(-40.0) == -1.0 and L.oracle_math_tanh(1e-300) == 1e-300
+    assert math.copysign(1.0, L.oracle_math_tanh(-0.0)) == -1.0 and L.oracle_math_tanh(0.0) == 0.0
+    assert L.oracle_math_log(inf) == inf and L.oracle_math_log(0.0) == -inf and L.oracle_math_log(1.0) == 0.0
+    assert math.isnan(L.oracle_math_log(-1.0)) and math.isnan(L.oracle_math_log(nan))
+    assert abs(L.oracle_math_log(5e-324) - math.log(5e-324)) < 1e-12
+
+
+def test_product_sum_shared_vs_libm_modes(oracle_mod, cfg_codes):
+    """The two arithmetic modes of the oracle on config 4 (product-sum + OSD-E 10): decodings agree on every shot that
+    stops early and on nearly all others (a last-bit difference needs hundreds of iterations to reach a hard decision)."""
+    H = cfg_codes(4).hz
+    kw = dict(max_iter=60, bp_method="ps", ms_scaling_factor=0, osd_method="osd_e", osd_order=10)
+    _, syn = random_syndromes(H, 0.05, 150, seed=21)
+    a = oracle_mod.OracleDecoder(H, error_rate=0.05, math="shared", **kw).decode_batch(syn)
+    b = oracle_mod.OracleDecoder(H, error_rate=0.05, math="libm", **kw).decode_batch(syn)
+    quick = b["iter"] <= 20
+    assert quick.sum() > 50
+    assert (a["iter"][quick] == b["iter"][quick]).all() and (a["bp"][quick] == b["bp"][quick]).all()
+    assert np.allclose(a["llr"][quick], b["llr"][quick], rtol=1e-9, atol=0)
+    assert (a["osdw"] == b["osdw"]).all(1).mean() >= 0.95
