@@ -74,7 +74,7 @@ struct bposd_handle {
     bool osd_large = false;
     int osd_variant = 0; // 0 auto, 1 T-matrix shared-memory kernel, 2 HBM-resident kernel, 3 T-matrix register kernel
     bool osd_reg = false; // the register kernel is selected (m <= 1024)
-    int osdr_W = 0, osdr_threads = 0, osdr_smem = 0;
+    int osdr_W = 0, osdr_KD = 4, osdr_threads = 0, osdr_smem = 0;
     int osdl_smem = 0, osdl_grid = 0, osdl_npanels = 0;
     long long osdl_ws_cap = 16ll << 30;
     uint32_t *d_osdl_mask = nullptr;
@@ -310,38 +310,36 @@ static int plan_geometry_t(bposd_handle *h) {
         h->osdl_grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, h->osdl_ws_cap / (long long)std::max<size_t>(per_cta, 1)));
         h->osd_supported = true;
     }
-    // register kernel (default whenever it applies): T in registers, two barriers per 16 sorted columns
+    // register kernel (default whenever it applies): T in registers, one barrier per 16 sorted columns
     {
         const int Sw = (m + 31) / 32;
         h->osdr_W = Sw <= 4 ? 4 : (Sw <= 8 ? 8 : (Sw <= 16 ? 16 : 32));
-        h->osdr_threads = std::max(64, ((m + kOsdRegCPT - 1) / kOsdRegCPT + 31) / 32 * 32);
-        size_t rs_ = 0;
-        switch (h->osdr_W) {
-            case 4: rs_ = osd_reg_smem_bytes<4>(m, n, h->osdr_threads, std::max(h->max_col_deg, 1)); break;
-            case 8: rs_ = osd_reg_smem_bytes<8>(m, n, h->osdr_threads, std::max(h->max_col_deg, 1)); break;
-            case 16: rs_ = osd_reg_smem_bytes<16>(m, n, h->osdr_threads, std::max(h->max_col_deg, 1)); break;
-            default: rs_ = osd_reg_smem_bytes<32>(m, n, h->osdr_threads, std::max(h->max_col_deg, 1)); break;
-        }
-        h->osdr_smem = (int)rs_;
-        const bool reg_ok = m >= 1 && m <= 1024 && n < 65535 && h->max_col_deg <= 64 && rs_ <= (size_t)h->smem_optin;
+        h->osdr_KD = h->max_col_deg <= 4 ? 4 : 8;
+        h->osdr_threads = osd_reg_threads(m);
+        const size_t rs_ = osd_reg_layout(m, n, E, h->osdr_W, h->osdr_KD, kOsdRegG, h->osdr_threads, osd_reg_np2(n)).total;
+        h->osdr_smem = (int)std::min<size_t>(rs_, (size_t)1 << 30);
+        const bool reg_ok = m >= 1 && m <= 1024 && n < 65535 && E < 65536 && h->max_col_deg <= 8 && rs_ <= (size_t)h->smem_optin;
         if (h->osd_variant == 3 && !reg_ok)
-            return fail(h, BPOSD_EUNSUP, "the register OSD kernel needs m <= 1024, n < 65535 and column degrees up to 64");
+            return fail(h, BPOSD_EUNSUP, "the register OSD kernel needs m <= 1024, n < 65535, fewer than 65536 edges and column degrees up to 8");
         h->osd_reg = reg_ok && (h->osd_variant == 3 || h->osd_variant == 0);
         if (h->osd_reg) {
             h->osd_large = false;
             h->osd_supported = true;
             int occ4 = 0;
-#define BPOSD_OSDR_SETUP(Wv)                                                                                                         \
-    do {                                                                                                                             \
-        CU_TRY(h, cudaFuncSetAttribute(osd_reg_kernel<real, Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->osdr_smem));         \
-        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, osd_reg_kernel<real, Wv>, h->osdr_threads, h->osdr_smem));      \
+#define BPOSD_OSDR_SETUP(Wv, KDv)                                                                                                         \
+    do {                                                                                                                                  \
+        CU_TRY(h, cudaFuncSetAttribute(osd_reg_kernel<real, Wv, KDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->osdr_smem));         \
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, osd_reg_kernel<real, Wv, KDv>, h->osdr_threads, h->osdr_smem));      \
     } while (0)
-            switch (h->osdr_W) {
-                case 4: BPOSD_OSDR_SETUP(4); break;
-                case 8: BPOSD_OSDR_SETUP(8); break;
-                case 16: BPOSD_OSDR_SETUP(16); break;
-                default: BPOSD_OSDR_SETUP(32); break;
-            }
+#define BPOSD_OSDR_W(KDv)                                                                        \
+    switch (h->osdr_W) {                                                                         \
+        case 4: BPOSD_OSDR_SETUP(4, KDv); break;                                                 \
+        case 8: BPOSD_OSDR_SETUP(8, KDv); break;                                                 \
+        case 16: BPOSD_OSDR_SETUP(16, KDv); break;                                               \
+        default: BPOSD_OSDR_SETUP(32, KDv); break;                                               \
+    }
+            if (h->osdr_KD == 4) { BPOSD_OSDR_W(4) } else { BPOSD_OSDR_W(8) }
+#undef BPOSD_OSDR_W
 #undef BPOSD_OSDR_SETUP
             h->osd_ctas_per_sm = std::max(1, occ4);
         }
@@ -610,7 +608,7 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
         OsdArgs<real> o;
         o.g = g;
         o.S = h->osd_S; o.St = h->osd_St;
-        o.maxrank = h->rank; o.maxdeg = std::max(h->max_col_deg, 1);
+        o.maxrank = h->rank; o.maxdeg = std::max(h->max_col_deg, 1); o.np2 = osd_reg_np2(n);
         o.method = h->osd_method; o.order = h->osd_order;
         o.uniform = (per_shot_priors || d_weights) ? 0 : h->uniform;
         o.weight = d_weights ? d_weights : h->d_weight;
@@ -624,12 +622,17 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
         o.stat = d_stat;
         const int ogrid = (int)std::min<long long>(Bc, (long long)h->osd_ctas_per_sm * h->sm_count);
         if (h->osd_reg) {
-            switch (h->osdr_W) {
-                case 4: osd_reg_kernel<real, 4><<<ogrid, h->osdr_threads, h->osdr_smem, st>>>(o); break;
-                case 8: osd_reg_kernel<real, 8><<<ogrid, h->osdr_threads, h->osdr_smem, st>>>(o); break;
-                case 16: osd_reg_kernel<real, 16><<<ogrid, h->osdr_threads, h->osdr_smem, st>>>(o); break;
-                default: osd_reg_kernel<real, 32><<<ogrid, h->osdr_threads, h->osdr_smem, st>>>(o); break;
-            }
+#define BPOSD_OSDR_LAUNCH(Wv, KDv) osd_reg_kernel<real, Wv, KDv><<<ogrid, h->osdr_threads, h->osdr_smem, st>>>(o)
+#define BPOSD_OSDR_W(KDv)                                                                        \
+    switch (h->osdr_W) {                                                                         \
+        case 4: BPOSD_OSDR_LAUNCH(4, KDv); break;                                                \
+        case 8: BPOSD_OSDR_LAUNCH(8, KDv); break;                                                \
+        case 16: BPOSD_OSDR_LAUNCH(16, KDv); break;                                              \
+        default: BPOSD_OSDR_LAUNCH(32, KDv); break;                                              \
+    }
+            if (h->osdr_KD == 4) { BPOSD_OSDR_W(4) } else { BPOSD_OSDR_W(8) }
+#undef BPOSD_OSDR_W
+#undef BPOSD_OSDR_LAUNCH
         } else
         osd_kernel<real><<<ogrid, h->osd_threads, h->osd_smem, st>>>(o);
         CU_TRY(h, cudaGetLastError());

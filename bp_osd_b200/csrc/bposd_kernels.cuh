@@ -278,7 +278,8 @@ struct OsdArgs {
     uint8_t *osd0, *osdw;
     unsigned long long *stat; // [2] osd invocations
     int maxrank;  // rank(H): no pivot can follow the maxrank-th (osd_reg_kernel stops its scan there)
-    int maxdeg;   // largest column degree of H (osd_reg_kernel: capacity of a candidate's row list)
+    int maxdeg;   // largest column degree of H
+    int np2;      // n rounded up to a power of two (osd_reg_kernel: size of its bitonic sort)
 };
 
 __device__ __forceinline__ unsigned long long sort_key(double x) {
@@ -294,11 +295,26 @@ __device__ __forceinline__ unsigned long long sort_key(float x) {
 
 #define OSD_NONE 0xFFFFu
 
+// Column view of H for the OSD kernels: the CSC arrays in global memory, or a 16-bit copy of them in shared memory
+// (osd_reg_kernel stages one per CTA: the candidate search walks a column per candidate, and two dependent L2 round
+// trips per candidate were most of its time).
+struct CscView {
+    const int *ptr32, *row32;
+    const uint16_t *ptr16, *row16;
+    __device__ __forceinline__ int beg(int c) const { return ptr16 ? (int)ptr16[c] : ptr32[c]; }
+    __device__ __forceinline__ int end(int c) const { return ptr16 ? (int)ptr16[c + 1] : ptr32[c + 1]; }
+    __device__ __forceinline__ int row(int q) const { return row16 ? (int)row16[q] : row32[q]; }
+};
+__device__ __forceinline__ CscView csc_global(const GraphDev &g) { return CscView{g.col_ptr, g.row_idx, nullptr, nullptr}; }
+
 // XOR of the T columns selected by H column c, word w
-__device__ __forceinline__ uint32_t reduced_col_word(const GraphDev &g, const uint32_t *Tc, int St, int c, int w) {
+__device__ __forceinline__ uint32_t reduced_col_word(const CscView &cv, const uint32_t *Tc, int St, int c, int w) {
     uint32_t v = 0;
-    for (int q = g.col_ptr[c]; q < g.col_ptr[c + 1]; q++) v ^= Tc[g.row_idx[q] * St + w];
+    for (int q = cv.beg(c), qe = cv.end(c); q < qe; q++) v ^= Tc[cv.row(q) * St + w];
     return v;
+}
+__device__ __forceinline__ uint32_t reduced_col_word(const GraphDev &g, const uint32_t *Tc, int St, int c, int w) {
+    return reduced_col_word(csc_global(g), Tc, St, c, w);
 }
 
 // a11 read-out + a12-a14 candidate search + result write of one failed shot, shared by the OSD kernels.  On entry the
@@ -309,9 +325,8 @@ template <typename real>
 __device__ __forceinline__ void osd_readout_and_search(const OsdArgs<real> &a, long long shot, const double *weight, const uint32_t *Tc,
                                                        int St, const uint32_t *used, const uint32_t *sprime, uint32_t *wscr, double *red_w,
                                                        int *red_c, const uint16_t *order, const uint16_t *prow, const uint16_t *np, int nnp,
-                                                       int *sh_best, int *sh_found) {
-    const GraphDev &g = a.g;
-    const int n = g.n, S = a.S;
+                                                       int *sh_best, int *sh_found, const CscView g) {
+    const int n = a.g.n, S = a.S;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const long long base = shot * (long long)n;
     for (int j = tid; j < n; j += T) {
@@ -576,7 +591,7 @@ __global__ void __launch_bounds__(1024, 1) osd_kernel(OsdArgs<real> a) {
             }
             __syncthreads();
         }
-        osd_readout_and_search<real>(a, shot, weight, Tc, St, used, sprime, wscr, red_w, red_c, order, prow, np, nnp, &sh_best, &sh_found);
+        osd_readout_and_search<real>(a, shot, weight, Tc, St, used, sprime, wscr, red_w, red_c, order, prow, np, nnp, &sh_best, &sh_found, csc_global(g));
     }
 }
 
