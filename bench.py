@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- shots/sec of BP+OSD-CS(7) on the [[1922,50,16]] hypergraph-product code (BASELINE.json).
+"""bench.py -- shots/sec of BP+OSD on the codes of BASELINE.json; default: BP+OSD-CS(7) on the [[1922,50,16]] HGP code.
 
     python bench.py --gpus N --steps K --warmup W            # this framework, N ranks (torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle restatement of ldpc
-                                                             # (ldpc itself is not installable offline)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: ldpc's BpOsdDecoder when it can be imported,
+                                                             # else the oracle restatement of it (ldpc is not installable offline)
+    python bench.py --config 3 --ms-scaling-factor 0.625     # the harness-default scaling: half the shots reach OSD
+    python bench.py --config {1,2,4,5}                       # the other BASELINE configs (see CONFIGS below)
 
-One step = one pass of the decode hot path over one batch of synthetic syndromes per GPU
-(weak scaling: the per-GPU batch is fixed; at 8 GPUs the job is BASELINE's 10M shots).  Syndromes
-come from the device Philox sampler with global shot indices, so the union over ranks is the same
-shot set for any N.  `value` is timed with the syndromes resident in HBM; `e2e` goes through the
-public `decode_batch(numpy)` call with pinned host buffers, H2D and D2H inside the timed region.
+One step = one pass of the decode hot path over one batch of synthetic syndromes per GPU (weak scaling: the per-GPU
+batch is fixed; at 8 GPUs the default job is BASELINE's 10M shots).  Syndromes come from the device Philox sampler with
+global shot indices, so the union over ranks is the same shot set for any N.
+`value`  : syndromes resident in HBM, every output written to HBM (CUDA events, max over ranks).
+`e2e`    : the public `decode_batch(host array, packed=True)` call on pre-staged pinned host batches -- H2D of the
+           bit-packed syndromes and D2H of the bit-packed decodings, converge flags and iteration counts inside the
+           timed region, nothing else.
+`roofline`: the BP kernel against the MEASURED shared-memory bandwidth (its messages live in shared memory); the
+           SURVEY 8(d) HBM figure and the measured DRAM traffic are kept beside it.
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -27,13 +33,40 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(cfg=3, p=0.05, max_iter=0, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=7)
 SEED = 0xB905D
+# BASELINE.json configs[cfg-1]; decoder arguments per SURVEY.md 8(d) "Synthetic inputs"
+CONFIGS = {
+    1: dict(name="d=5 surface code hgp(rep_code(5)) hz [[41,1,5]]", p=0.05, max_iter=0, bp_method="ms", ms_scaling_factor=0.0,
+            osd_method="osd_cs", osd_order=7, shots=1_000_000, cpu_shots=20000),
+    2: dict(name="[[400,16,6]] HGP hz", p=0.05, max_iter=0, bp_method="ms", ms_scaling_factor=0.0, osd_method="osd_cs",
+            osd_order=7, shots=1_000_000, cpu_shots=4000),
+    3: dict(name="[[1922,50,16]] HGP hz", p=0.05, max_iter=0, bp_method="ms", ms_scaling_factor=0.0, osd_method="osd_cs",
+            osd_order=7, shots=1_250_000, cpu_shots=1000),
+    4: dict(name="[[882,24]] lifted-product hz", p=0.05, max_iter=0, bp_method="ps", ms_scaling_factor=0.0, osd_method="osd_e",
+            osd_order=10, shots=200_000, cpu_shots=300),
+    5: dict(name="40k-qubit HGP hz (m=19200, n=40000)", p=0.02, max_iter=0, bp_method="ms", ms_scaling_factor=0.0,
+            osd_method="osd0", osd_order=0, shots=4096, cpu_shots=4),
+}
+METRIC = "shots/sec BP+OSD-CS(7) on [[1922,50,16]] HGP"
 
 
-def workload_name(shots, prec):
-    return (f"[[1922,50,16]] HGP hz sector (m=961,n=1922,E=5766), bit-flip p=0.05, BP min-sum alpha=1-2^-it "
-            f"max_iter=n + OSD-CS order 7, {shots} shots/GPU/step, fp{prec}")
+def decoder_kwargs(c):
+    return dict(max_iter=c["max_iter"], bp_method=c["bp_method"], ms_scaling_factor=c["ms_scaling_factor"],
+                osd_method=c["osd_method"], osd_order=c["osd_order"])
+
+
+def workload_name(cfg, c, m, n, E, prec):
+    """The same string in both arms (the driver compares `config` across them): no batch sizes in here."""
+    alpha = "alpha=1-2^-it" if c["ms_scaling_factor"] == 0 else f"alpha={c['ms_scaling_factor']:g}"
+    bp = f"BP min-sum {alpha}" if c["bp_method"] == "ms" else "BP product-sum"
+    osd = {"osd_cs": f"OSD-CS order {c['osd_order']}", "osd_e": f"OSD-E order {c['osd_order']}", "osd0": "OSD-0"}[c["osd_method"]]
+    return (f"config {cfg}: {c['name']} (m={m},n={n},E={E}), bit-flip p={c['p']:g}, {bp} max_iter=n + {osd}, fp{prec}")
+
+
+def metric_name(cfg, c):
+    if cfg == 3 and c["osd_method"] == "osd_cs" and c["osd_order"] == 7:
+        return METRIC
+    return f"shots/sec BP+{c['osd_method']}({c['osd_order']}) on BASELINE config {cfg}"
 
 
 def algorithmic_bp_bytes(n, m, E, iterations, shots, w):
@@ -84,7 +117,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def measured_peak():
+def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -93,19 +126,40 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle on all host cores
+# CPU arm: ldpc.BpOsdDecoder when importable (baseline/_ref or site-packages), else the oracle, on all host cores
 # ------------------------------------------------------------------------------------------------
 _W = {}
 
 
-def _cpu_init():
+def try_import_ldpc():
+    """The reference's decoder is `from ldpc import BpOsdDecoder` (/root/reference/src/bposd/css_decode_sim.py:6)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        import ldpc  # noqa: F401
+        from ldpc import BpOsdDecoder  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def _cpu_init(cfg, c, use_ldpc):
     from bp_osd_b200 import codes
-    from oracle.oracle import OracleDecoder
-    H = codes.config_code(CFG["cfg"], logicals=False).hz if CFG["cfg"] != 3 else codes.config_code(3).hz
-    _W["dec"] = OracleDecoder(H, error_rate=CFG["p"], max_iter=CFG["max_iter"], bp_method=CFG["bp_method"],
-                              ms_scaling_factor=CFG["ms_scaling_factor"], osd_method=CFG["osd_method"],
-                              osd_order=CFG["osd_order"])
-    _W["n"] = H.shape[1]
+    H = codes.config_code(cfg, logicals=False).hz
+    kw = decoder_kwargs(c)
+    if use_ldpc:
+        from ldpc import BpOsdDecoder as Ref
+        # the constructor call of the reference harness, css_decode_sim.py:444-452
+        _W["dec"] = Ref(H, channel_probs=np.full(H.shape[1], c["p"]), max_iter=kw["max_iter"] or H.shape[1],
+                        bp_method=kw["bp_method"], ms_scaling_factor=float(kw["ms_scaling_factor"]), osd_method=kw["osd_method"],
+                        osd_order=kw["osd_order"])
+    else:
+        from oracle.oracle import OracleDecoder
+        _W["dec"] = OracleDecoder(H, error_rate=c["p"], math="libm", **kw)  # libm: the arithmetic ldpc itself runs
+    from oracle.oracle import OracleDecoder as _O
+    _W["syn"] = _O(H, error_rate=c["p"], osd_method="osd0")
+    _W["n"], _W["p"], _W["ldpc"] = H.shape[1], c["p"], use_ldpc
 
 
 def _cpu_work(args):
@@ -113,10 +167,15 @@ def _cpu_work(args):
     shot0, shots = args
     dec = _W["dec"]
     z = np.zeros(_W["n"])
-    ex, _ = sample_errors(SEED, shot0, shots, z, np.full(_W["n"], CFG["p"]), z)
-    s = dec.syndrome(ex)
-    t = time.perf_counter()
+    ex, _ = sample_errors(SEED, shot0, shots, z, np.full(_W["n"], _W["p"]), z)
+    s = _W["syn"].syndrome(ex)
+    if _W["ldpc"]:
+        t = time.perf_counter()
+        for b in range(shots):
+            dec.decode(s[b])          # the per-shot call of css_decode_sim.py:174
+        return shots, time.perf_counter() - t, 0, 0, 0
     x0, n0 = dec.totals
+    t = time.perf_counter()          # sampling and syndromes above are not part of the decode path that is timed
     out = dec.decode_batch(s, want_llr=False)
     dt = time.perf_counter() - t
     x1, n1 = dec.totals
@@ -124,50 +183,57 @@ def _cpu_work(args):
 
 
 class CpuArm:
-    def __init__(self):
+    def __init__(self, cfg, c):
         import multiprocessing as mp
+        from functools import partial
         self.cores = len(os.sched_getaffinity(0))
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init)
+        self.ldpc = try_import_ldpc()
+        self.kind = "ldpc" if self.ldpc else "port"
+        self.what = ("ldpc.BpOsdDecoder.decode per shot (the reference's own decoder)" if self.ldpc else
+                     "oracle/bposd_oracle.c -O3 (restatement of ldpc v2; ldpc is not installable offline)")
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=partial(_cpu_init, cfg, c, self.ldpc))
 
     def step(self, shot0, shots_per_core):
-        jobs = [(shot0 + c * shots_per_core, shots_per_core) for c in range(self.cores)]
-        t = time.perf_counter()
+        jobs = [(shot0 + k * shots_per_core, shots_per_core) for k in range(self.cores)]
         res = self.pool.map(_cpu_work, jobs)
-        wall = time.perf_counter() - t
         self.elim_wordxors = sum(r[3] for r in res)   # algorithmic elimination ops counted by the oracle
         self.osd_shots = sum(r[4] for r in res)
-        return sum(r[0] for r in res), wall
+        # all cores decode concurrently: the step lasts as long as its slowest worker's decode loop
+        return sum(r[0] for r in res), max(r[1] for r in res)
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
-def run_reference(args):
+def run_reference(args, cfg, c):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from bp_osd_b200 import codes
     from oracle import oracle as _o
     _o.build()
-    arm = CpuArm()
-    per_core = args.cpu_shots_per_core
+    H = codes.config_code(cfg, logicals=False).hz
+    m, n = H.shape
+    arm = CpuArm(cfg, c)
+    per_core = args.cpu_shots_per_core or c["cpu_shots"]
     shot0 = 0
     for _ in range(args.warmup):
-        n, _w = arm.step(shot0, max(per_core // 4, 50)); shot0 += n
+        k, _w = arm.step(shot0, max(per_core // 4, 1)); shot0 += k
     tot, wall = 0, 0.0
     for _ in range(args.steps):
-        n, w = arm.step(shot0, per_core); shot0 += n
-        tot += n; wall += w
+        k, w = arm.step(shot0, per_core); shot0 += k
+        tot += k; wall += w
     arm.close()
     v = tot / wall
-    sample = f"{per_core} shots/core/step x {arm.cores} cores x {args.steps} steps of the same workload (Philox seed {SEED:#x})"
+    sample = f"{per_core} shots/core/step x {arm.cores} cores x {args.steps} steps of the same workload (Philox seed {SEED:#x}); {arm.what}"
     line = {
-        "impl": "reference", "metric": "shots/sec BP+OSD-CS(7) on [[1922,50,16]] HGP", "value": v, "unit": "shots/s",
+        "impl": "reference", "metric": metric_name(cfg, c), "value": v, "unit": "shots/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(per_core * arm.cores, 64),
-                   "note": "CPU restatement of ldpc v2 bposd_decoder (oracle/bposd_oracle.c); ldpc is not installable offline"},
-        "cpu_baseline": {"value": v, "unit": "shots/s", "cores": arm.cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(cfg, c, m, n, H.nnz, 64)},
+        "shots_per_step": per_core * arm.cores,
+        "cpu_baseline": {"value": v, "unit": "shots/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": v, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -177,7 +243,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_gpu(args):
+def run_gpu(args, cfg, c):
     import torch
     import torch.distributed as dist
     from bp_osd_b200 import codes, BpOsdDecoder
@@ -199,29 +265,31 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    code = codes.config_code(CFG["cfg"])
+    code = codes.config_code(cfg, logicals=cfg != 5)
     H = code.hz
     m, n = H.shape
     E = H.nnz
     prec = args.precision
     w = prec // 8
-    dec = BpOsdDecoder(H, error_rate=CFG["p"], max_iter=CFG["max_iter"], bp_method=CFG["bp_method"],
-                       ms_scaling_factor=CFG["ms_scaling_factor"], osd_method=CFG["osd_method"],
-                       osd_order=CFG["osd_order"], precision=prec, device=local)
+    dec = BpOsdDecoder(H, error_rate=c["p"], precision=prec, device=local, **decoder_kwargs(c))
     if args.bp_kernel is not None or args.bp_threads:
         dec.set_tuning(bp_kernel=args.bp_kernel, bp_threads=args.bp_threads)
-    dec.set_error_channel(px=CFG["p"])
-    dec.set_logicals(code.lz)
+    if args.osd_variant is not None:
+        dec.set_osd_variant(args.osd_variant)
+    dec.set_error_channel(px=c["p"])
+    have_logicals = getattr(code, "lz", None) is not None and cfg != 5
+    if have_logicals:
+        dec.set_logicals(code.lz)
     info = dec.info()
-    S = args.shots_per_gpu
+    S = args.shots_per_gpu or c["shots"]
     total_steps = args.warmup + args.steps
 
     # inputs: one fresh batch of syndromes per step, sampled on the device BEFORE the timed region and
-    # kept resident in HBM; each batch (S x 961 B, 1.2 GB at the default S) is larger than the 126 MB L2.
+    # kept resident in HBM; each batch (S x m bytes, 1.2 GB at the default) is larger than the 126 MB L2.
     syn_batches, err_last = [], None
     for step in range(total_steps):
         shot0 = (step * world + rank) * S
-        want_err = step == total_steps - 1
+        want_err = step == total_steps - 1 and have_logicals
         e_, s_ = dec.sample_syndromes(SEED, shot0, S, sector=0, return_errors=want_err)
         syn_batches.append(s_)
         if want_err:
@@ -253,10 +321,11 @@ def run_gpu(args):
             iters += st["bp_iterations"]; conv += st["bp_converged"]; osd_inv += st["osd_invocations"]
             launches += st["launches"]
     # the path's single collective: the logical-failure counters of the last step
-    fail = dec.logical_check(err_last, res.osdw_decoding)
     counters[0] = S
-    counters[1] = int(fail.sum())
-    launches += 1
+    if have_logicals:
+        fail = dec.logical_check(err_last, res.osdw_decoding)
+        counters[1] = int(fail.sum())
+        launches += 1
     if world > 1:
         dist.all_reduce(counters, op=dist.ReduceOp.SUM)
     ev1.record()
@@ -277,50 +346,61 @@ def run_gpu(args):
     torch.cuda.empty_cache()
 
     # ---- roofline of the dominant kernel (BP), from CUDA events on the launching stream ----
-    peak, peak_src = measured_peak()
+    # Bound: shared-memory bandwidth.  Every edge message is read and written once per sweep, 4*E*w bytes per
+    # shot-iteration, and the messages never leave shared memory (or the cluster's distributed shared memory, kernel 3);
+    # the peak is measured in this run (conflict-free 16-byte LDS + STS, the kernel's own access mix).
+    smem_peak = dec.smem_peak() / 1e9
+    smem_bytes = iters * 4 * E * w
+    achieved = smem_bytes / (ms_bp * 1e-3) / 1e9 if ms_bp > 0 else None
+    hbm_peak, hbm_src = measured_hbm_peak()
     alg_bytes_rank = algorithmic_bp_bytes(n, m, E, iters, S * args.steps, w)
-    achieved = alg_bytes_rank / (ms_bp * 1e-3) / 1e9 if ms_bp > 0 else None
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             tj = json.load(f)
-        per_shot = tj.get(f"bp_fp{prec}_dram_bytes_per_shot")
+        per_shot = tj.get(f"bp_fp{prec}_dram_bytes_per_shot") if cfg == 3 else None
         traffic = per_shot * S if per_shot else None  # ncu --set full capture, scaled to this launch's shots
     except Exception:
         pass
+    hbm_ach = alg_bytes_rank / (ms_bp * 1e-3) / 1e9 if ms_bp > 0 else None
     roofline = {
-        "bound": "hbm", "kernel": f"bp kernel variant {info['bp_kernel']} (fp{prec})", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": alg_bytes_rank / max(args.steps, 1),
-        "note": "algorithmic bytes = it*(4E+2n)*w + in/out per SURVEY 8(d); messages are kept in shared memory, so "
-                "frac can exceed 1: HBM is not the binding resource, shared-memory bandwidth is (see DESIGN.md)",
-        "smem": {"bound": "shared-memory pipe", "achieved": (iters * 4 * E * w) / (ms_bp * 1e-3) / 1e9 if ms_bp > 0 else None,
-                 "peak": info["sm_count"] * 128 * (clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9, "unit": "GB/s",
-                 "note": "4*E*w bytes per shot-iteration (each message read and written once per sweep) against "
-                         "SMs x 128 B/clk x max SM clock"},
+        "bound": "smem", "kernel": f"bp kernel variant {info['bp_kernel']} (fp{prec})", "achieved": achieved, "peak": smem_peak,
+        "unit": "GB/s", "frac": (achieved / smem_peak) if achieved else None, "traffic": traffic,
+        "peak_source": "measured in this run: bposd_smem_peak (16-byte LDS+STS, conflict free, all SMs)",
+        "peak_theoretical": info["sm_count"] * 128 * (clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9,
+        "algorithmic_bytes_per_launch": smem_bytes / max(args.steps, 1),
+        "note": "achieved = 4*E*w bytes per shot-iteration (each message read and written once per sweep) / CUDA-event time of "
+                "the BP launches; traffic = measured DRAM bytes per launch (ncu), i.e. only inputs and results touch HBM",
+        "hbm": {"bound": "hbm (SURVEY 8d formula; not the binding resource)", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (hbm_ach / hbm_peak) if hbm_ach else None, "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": alg_bytes_rank / max(args.steps, 1),
+                "note": "it*(4E+2n)*w + in/out bytes per SURVEY 8(d) against the measured copy bandwidth; above 1 because the "
+                        "messages are staged in shared memory"},
         "bp_ms_per_step": ms_bp / args.steps, "osd_ms_per_step": ms_osd / args.steps,
         "mean_iterations": iters / (S * args.steps), "bp_shot_iterations_per_s": iters / (ms_bp * 1e-3) if ms_bp else None,
     }
 
-    if roofline["smem"]["achieved"]:
-        roofline["smem"]["frac"] = roofline["smem"]["achieved"] / roofline["smem"]["peak"]
-
-    # ---- end to end through the public API with pinned host buffers ----
-    Se = min(S, args.e2e_shots_per_gpu)
-    h_syn = torch.empty((Se, m), dtype=torch.uint8, pin_memory=True)
-    h_out = {"osdw": torch.empty((Se, n), dtype=torch.uint8, pin_memory=True).numpy(),
+    # ---- end to end through the public API: pre-staged pinned host batches, bit-packed both ways ----
+    Se = min(S, args.e2e_shots_per_gpu or S)
+    mb, nb = (m + 7) // 8, (n + 7) // 8
+    nstage = min(total_steps, 3)
+    h_syn = []
+    for k in range(nstage):   # staged BEFORE the timed region; the timed loop rotates over them
+        _, syn = dec.sample_syndromes(SEED, ((total_steps + k) * world + rank) * Se, Se, sector=0, return_errors=False, packed=True)
+        hs = torch.empty((Se, mb), dtype=torch.uint8, pin_memory=True)
+        hs.copy_(syn)
+        h_syn.append(hs.numpy())
+        del syn
+    torch.cuda.synchronize()
+    h_out = {"osdw": torch.empty((Se, nb), dtype=torch.uint8, pin_memory=True).numpy(),
              "converge": torch.empty(Se, dtype=torch.uint8, pin_memory=True).numpy(),
              "iter": torch.empty(Se, dtype=torch.int32, pin_memory=True).numpy()}
-    e2e_ms = 0.0
+    t0 = time.perf_counter()
     for step in range(total_steps):
-        _, syn = dec.sample_syndromes(SEED, (step * world + rank) * Se, Se, sector=0, return_errors=False)
-        h_syn.copy_(syn)
-        torch.cuda.synchronize()
-        del syn
         if step == args.warmup:
             barrier()
             t0 = time.perf_counter()
-        dec.decode_batch(h_syn.numpy(), return_llr=False, return_all=False, out=h_out)
+        dec.decode_batch(h_syn[step % nstage], return_llr=False, return_all=False, out=h_out, packed=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -329,9 +409,11 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = Se * world * args.steps / (float(t2.item()) * 1e-3)
-    e2e = {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": int(Se * m),
-           "d2h_bytes_per_step": int(Se * n + Se + 4 * Se), "shots_per_gpu_per_step": Se,
-           "api": "BpOsdDecoder.decode_batch(numpy uint8[B,m]) -> bposd_decode_host (C ABI), pinned host buffers"}
+    e2e = {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": int(Se * mb),
+           "d2h_bytes_per_step": int(Se * nb + Se + 4 * Se), "shots_per_gpu_per_step": Se,
+           "api": "BpOsdDecoder.decode_batch(numpy uint8[B, ceil(m/8)], packed=True) -> bposd_decode_host_packed (C ABI); "
+                  "pinned host buffers staged before the timed region; results: packed osdw decoding, converge, iter"}
+    del h_syn, h_out
 
     # ---- single-shot latency of decode() (B=1: launch + D2H) ----
     lat = None
@@ -344,44 +426,47 @@ def run_gpu(args):
             t = time.perf_counter(); dec.decode(s1[i]); ts.append(time.perf_counter() - t)
         ts = np.array(ts[50:]) * 1e6
         lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "samples": int(ts.size),
-               "path": "decoder.decode(syndrome) -> bposd_decode_host B=1: one kernel launch + one stream synchronise, syndrome "
-                       "read from and results written to pinned host memory by the kernel, one SM per shot (latency geometry)"}
+               "path": "decoder.decode(syndrome) -> bposd_decode_host B=1"}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as _o
             _o.build()
-            arm = CpuArm()
-            arm.step(0, 50)
-            nshots, wall = arm.step(10**6, args.cpu_shots_per_core)
+            arm = CpuArm(cfg, c)
+            per_core = args.cpu_shots_per_core or c["cpu_shots"]
+            arm.step(0, max(per_core // 20, 1))
+            nshots, wall = arm.step(10**6, per_core)
             arm.close()
-            if arm.osd_shots:
+            if arm.osd_shots and osd_inv and ms_osd > 0:
                 # OSD roofline: algorithmic 32-bit word ops per OSD shot = bit-packed elimination word
                 # XORs as counted by the oracle on this sample + candidates x (XOR + POPC) x ceil(rank/32)
-                ncand = info["k"] + CFG["osd_order"] * (CFG["osd_order"] - 1) // 2
+                ncand = {"osd_cs": info["k"] + c["osd_order"] * (c["osd_order"] - 1) // 2, "osd_e": 2 ** c["osd_order"] - 1,
+                         "osd0": 0}[c["osd_method"]]
                 ops_shot = arm.elim_wordxors / arm.osd_shots + ncand * 2 * ((info["rank"] + 31) // 32)
                 peak_ops = dec.int32_peak()
-                ach = ops_shot * (osd_inv / args.steps) / (ms_osd / args.steps * 1e-3) if ms_osd > 0 else None
-                roofline["osd"] = {"bound": "int32 alu (LOP3)", "achieved": ach, "peak": peak_ops, "unit": "ops/s",
-                                   "frac": ach / peak_ops if ach else None,
+                ach = ops_shot * (osd_inv / args.steps) / (ms_osd / args.steps * 1e-3)
+                roofline["osd"] = {"bound": "int32 alu (LOP3)", "kernel": f"osd kernel variant {info['osd_variant']}", "achieved": ach,
+                                   "peak": peak_ops, "unit": "ops/s", "frac": ach / peak_ops,
                                    "algorithmic_ops_per_osd_shot": ops_shot, "osd_shots_sampled": arm.osd_shots,
+                                   "osd_shots_per_s": (osd_inv / args.steps) / (ms_osd / args.steps * 1e-3),
                                    "note": "peak = LOP3 microbenchmark in this run; ops per shot from the oracle's count"}
-            cpu_baseline = {"value": nshots / wall, "unit": "shots/s", "cores": arm.cores, "kind": "port",
-                            "sample": f"{args.cpu_shots_per_core} shots/core x {arm.cores} cores of the same workload, "
-                                      "oracle/bposd_oracle.c (restatement of ldpc v2; ldpc not installable offline)"}
+            cpu_baseline = {"value": nshots / wall, "unit": "shots/s", "cores": arm.cores, "kind": arm.kind,
+                            "sample": f"{per_core} shots/core x {arm.cores} cores of the same workload; {arm.what}"}
 
     if rank == 0:
         line = {
-            "metric": "shots/sec BP+OSD-CS(7) on [[1922,50,16]] HGP", "value": value, "unit": "shots/s",
+            "metric": metric_name(cfg, c), "value": value, "unit": "shots/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": f"f{prec}", "data": "synthetic",
-            "config": {"workload": workload_name(S, prec), "global_shots_per_step": S * world,
-                       "l2": "each step decodes a fresh syndrome batch larger than L2 (S*961 B)",
-                       "outputs": "osdw, osd0, bp, llr, converge, iter written to HBM for every shot",
-                       "bp_kernel": info["bp_kernel"], "bp_threads": info["bp_threads"],
-                       "bp_ctas_per_sm": info["bp_ctas_per_sm"], "sm_count": info["sm_count"]},
+            "config": {"workload": workload_name(cfg, c, m, n, E, prec)},
+            "shots_per_step": S * world,
+            "run": {"shots_per_gpu_per_step": S, "l2": "each step decodes a fresh syndrome batch larger than L2 (S*m bytes)",
+                    "outputs": "osdw, osd0, bp, llr, converge, iter written to HBM for every shot",
+                    "bp_kernel": info["bp_kernel"], "bp_threads": info["bp_threads"], "bp_ctas_per_sm": info["bp_ctas_per_sm"],
+                    "osd_variant": info["osd_variant"], "sm_count": info["sm_count"]},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_all,
             "clocks": clk, "latency": lat,
             "decode_stats": {"bp_converged_frac": conv_all / shots_all, "osd_invocation_frac": osd_all / shots_all,
-                             "logical_failures_last_step": int(counters[1].item()), "shots_last_step": int(counters[0].item())},
+                             "logical_failures_last_step": int(counters[1].item()) if have_logicals else None,
+                             "shots_last_step": int(counters[0].item())},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -394,20 +479,40 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--p", type=float, default=None, help="bit-flip probability (default: the config's)")
+    ap.add_argument("--ms-scaling-factor", type=float, default=None,
+                    help="min-sum scaling (0 = 1-2^-it, the README's; 0.625 = the reference harness's default, css_decode_sim.py:71)")
+    ap.add_argument("--osd-method", default=None, choices=["osd0", "osd_e", "osd_cs"])
+    ap.add_argument("--osd-order", type=int, default=None)
+    ap.add_argument("--max-iter", type=int, default=None)
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
-    ap.add_argument("--shots-per-gpu", type=int, default=1_250_000)
-    ap.add_argument("--e2e-shots-per-gpu", type=int, default=1_250_000)
-    ap.add_argument("--cpu-shots-per-core", type=int, default=1000)
+    ap.add_argument("--shots-per-gpu", type=int, default=0)
+    ap.add_argument("--e2e-shots-per-gpu", type=int, default=0)
+    ap.add_argument("--cpu-shots-per-core", type=int, default=0)
     ap.add_argument("--bp-kernel", type=int, default=None)
     ap.add_argument("--bp-threads", type=int, default=0)
+    ap.add_argument("--osd-variant", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = max(args.warmup, 0)
+    args.warmup = max(args.warmup, 0)
+    c = dict(CONFIGS[args.config])
+    if args.p is not None:
+        c["p"] = args.p
+    if args.ms_scaling_factor is not None:
+        c["ms_scaling_factor"] = args.ms_scaling_factor
+    if args.osd_method is not None:
+        c["osd_method"] = args.osd_method
+    if args.osd_order is not None:
+        c["osd_order"] = args.osd_order
+    if args.max_iter is not None:
+        c["max_iter"] = args.max_iter
+    if c["osd_method"] == "osd0":
+        c["osd_order"] = 0
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, args.config, c)
     else:
-        run_gpu(args)
+        run_gpu(args, args.config, c)
 
 
 if __name__ == "__main__":

@@ -7,4 +7,4 @@ __version__ = "0.1.0"
 
 from .css import css_code  # noqa: F401
 from .hgp import hgp, hgp_single  # noqa: F401
-from .decoder import BpOsdDecoder, bposd_decoder, BatchResult  # noqa: F401
+from .decoder import BpOsdDecoder, bposd_decoder, BatchResult, pack_bits, unpack_bits  # noqa: F401

@@ -46,6 +46,9 @@ SIGNATURES = {
     "bposd_update_channel_probs": (C.c_int, [P, P]),
     "bposd_decode_batch": (C.c_int, [P, P, C.c_int64, C.POINTER(Out), P, P, P]),
     "bposd_decode_host": (C.c_int, [P, P, C.c_int64, P, P, P, P, P, P]),
+    "bposd_decode_batch_packed": (C.c_int, [P, P, C.c_int64, C.POINTER(Out), P, P, P]),
+    "bposd_decode_host_packed": (C.c_int, [P, P, C.c_int64, P, P, P, P, P, P]),
+    "bposd_sample_syndromes_packed": (C.c_int, [P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, P, P, P]),
     "bposd_set_channel_thresholds": (C.c_int, [P, P, P, P]),
     "bposd_sample_syndromes": (C.c_int, [P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, P, P, P]),
     "bposd_set_logicals": (C.c_int, [P, P, P, C.c_int32]),
@@ -57,6 +60,7 @@ SIGNATURES = {
     "bposd_get_stats": (C.c_int, [P, C.POINTER(Stats)]),
     "bposd_set_tuning": (C.c_int, [P, C.c_int32, C.c_int32, C.c_int64]),
     "bposd_int32_peak": (C.c_int, [P, C.POINTER(C.c_double)]),
+    "bposd_smem_peak": (C.c_int, [P, C.POINTER(C.c_double)]),
     "bposd_set_cluster_size": (C.c_int, [P, C.c_int32]),
     "bposd_set_osd_variant": (C.c_int, [P, C.c_int32, C.c_int64]),
     "bposd_last_error": (C.c_char_p, [P]),

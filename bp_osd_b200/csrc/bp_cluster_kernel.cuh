@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
 
         for (int p = tid; p < rpc; p += T) {
             const uint32_t orig = t.row_of[(size_t)rank * rpc + p];
-            const unsigned s = (orig != BPC_NONE) ? (a.synd[shot * a.g.m + orig] & 1u) : 0u;
+            const unsigned s = (orig != BPC_NONE) ? synd_bit(a.synd, shot, a.g.m, (int)orig, a.synd_packed) : 0u;
             const unsigned deg = t.cdeg[(size_t)rank * rpc + p];
             meta[p] = (uint8_t)(s | (deg << 1) | (s << 7));
             if (!REG)

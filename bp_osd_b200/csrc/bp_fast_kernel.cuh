@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG>
         const real *prior = a.prior + shot * a.prior_stride;
 
         for (int p = tid; p < m; p += T) {
-            const unsigned s = a.synd[shot * m + row_of_tab[p]] & 1u;
+            const unsigned s = synd_bit(a.synd, shot, m, row_of_tab[p], a.synd_packed);
             const unsigned deg = cdeg_tab[p];
             meta[p] = s | (deg << 1) | (s << 7);
             if (!REG) // absent slots of short rows hold +max: neutral for min and sign (the result staging

@@ -48,6 +48,7 @@ struct bposd_handle {
         void *d_fail_llr = nullptr;
         long long fail_list_cap = 0, fail_llr_cap = 0;
         uint8_t *b_synd = nullptr, *b_err = nullptr, *b_osdw = nullptr, *b_osd0 = nullptr, *b_bp = nullptr, *b_conv = nullptr;
+        uint8_t *b_pk_osdw = nullptr, *b_pk_osd0 = nullptr, *b_pk_bp = nullptr; // bit-packed copies of the decodings ([cap, ceil(n/8)])
         void *b_llr = nullptr;
         int32_t *b_iter = nullptr;
         long long b_cap = 0;
@@ -377,6 +378,7 @@ extern "C" void bposd_destroy(bposd_t *h) {
         if (sl.h_ctrl) cudaFreeHost(sl.h_ctrl);
         cudaFree(sl.b_synd); cudaFree(sl.b_err); cudaFree(sl.b_osdw); cudaFree(sl.b_osd0); cudaFree(sl.b_bp);
         cudaFree(sl.b_conv); cudaFree(sl.b_llr); cudaFree(sl.b_iter);
+        cudaFree(sl.b_pk_osdw); cudaFree(sl.b_pk_osd0); cudaFree(sl.b_pk_bp);
         for (auto &e : sl.ev) if (e) cudaEventDestroy(e);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
@@ -524,6 +526,33 @@ extern "C" int bposd_int32_peak(bposd_t *h, double *ops_per_s) {
     return BPOSD_OK;
 }
 
+extern "C" int bposd_smem_peak(bposd_t *h, double *bytes_per_s) {
+    if (!h || !bytes_per_s) return BPOSD_EINVAL;
+    CU_TRY(h, cudaSetDevice(h->device));
+    float *d_out = nullptr;
+    CU_TRY(h, cudaMalloc((void **)&d_out, 4));
+    const int iters = 1 << 14, threads = 512, per_sm = 2, grid = h->sm_count * per_sm;
+    const size_t smem = (size_t)threads * 16 * 4;
+    CU_TRY(h, cudaFuncSetAttribute(smem_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CU_TRY(h, cudaEventCreate(&e0));
+    CU_TRY(h, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) { // first repetition warms up
+        CU_TRY(h, cudaEventRecord(e0, nullptr));
+        smem_peak_kernel<<<grid, threads, smem>>>(d_out, iters);
+        CU_TRY(h, cudaEventRecord(e1, nullptr));
+        CU_TRY(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    // per trip and thread: four 16-byte loads + four 16-byte stores
+    *bytes_per_s = 128.0 * iters * (double)grid * threads / (best * 1e-3);
+    return BPOSD_OK;
+}
+
 extern "C" int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size) {
     if (!h) return BPOSD_EINVAL;
     if (cluster_size != 0 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8 && cluster_size != 16)
@@ -570,7 +599,7 @@ extern "C" int bposd_get_stats(const bposd_t *h, bposd_stats_t *stats) {
 // OSD on the shots of a chunk that BP did not settle: `d_fail_list[0 .. *d_fail_count)` are their indices into the
 // chunk; `llr` is indexed by shot (llr_by_shot) or by position in the list.  All pointers are device-visible.
 template <typename real>
-static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const uint8_t *d_synd, const real *llr, int llr_by_shot,
+static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const uint8_t *d_synd, int synd_packed, const real *llr, int llr_by_shot,
                       const int *d_fail_count, const int *d_fail_list, uint8_t *d_osd0, uint8_t *d_osdw,
                       unsigned long long *d_stat, long long Bc, bool per_shot_priors, const double *d_weights, int *launches) {
     const int n = h->n, m = h->m;
@@ -591,6 +620,7 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
         OsdLargeArgs<real> o;
         o.g = g;
         o.synd = d_synd;
+        o.synd_packed = synd_packed;
         o.llr = llr;
         o.llr_by_shot = llr_by_shot;
         o.fail_count = d_fail_count;
@@ -614,6 +644,7 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
         o.weight = d_weights ? d_weights : h->d_weight;
         o.weight_stride = d_weights ? n : 0;
         o.synd = d_synd;
+        o.synd_packed = synd_packed;
         o.llr = llr;
         o.llr_by_shot = llr_by_shot;
         o.fail_count = d_fail_count;
@@ -644,7 +675,7 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
 // Enqueue one chunk (BP -> OSD -> control-word read-back) on `st`.  No host synchronisation.
 template <typename real>
 static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st, const uint8_t *d_synd, long long Bc,
-                        const bposd_out_t &out, const void *d_priors, const double *d_weights) {
+                        const bposd_out_t &out, const void *d_priors, const double *d_weights, int synd_packed = 0) {
     const int n = h->n, m = h->m;
     const bool osd_on = h->osd_method != BPOSD_OSD_OFF;
     real *llr_out = static_cast<real *>(out.d_llr);
@@ -674,6 +705,7 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     if (d_priors) { a.prior = static_cast<const real *>(d_priors); a.prior_stride = n; }
     else { a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32; a.prior_stride = 0; }
     a.synd = d_synd;
+    a.synd_packed = synd_packed;
     a.B = Bc;
     a.bp = out.d_bp; a.osd0 = out.d_osd0; a.osdw = out.d_osdw;
     a.llr = llr_out;
@@ -699,7 +731,7 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     CU_TRY(h, cudaEventRecord(sl.ev[1], st));
     if (osd_on) {
         int nl = 0;
-        const int rc = launch_osd<real>(h, st, a.g, a.synd, llr_out ? llr_out : static_cast<const real *>(sl.d_fail_llr), llr_out ? 1 : 0,
+        const int rc = launch_osd<real>(h, st, a.g, a.synd, synd_packed, llr_out ? llr_out : static_cast<const real *>(sl.d_fail_llr), llr_out ? 1 : 0,
                                         d_fail_count, sl.d_fail_list, a.osd0, a.osdw, sl.d_ctrl + 1, Bc, d_priors != nullptr, d_weights, &nl);
         if (rc) return rc;
         launches += nl;
@@ -737,29 +769,53 @@ static int check_osd_supported(bposd_handle *h) {
     return BPOSD_OK;
 }
 
+static int ensure_buffers(bposd_handle *h, bposd_handle::Slot &sl, long long B, bool want_llr, bool want_err, bool want_packed);
+static int pack_launch(bposd_handle *h, const uint8_t *src, long long Bc, uint8_t *dst, cudaStream_t st);
+
 template <typename real>
 static int decode_batch_t(bposd_handle *h, const uint8_t *d_synd, long long B, const bposd_out_t *out,
-                          const void *d_priors, const double *d_weights, cudaStream_t st) {
+                          const void *d_priors, const double *d_weights, cudaStream_t st, int packed = 0) {
     const int n = h->n, m = h->m;
     int rc = check_osd_supported(h);
     if (rc) return rc;
     const bool need_ws = h->osd_method != BPOSD_OSD_OFF && !out->d_llr;
     long long chunk = std::min<long long>(need_ws ? std::min(B, h->fail_cap) : B, 1ll << 30);
+    // bit-packed form: the kernels write one byte per bit into the slot's buffers, a pack kernel hands the bits to the caller
+    const long long sb = packed ? (m + 7) / 8 : m, db = packed ? (n + 7) / 8 : n;
+    if (packed) chunk = std::min<long long>(chunk, 262144);
     h->stats = bposd_stats_t{};
     bposd_handle::Slot &sl = h->slot[0];
+    if (packed) {
+        rc = collect_chunk(h, sl);
+        if (rc) return rc;
+        rc = ensure_buffers(h, sl, std::min(chunk, B), false, false, false);
+        if (rc) return rc;
+    }
     for (long long c0 = 0; c0 < B; c0 += chunk) {
         const long long Bc = std::min(chunk, B - c0);
         bposd_out_t o{};
-        o.d_bp = out->d_bp ? out->d_bp + c0 * n : nullptr;
-        o.d_osd0 = out->d_osd0 ? out->d_osd0 + c0 * n : nullptr;
-        o.d_osdw = out->d_osdw ? out->d_osdw + c0 * n : nullptr;
+        if (!packed) {
+            o.d_bp = out->d_bp ? out->d_bp + c0 * n : nullptr;
+            o.d_osd0 = out->d_osd0 ? out->d_osd0 + c0 * n : nullptr;
+            o.d_osdw = out->d_osdw ? out->d_osdw + c0 * n : nullptr;
+        } else {
+            o.d_bp = out->d_bp ? sl.b_bp : nullptr;
+            o.d_osd0 = out->d_osd0 ? sl.b_osd0 : nullptr;
+            o.d_osdw = out->d_osdw ? sl.b_osdw : nullptr;
+        }
         o.d_llr = out->d_llr ? static_cast<void *>(static_cast<real *>(out->d_llr) + c0 * n) : nullptr;
         o.d_converge = out->d_converge ? out->d_converge + c0 : nullptr;
         o.d_iter = out->d_iter ? out->d_iter + c0 : nullptr;
-        rc = launch_chunk<real>(h, sl, st, d_synd + c0 * m, Bc, o,
+        rc = launch_chunk<real>(h, sl, st, d_synd + c0 * sb, Bc, o,
                                 d_priors ? static_cast<const void *>(static_cast<const real *>(d_priors) + c0 * n) : nullptr,
-                                d_weights ? d_weights + c0 * n : nullptr);
+                                d_weights ? d_weights + c0 * n : nullptr, packed);
         if (rc) return rc;
+        if (packed) {
+            if (out->d_osdw) { rc = pack_launch(h, sl.b_osdw, Bc, out->d_osdw + c0 * db, st); if (rc) return rc; }
+            if (out->d_osd0) { rc = pack_launch(h, sl.b_osd0, Bc, out->d_osd0 + c0 * db, st); if (rc) return rc; }
+            if (out->d_bp) { rc = pack_launch(h, sl.b_bp, Bc, out->d_bp + c0 * db, st); if (rc) return rc; }
+            sl.pending_launches += (out->d_osdw ? 1 : 0) + (out->d_osd0 ? 1 : 0) + (out->d_bp ? 1 : 0);
+        }
         CU_TRY(h, cudaEventRecord(sl.ev[3], st));
         rc = collect_chunk(h, sl); // the control words and events are re-used by the next chunk
         if (rc) return rc;
@@ -767,23 +823,35 @@ static int decode_batch_t(bposd_handle *h, const uint8_t *d_synd, long long B, c
     return BPOSD_OK;
 }
 
-extern "C" int bposd_decode_batch(bposd_t *h, const uint8_t *d_synd, int64_t B, const bposd_out_t *out,
-                                  const void *d_priors, const double *d_weights, void *stream) {
+static int decode_batch_entry(bposd_t *h, const uint8_t *d_synd, int64_t B, const bposd_out_t *out, const void *d_priors,
+                              const double *d_weights, void *stream, int packed) {
     if (!h) return BPOSD_EINVAL;
     if (!out || (!d_synd && B > 0 && h->m > 0)) return fail(h, BPOSD_EINVAL, "NULL argument");
     if (B < 0) return fail(h, BPOSD_EINVAL, "negative batch size");
     CU_TRY(h, cudaSetDevice(h->device));
     if (B == 0) { h->stats = bposd_stats_t{}; return BPOSD_OK; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return h->precision == 64 ? decode_batch_t<double>(h, d_synd, B, out, d_priors, d_weights, st)
-                              : decode_batch_t<float>(h, d_synd, B, out, d_priors, d_weights, st);
+    return h->precision == 64 ? decode_batch_t<double>(h, d_synd, B, out, d_priors, d_weights, st, packed)
+                              : decode_batch_t<float>(h, d_synd, B, out, d_priors, d_weights, st, packed);
 }
 
-static int ensure_buffers(bposd_handle *h, bposd_handle::Slot &sl, long long B, bool want_llr, bool want_err) {
+extern "C" int bposd_decode_batch(bposd_t *h, const uint8_t *d_synd, int64_t B, const bposd_out_t *out,
+                                  const void *d_priors, const double *d_weights, void *stream) {
+    return decode_batch_entry(h, d_synd, B, out, d_priors, d_weights, stream, 0);
+}
+
+extern "C" int bposd_decode_batch_packed(bposd_t *h, const uint8_t *d_synd_bits, int64_t B, const bposd_out_t *out,
+                                         const void *d_priors, const double *d_weights, void *stream) {
+    return decode_batch_entry(h, d_synd_bits, B, out, d_priors, d_weights, stream, 1);
+}
+
+static int ensure_buffers(bposd_handle *h, bposd_handle::Slot &sl, long long B, bool want_llr, bool want_err, bool want_packed) {
     const size_t rs = h->precision == 64 ? 8 : 4;
     if (B > sl.b_cap) {
         cudaFree(sl.b_synd); cudaFree(sl.b_osdw); cudaFree(sl.b_osd0); cudaFree(sl.b_bp); cudaFree(sl.b_conv);
         cudaFree(sl.b_iter); cudaFree(sl.b_err); cudaFree(sl.b_llr);
+        cudaFree(sl.b_pk_osdw); cudaFree(sl.b_pk_osd0); cudaFree(sl.b_pk_bp);
+        sl.b_pk_osdw = sl.b_pk_osd0 = sl.b_pk_bp = nullptr;
         sl.b_synd = sl.b_osdw = sl.b_osd0 = sl.b_bp = sl.b_conv = sl.b_err = nullptr;
         sl.b_iter = nullptr; sl.b_llr = nullptr;
         sl.b_cap = 0;
@@ -797,6 +865,22 @@ static int ensure_buffers(bposd_handle *h, bposd_handle::Slot &sl, long long B, 
     }
     if (want_llr && !sl.b_llr) CU_TRY(h, cudaMalloc(&sl.b_llr, (size_t)sl.b_cap * h->n * rs));
     if (want_err && !sl.b_err) CU_TRY(h, cudaMalloc((void **)&sl.b_err, (size_t)sl.b_cap * h->n));
+    if (want_packed && !sl.b_pk_osdw) {
+        const size_t nb = ((size_t)h->n + 7) / 8;
+        CU_TRY(h, cudaMalloc((void **)&sl.b_pk_osdw, (size_t)sl.b_cap * nb));
+        CU_TRY(h, cudaMalloc((void **)&sl.b_pk_osd0, (size_t)sl.b_cap * nb));
+        CU_TRY(h, cudaMalloc((void **)&sl.b_pk_bp, (size_t)sl.b_cap * nb));
+    }
+    return BPOSD_OK;
+}
+
+// [Bc, n] bytes -> [Bc, ceil(n/8)] bytes on `st` (the BP / OSD kernels write one byte per bit; the packed entry points
+// hand out bits)
+static int pack_launch(bposd_handle *h, const uint8_t *src, long long Bc, uint8_t *dst, cudaStream_t st) {
+    const long long total = Bc * (((long long)h->n + 7) / 8);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16));
+    pack_bits_kernel<<<grid, 256, 0, st>>>(src, Bc, h->n, dst);
+    CU_TRY(h, cudaGetLastError());
     return BPOSD_OK;
 }
 
@@ -834,7 +918,7 @@ static int decode_latency_t(bposd_handle *h, const uint8_t *h_synd, long long B,
     bposd_handle::Slot &sl = h->slot[0];
     const bool osd_on = h->osd_method != BPOSD_OSD_OFF;
     if (!h_llr) {
-        rc = ensure_buffers(h, sl, B, true, false);
+        rc = ensure_buffers(h, sl, B, true, false, false);
         if (rc) return rc;
     }
     cudaStream_t st = sl.stream;
@@ -849,6 +933,7 @@ static int decode_latency_t(bposd_handle *h, const uint8_t *h_synd, long long B,
     a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32;
     a.prior_stride = 0;
     a.synd = dg + o_synd;
+    a.synd_packed = 0;
     a.B = B;
     a.bp = h_bp ? dg + o_bp : nullptr;
     a.osd0 = h_osd0 ? dg + o_osd0 : nullptr;
@@ -878,7 +963,7 @@ static int decode_latency_t(bposd_handle *h, const uint8_t *h_synd, long long B,
     if (osd_on && nfail > 0 && (a.osd0 || a.osdw)) {
         *cnt = nfail;
         int nl = 0;
-        rc = launch_osd<real>(h, st, a.g, a.synd, a.llr, 1, reinterpret_cast<const int *>(dg + o_cnt),
+        rc = launch_osd<real>(h, st, a.g, a.synd, 0, a.llr, 1, reinterpret_cast<const int *>(dg + o_cnt),
                               reinterpret_cast<const int *>(dg + o_list), a.osd0, a.osdw, nullptr, nfail, false, nullptr, &nl);
         if (rc) return rc;
         CU_TRY(h, cudaStreamSynchronize(st));
@@ -906,13 +991,34 @@ static int decode_latency_t(bposd_handle *h, const uint8_t *h_synd, long long B,
 // single-slot.
 template <typename real>
 static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, uint8_t *h_osdw, uint8_t *h_osd0,
-                         uint8_t *h_bp, void *h_llr, uint8_t *h_conv, int32_t *h_iter) {
+                         uint8_t *h_bp, void *h_llr, uint8_t *h_conv, int32_t *h_iter, int packed = 0) {
     const int n = h->n, m = h->m;
     int rc = check_osd_supported(h);
     if (rc) return rc;
+    // bytes per shot on the host side: one per bit, or bit-packed (syndromes ceil(m/8), decodings ceil(n/8))
+    const size_t sb = packed ? ((size_t)m + 7) / 8 : (size_t)m, db = packed ? ((size_t)n + 7) / 8 : (size_t)n;
     if (h->bp_kernel == 2 && h->lat_geom >= 0 && B <= h->lat_max_shots) {
         bool taken = false;
-        rc = decode_latency_t<real>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter, &taken);
+        if (!packed) {
+            rc = decode_latency_t<real>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter, &taken);
+        } else {
+            // a handful of shots: the bits are unpacked / packed on the host around the byte-per-bit latency path
+            std::vector<uint8_t> us((size_t)B * m), uw(h_osdw ? (size_t)B * n : 0), u0(h_osd0 ? (size_t)B * n : 0), ub(h_bp ? (size_t)B * n : 0);
+            for (long long b = 0; b < B; b++)
+                for (int i = 0; i < m; i++) us[(size_t)b * m + i] = (h_synd[(size_t)b * sb + (i >> 3)] >> (i & 7)) & 1;
+            rc = decode_latency_t<real>(h, us.data(), B, h_osdw ? uw.data() : nullptr, h_osd0 ? u0.data() : nullptr,
+                                        h_bp ? ub.data() : nullptr, h_llr, h_conv, h_iter, &taken);
+            if (!rc && taken) {
+                auto pack = [&](const std::vector<uint8_t> &u, uint8_t *dst) {
+                    std::memset(dst, 0, (size_t)B * db);
+                    for (long long b = 0; b < B; b++)
+                        for (int j = 0; j < n; j++) dst[(size_t)b * db + (j >> 3)] |= (uint8_t)((u[(size_t)b * n + j] & 1) << (j & 7));
+                };
+                if (h_osdw) pack(uw, h_osdw);
+                if (h_osd0) pack(u0, h_osd0);
+                if (h_bp) pack(ub, h_bp);
+            }
+        }
         if (rc || taken) return rc;
     }
     const bool need_ws = h->osd_method != BPOSD_OSD_OFF && !h_llr;
@@ -922,12 +1028,22 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
     if (need_ws) chunk = std::min(chunk, h->fail_cap);
     const int nslots = pipelined ? 2 : 1;
     h->stats = bposd_stats_t{};
+    // device-side sources of the three decodings of a slot: the kernels' byte-per-bit buffers, or their packed copies
+    auto pack_outputs = [&](bposd_handle::Slot &sl, long long Bc, cudaStream_t st) -> int {
+        if (!packed) return BPOSD_OK;
+        int r = BPOSD_OK;
+        if (h_osdw && !r) r = pack_launch(h, sl.b_osdw, Bc, sl.b_pk_osdw, st);
+        if (h_osd0 && !r) r = pack_launch(h, sl.b_osd0, Bc, sl.b_pk_osd0, st);
+        if (h_bp && !r) r = pack_launch(h, sl.b_bp, Bc, sl.b_pk_bp, st);
+        sl.pending_launches += (h_osdw ? 1 : 0) + (h_osd0 ? 1 : 0) + (h_bp ? 1 : 0);
+        return r;
+    };
     // Small batches (single-shot decode() above all): pageable host buffers would make every copy a blocking
     // call, so inputs and outputs go through one pinned staging block and the copies are truly asynchronous.
     {
         auto al = [](size_t x) { return (x + 15) / 16 * 16; };
-        const size_t o_synd = 0, o_osdw = o_synd + al((size_t)B * m), o_osd0 = o_osdw + (h_osdw ? al((size_t)B * n) : 0),
-                     o_bp = o_osd0 + (h_osd0 ? al((size_t)B * n) : 0), o_llr = o_bp + (h_bp ? al((size_t)B * n) : 0),
+        const size_t o_synd = 0, o_osdw = o_synd + al((size_t)B * sb), o_osd0 = o_osdw + (h_osdw ? al((size_t)B * db) : 0),
+                     o_bp = o_osd0 + (h_osd0 ? al((size_t)B * db) : 0), o_llr = o_bp + (h_bp ? al((size_t)B * db) : 0),
                      o_conv = o_llr + (h_llr ? al((size_t)B * n * sizeof(real)) : 0), o_iter = o_conv + (h_conv ? al((size_t)B) : 0),
                      total = o_iter + (h_iter ? al((size_t)B * 4) : 0);
         if (!pipelined && chunk == B && total <= h->stage_bytes) {
@@ -936,12 +1052,12 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
             bposd_handle::Slot &sl = h->slot[0];
             rc = collect_chunk(h, sl);
             if (rc) return rc;
-            rc = ensure_buffers(h, sl, B, h_llr != nullptr, false);
+            rc = ensure_buffers(h, sl, B, h_llr != nullptr, false, packed != 0);
             if (rc) return rc;
             cudaStream_t st = sl.stream;
             uint8_t *sg = h->h_stage;
-            std::memcpy(sg + o_synd, h_synd, (size_t)B * m);
-            CU_TRY(h, cudaMemcpyAsync(sl.b_synd, sg + o_synd, (size_t)B * m, cudaMemcpyHostToDevice, st));
+            std::memcpy(sg + o_synd, h_synd, (size_t)B * sb);
+            CU_TRY(h, cudaMemcpyAsync(sl.b_synd, sg + o_synd, (size_t)B * sb, cudaMemcpyHostToDevice, st));
             bposd_out_t o{};
             o.d_osdw = h_osdw ? sl.b_osdw : nullptr;
             o.d_osd0 = h_osd0 ? sl.b_osd0 : nullptr;
@@ -949,20 +1065,22 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
             o.d_llr = h_llr ? sl.b_llr : nullptr;
             o.d_converge = h_conv ? sl.b_conv : nullptr;
             o.d_iter = h_iter ? sl.b_iter : nullptr;
-            rc = launch_chunk<real>(h, sl, st, sl.b_synd, B, o, nullptr, nullptr);
+            rc = launch_chunk<real>(h, sl, st, sl.b_synd, B, o, nullptr, nullptr, packed);
             if (rc) return rc;
-            if (h_osdw) CU_TRY(h, cudaMemcpyAsync(sg + o_osdw, sl.b_osdw, (size_t)B * n, cudaMemcpyDeviceToHost, st));
-            if (h_osd0) CU_TRY(h, cudaMemcpyAsync(sg + o_osd0, sl.b_osd0, (size_t)B * n, cudaMemcpyDeviceToHost, st));
-            if (h_bp) CU_TRY(h, cudaMemcpyAsync(sg + o_bp, sl.b_bp, (size_t)B * n, cudaMemcpyDeviceToHost, st));
+            rc = pack_outputs(sl, B, st);
+            if (rc) return rc;
+            if (h_osdw) CU_TRY(h, cudaMemcpyAsync(sg + o_osdw, packed ? sl.b_pk_osdw : sl.b_osdw, (size_t)B * db, cudaMemcpyDeviceToHost, st));
+            if (h_osd0) CU_TRY(h, cudaMemcpyAsync(sg + o_osd0, packed ? sl.b_pk_osd0 : sl.b_osd0, (size_t)B * db, cudaMemcpyDeviceToHost, st));
+            if (h_bp) CU_TRY(h, cudaMemcpyAsync(sg + o_bp, packed ? sl.b_pk_bp : sl.b_bp, (size_t)B * db, cudaMemcpyDeviceToHost, st));
             if (h_llr) CU_TRY(h, cudaMemcpyAsync(sg + o_llr, sl.b_llr, (size_t)B * n * sizeof(real), cudaMemcpyDeviceToHost, st));
             if (h_conv) CU_TRY(h, cudaMemcpyAsync(sg + o_conv, sl.b_conv, (size_t)B, cudaMemcpyDeviceToHost, st));
             if (h_iter) CU_TRY(h, cudaMemcpyAsync(sg + o_iter, sl.b_iter, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
             CU_TRY(h, cudaEventRecord(sl.ev[3], st));
             rc = collect_chunk(h, sl);
             if (rc) return rc;
-            if (h_osdw) std::memcpy(h_osdw, sg + o_osdw, (size_t)B * n);
-            if (h_osd0) std::memcpy(h_osd0, sg + o_osd0, (size_t)B * n);
-            if (h_bp) std::memcpy(h_bp, sg + o_bp, (size_t)B * n);
+            if (h_osdw) std::memcpy(h_osdw, sg + o_osdw, (size_t)B * db);
+            if (h_osd0) std::memcpy(h_osd0, sg + o_osd0, (size_t)B * db);
+            if (h_bp) std::memcpy(h_bp, sg + o_bp, (size_t)B * db);
             if (h_llr) std::memcpy(h_llr, sg + o_llr, (size_t)B * n * sizeof(real));
             if (h_conv) std::memcpy(h_conv, sg + o_conv, (size_t)B);
             if (h_iter) std::memcpy(h_iter, sg + o_iter, (size_t)B * 4);
@@ -975,10 +1093,10 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
         bposd_handle::Slot &sl = h->slot[idx % nslots];
         rc = collect_chunk(h, sl); // the slot's previous chunk must have left its buffers
         if (rc) return rc;
-        rc = ensure_buffers(h, sl, std::min(chunk, B), h_llr != nullptr, false);
+        rc = ensure_buffers(h, sl, std::min(chunk, B), h_llr != nullptr, false, packed != 0);
         if (rc) return rc;
         cudaStream_t st = sl.stream;
-        CU_TRY(h, cudaMemcpyAsync(sl.b_synd, h_synd + c0 * m, (size_t)Bc * m, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(sl.b_synd, h_synd + c0 * sb, (size_t)Bc * sb, cudaMemcpyHostToDevice, st));
         bposd_out_t o{};
         o.d_osdw = h_osdw ? sl.b_osdw : nullptr;
         o.d_osd0 = h_osd0 ? sl.b_osd0 : nullptr;
@@ -986,11 +1104,13 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
         o.d_llr = h_llr ? sl.b_llr : nullptr;
         o.d_converge = h_conv ? sl.b_conv : nullptr;
         o.d_iter = h_iter ? sl.b_iter : nullptr;
-        rc = launch_chunk<real>(h, sl, st, sl.b_synd, Bc, o, nullptr, nullptr);
+        rc = launch_chunk<real>(h, sl, st, sl.b_synd, Bc, o, nullptr, nullptr, packed);
         if (rc) return rc;
-        if (h_osdw) CU_TRY(h, cudaMemcpyAsync(h_osdw + c0 * n, sl.b_osdw, (size_t)Bc * n, cudaMemcpyDeviceToHost, st));
-        if (h_osd0) CU_TRY(h, cudaMemcpyAsync(h_osd0 + c0 * n, sl.b_osd0, (size_t)Bc * n, cudaMemcpyDeviceToHost, st));
-        if (h_bp) CU_TRY(h, cudaMemcpyAsync(h_bp + c0 * n, sl.b_bp, (size_t)Bc * n, cudaMemcpyDeviceToHost, st));
+        rc = pack_outputs(sl, Bc, st);
+        if (rc) return rc;
+        if (h_osdw) CU_TRY(h, cudaMemcpyAsync(h_osdw + c0 * db, packed ? sl.b_pk_osdw : sl.b_osdw, (size_t)Bc * db, cudaMemcpyDeviceToHost, st));
+        if (h_osd0) CU_TRY(h, cudaMemcpyAsync(h_osd0 + c0 * db, packed ? sl.b_pk_osd0 : sl.b_osd0, (size_t)Bc * db, cudaMemcpyDeviceToHost, st));
+        if (h_bp) CU_TRY(h, cudaMemcpyAsync(h_bp + c0 * db, packed ? sl.b_pk_bp : sl.b_bp, (size_t)Bc * db, cudaMemcpyDeviceToHost, st));
         if (h_llr) CU_TRY(h, cudaMemcpyAsync(static_cast<real *>(h_llr) + c0 * n, sl.b_llr, (size_t)Bc * n * sizeof(real), cudaMemcpyDeviceToHost, st));
         if (h_conv) CU_TRY(h, cudaMemcpyAsync(h_conv + c0, sl.b_conv, (size_t)Bc, cudaMemcpyDeviceToHost, st));
         if (h_iter) CU_TRY(h, cudaMemcpyAsync(h_iter + c0, sl.b_iter, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
@@ -1003,14 +1123,24 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
     return BPOSD_OK;
 }
 
-extern "C" int bposd_decode_host(bposd_t *h, const uint8_t *h_synd, int64_t B, uint8_t *h_osdw, uint8_t *h_osd0,
-                                 uint8_t *h_bp, void *h_llr, uint8_t *h_conv, int32_t *h_iter) {
+static int decode_host_entry(bposd_t *h, const uint8_t *h_synd, int64_t B, uint8_t *h_osdw, uint8_t *h_osd0, uint8_t *h_bp,
+                             void *h_llr, uint8_t *h_conv, int32_t *h_iter, int packed) {
     if (!h) return BPOSD_EINVAL;
     if (B < 0 || (!h_synd && B > 0 && h->m > 0)) return fail(h, BPOSD_EINVAL, "bad argument");
     CU_TRY(h, cudaSetDevice(h->device));
     if (B == 0) { h->stats = bposd_stats_t{}; return BPOSD_OK; }
-    return h->precision == 64 ? decode_host_t<double>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter)
-                              : decode_host_t<float>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter);
+    return h->precision == 64 ? decode_host_t<double>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter, packed)
+                              : decode_host_t<float>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter, packed);
+}
+
+extern "C" int bposd_decode_host(bposd_t *h, const uint8_t *h_synd, int64_t B, uint8_t *h_osdw, uint8_t *h_osd0,
+                                 uint8_t *h_bp, void *h_llr, uint8_t *h_conv, int32_t *h_iter) {
+    return decode_host_entry(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter, 0);
+}
+
+extern "C" int bposd_decode_host_packed(bposd_t *h, const uint8_t *h_synd_bits, int64_t B, uint8_t *h_osdw_bits, uint8_t *h_osd0_bits,
+                                        uint8_t *h_bp_bits, void *h_llr, uint8_t *h_conv, int32_t *h_iter) {
+    return decode_host_entry(h, h_synd_bits, B, h_osdw_bits, h_osd0_bits, h_bp_bits, h_llr, h_conv, h_iter, 1);
 }
 
 extern "C" int bposd_set_channel_thresholds(bposd_t *h, const uint32_t *t1, const uint32_t *t2, const uint32_t *t3) {
@@ -1030,8 +1160,8 @@ extern "C" int bposd_set_channel_thresholds(bposd_t *h, const uint32_t *t1, cons
     return BPOSD_OK;
 }
 
-extern "C" int bposd_sample_syndromes(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector,
-                                      uint8_t *d_errors, uint8_t *d_synd, void *stream) {
+static int sample_entry(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector, uint8_t *d_errors, uint8_t *d_synd,
+                        void *stream, int packed) {
     if (!h) return BPOSD_EINVAL;
     if (!h->d_t1) return fail(h, BPOSD_EINVAL, "call bposd_set_channel_thresholds first");
     if (B < 0 || (!d_synd && B > 0) || (sector != 0 && sector != 1)) return fail(h, BPOSD_EINVAL, "bad argument");
@@ -1041,7 +1171,7 @@ extern "C" int bposd_sample_syndromes(bposd_t *h, uint64_t seed, uint64_t shot0,
     a.g = graph_of(h);
     a.t1 = h->d_t1; a.t2 = h->d_t2; a.t3 = h->d_t3;
     a.seed = seed; a.shot0 = shot0; a.B = B; a.sector = sector;
-    a.errors = d_errors; a.synd = d_synd;
+    a.errors = d_errors; a.synd = d_synd; a.synd_packed = packed;
     const int threads = std::min(1024, std::max(32, ((h->n + 3) / 4 + 31) / 32 * 32));
     const size_t smem = (size_t)h->n + 16;
     if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(sample_syndrome_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1049,6 +1179,16 @@ extern "C" int bposd_sample_syndromes(bposd_t *h, uint64_t seed, uint64_t shot0,
     sample_syndrome_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     CU_TRY(h, cudaGetLastError());
     return BPOSD_OK;
+}
+
+extern "C" int bposd_sample_syndromes(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector,
+                                      uint8_t *d_errors, uint8_t *d_synd, void *stream) {
+    return sample_entry(h, seed, shot0, B, sector, d_errors, d_synd, stream, 0);
+}
+
+extern "C" int bposd_sample_syndromes_packed(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector,
+                                             uint8_t *d_errors, uint8_t *d_synd_bits, void *stream) {
+    return sample_entry(h, seed, shot0, B, sector, d_errors, d_synd_bits, stream, 1);
 }
 
 extern "C" int bposd_set_logicals(bposd_t *h, const int32_t *indptr, const int32_t *indices, int32_t K) {
@@ -1170,7 +1310,7 @@ extern "C" int bposd_sample_and_decode(bposd_t *h, uint64_t seed, uint64_t shot0
     if (B == 0) return BPOSD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     bposd_handle::Slot &sl = h->slot[0];
-    int rc = ensure_buffers(h, sl, B, false, true);
+    int rc = ensure_buffers(h, sl, B, false, true, false);
     if (rc) return rc;
     rc = bposd_sample_syndromes(h, seed, shot0, B, sector, sl.b_err, sl.b_synd, stream);
     if (rc) return rc;

@@ -40,6 +40,7 @@ struct BpArgs {
     long long prior_stride; // 0: one prior vector for all shots, n: per-shot rows
     int uniform_prior;      // 1: every bit has the same prior (a scalar in registers)
     const uint8_t *synd;
+    int synd_packed;        // 0: [B, m] bytes (0/1); 1: [B, ceil(m/8)] bytes, bit i%8 of byte i/8 = check i
     long long B;
     uint8_t *bp, *osd0, *osdw;
     real *llr;
@@ -58,6 +59,12 @@ struct BpArgs {
 template <typename real> __device__ __forceinline__ real real_max();
 template <> __device__ __forceinline__ double real_max<double>() { return DBL_MAX; }
 template <> __device__ __forceinline__ float real_max<float>() { return FLT_MAX; }
+
+// syndrome bit of check i of a shot, from the byte-per-check or the bit-packed layout
+__device__ __forceinline__ unsigned synd_bit(const uint8_t *synd, long long shot, int m, int i, int packed) {
+    return packed ? ((unsigned)(synd[shot * (long long)((m + 7) >> 3) + (i >> 3)] >> (i & 7)) & 1u)
+                  : ((unsigned)synd[shot * (long long)m + i] & 1u);
+}
 
 __device__ __forceinline__ double ms_alpha(double alpha0, int it) {
     return alpha0 == 0.0 ? 1.0 - ldexp(1.0, -it) : alpha0;
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(BpArgs<real> a) {
         if (shot >= a.B) break;
         const real *prior = a.prior + shot * a.prior_stride;
 
-        for (int i = tid; i < m; i += T) synd_s[i] = a.synd[shot * m + i] & 1;
+        for (int i = tid; i < m; i += T) synd_s[i] = (uint8_t)synd_bit(a.synd, shot, m, i, a.synd_packed);
         for (int j = tid; j < n; j += T) { // a3
             real p = prior[j];
             llr_s[j] = p;
@@ -271,6 +278,7 @@ struct OsdArgs {
     const double *weight; // [n] log(1/p_j), or [B, n] per shot when weight_stride == n
     long long weight_stride;
     const uint8_t *synd;
+    int synd_packed;      // as BpArgs::synd_packed
     const real *llr;      // [B, n] if llr_by_shot else [capacity, n] indexed by fail slot
     int llr_by_shot;
     const int *fail_count;
@@ -480,7 +488,6 @@ __global__ void __launch_bounds__(1024, 1) osd_kernel(OsdArgs<real> a) {
     for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
         const long long shot = a.fail_list[f];
         const real *llr = a.llr + (a.llr_by_shot ? shot : (long long)f) * n;
-        const uint8_t *synd = a.synd + shot * m;
         const double *weight = a.weight + shot * a.weight_stride;
         __syncthreads();
 
@@ -580,7 +587,7 @@ __global__ void __launch_bounds__(1024, 1) osd_kernel(OsdArgs<real> a) {
             for (int w = lane; w < S; w += 32) {
                 uint32_t acc = 0;
                 for (int r = warp; r < m; r += nwarps)
-                    if (synd[r] & 1) acc ^= Tc[(size_t)r * St + w];
+                    if (synd_bit(a.synd, shot, m, r, a.synd_packed)) acc ^= Tc[(size_t)r * St + w];
                 mine[w] = acc;
             }
             __syncthreads();
@@ -620,6 +627,7 @@ template <typename real>
 struct OsdLargeArgs {
     GraphDev g;
     const uint8_t *synd;
+    int synd_packed;
     const real *llr;
     int llr_by_shot;
     const int *fail_count;
@@ -664,7 +672,6 @@ __global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) 
     for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
         const long long shot = a.fail_list[f];
         const real *llr = a.llr + (a.llr_by_shot ? shot : (long long)f) * n;
-        const uint8_t *synd = a.synd + shot * m;
         __syncthreads();
 
         // ---- a9: stable ascending rank sort on (llr, index); keys streamed from global (broadcast loads)
@@ -686,7 +693,7 @@ __global__ void __launch_bounds__(1024) osd0_large_kernel(OsdLargeArgs<real> a) 
             for (int u = 0; u < 8; u++)
                 if (j0 + u * T < n) order[rk[u]] = j0 + u * T;
         }
-        for (int i = tid; i < m; i += T) { rowpanel[i] = OSDL_UNUSED; s8[i] = synd[i] & 1; }
+        for (int i = tid; i < m; i += T) { rowpanel[i] = OSDL_UNUSED; s8[i] = (uint8_t)synd_bit(a.synd, shot, m, i, a.synd_packed); }
         if (tid == 0) { sh_rank = 0; pstart_s[0] = 0; }
         __syncthreads();
 
@@ -845,6 +852,7 @@ struct SampleArgs {
     int sector; // 0: X component, 1: Z component
     uint8_t *errors;
     uint8_t *synd;
+    int synd_packed; // 1: write ceil(m/8) bytes per shot (bit i%8 of byte i/8 = check i) instead of m
 };
 
 // one CTA per shot (grid-stride): errors staged in shared memory, one thread per check for H e
@@ -873,10 +881,23 @@ __global__ void __launch_bounds__(1024) sample_syndrome_kernel(SampleArgs a) {
             }
         }
         __syncthreads();
-        for (int i = tid; i < m; i += T) {
-            int acc = 0;
-            for (int p = a.g.row_ptr[i]; p < a.g.row_ptr[i + 1]; p++) acc ^= e_s[a.g.col_idx[p]];
-            a.synd[b * m + i] = (uint8_t)acc;
+        if (!a.synd_packed) {
+            for (int i = tid; i < m; i += T) {
+                int acc = 0;
+                for (int p = a.g.row_ptr[i]; p < a.g.row_ptr[i + 1]; p++) acc ^= e_s[a.g.col_idx[p]];
+                a.synd[b * m + i] = (uint8_t)acc;
+            }
+        } else {
+            // bit-packed H e mod 2: a warp ballots 32 checks at a time, every eighth lane stores one byte
+            const long long mb = (m + 7) >> 3;
+            for (int i0 = 0; i0 < m; i0 += T) {
+                const int i = i0 + tid;
+                int acc = 0;
+                if (i < m)
+                    for (int p = a.g.row_ptr[i]; p < a.g.row_ptr[i + 1]; p++) acc ^= e_s[a.g.col_idx[p]];
+                const unsigned bal = __ballot_sync(0xffffffffu, acc & 1);
+                if ((tid & 7) == 0 && i < m) a.synd[b * mb + (i >> 3)] = (uint8_t)(bal >> (tid & 31));
+            }
         }
     }
 }
@@ -949,6 +970,22 @@ __global__ void __launch_bounds__(256) channel_update_kernel(const uint8_t *__re
     }
 }
 
+// [B, n] bytes (0/1) -> [B, ceil(n/8)] bytes, bit j%8 of byte j/8 = entry j (the layout of numpy.packbits(bitorder="little"))
+__global__ void __launch_bounds__(256) pack_bits_kernel(const uint8_t *__restrict__ src, long long B, int n, uint8_t *__restrict__ dst) {
+    const long long nb = (n + 7) >> 3, total = B * nb;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / nb;
+        const int jb = (int)(idx - b * nb);
+        const uint8_t *row = src + b * n + jb * 8;
+        const int cnt = min(8, n - jb * 8);
+        unsigned v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < cnt) v |= (unsigned)(row[k] & 1) << k;
+        dst[idx] = (uint8_t)v;
+    }
+}
+
 // INT32 logic-op calibration for the OSD roofline ("measure a LOP3 microbenchmark peak in the
 // same run"): eight independent LOP3 chains per thread, 8 * iters logic ops per thread.
 __global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t *out, int iters) {
@@ -963,6 +1000,33 @@ __global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t *out, int iters
 #pragma unroll
     for (int j = 0; j < 8; j++) r ^= a[j];
     if (r == 0x12345678u) out[0] = r; // keeps the chains alive
+}
+
+// Shared-memory bandwidth calibration for the BP roofline: the message traffic of the in-place BP kernels is 16-byte
+// LDS / STS in equal parts, so the peak is measured the same way -- every thread loads, modifies and stores 16-byte
+// words of its own (lane-consecutive, i.e. conflict free: four 128-byte wavefronts per warp instruction), four
+// independent words per trip so that the loop is bandwidth and not latency bound.
+__global__ void __launch_bounds__(1024) smem_peak_kernel(float *out, int iters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw) + threadIdx.x * 16u;
+    const unsigned stride = blockDim.x * 16u;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        v[k] = make_float4(threadIdx.x, k, 1.f, 2.f);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + k * stride), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w) : "memory");
+    }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "r"(base + k * stride) : "memory");
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            v[k].x += 1.f;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + k * stride), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w) : "memory");
+        }
+    }
+    if (v[0].x + v[1].x + v[2].x + v[3].x == -1.f) out[0] = v[0].y;
 }
 
 struct CssSector {

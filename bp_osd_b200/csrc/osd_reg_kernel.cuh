@@ -7,7 +7,7 @@
 //   * the sorted columns are consumed in rounds of G candidates, ONE block barrier per round (osd_kernel: two per
 //     pivot, ~1 900 pivot steps on the bench code);
 //   * the CTA is warp specialised and software pipelined: in round R
-//       warp 0, the RESOLVER  takes the reduced images of the G candidates of round R (lane l holds word l of each;
+//       one warp, the RESOLVER takes the reduced images of the G candidates of round R (lane l holds word l of each;
 //                             they were mirrored by the updaters one round earlier, so the resolver first applies the
 //                             pivots of round R-1, which it still holds in registers), walks them in sorted order -- a
 //                             candidate with a 1 in an unused row is a pivot (lowest such row; the OSD result does not
@@ -141,7 +141,11 @@ __global__ void __launch_bounds__(32 + (W * 32 / kOsdRegCPT < 64 ? 64 : W * 32 /
     const GraphDev &g = a.g;
     const int m = g.m, n = g.n, E = g.nnz, S = a.S;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int TU = T - 32, tu = tid - 32; // updater threads
+    // the resolver is the LAST warp: the sub-partition schedulers of sm_100a favour the highest warp id, and the resolver's
+    // serial chain, not the updaters' bulk work, sets the length of a round (ncu: with the resolver as warp 0 the
+    // updaters spent 47 % of their time at the round barrier, profiles/r2c_osd_ncu_summary.md)
+    const int TU = T - 32, tu = tid; // updater threads are 0 .. TU-1
+    const bool resolver = warp == (T >> 5) - 1;
     const int NP = a.np2;
     const OsdRegLayout L = osd_reg_layout(m, n, E, W, KD, G, T, NP);
     uint32_t *Tmir = reinterpret_cast<uint32_t *>(smem_raw + L.o_mirror);
@@ -193,7 +197,6 @@ __global__ void __launch_bounds__(32 + (W * 32 / kOsdRegCPT < 64 ? 64 : W * 32 /
     for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
         const long long shot = a.fail_list[f];
         const real *llr = a.llr + (a.llr_by_shot ? shot : (long long)f) * n;
-        const uint8_t *synd = a.synd + shot * m;
         const double *weight = a.weight + shot * a.weight_stride;
         __syncthreads();
 
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(32 + (W * 32 / kOsdRegCPT < 64 ? 64 : W * 32 /
         __syncthreads();
         const bool need_T = !(a.method == 0 || a.order <= 0 || !a.osdw); // the candidate search reads T
         int R = 0;
-        if (warp == 0) {
+        if (resolver) {
             // =================== resolver warp ===================
             prepare(1, lane, 32);
             // used-row mask and transformed syndrome, one word per lane
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(32 + (W * 32 / kOsdRegCPT < 64 ? 64 : W * 32 /
 #pragma unroll 4
                 for (int b = 0; b < 32; b++) {
                     const int i = lane * 32 + b;
-                    if (i < m) r_sp |= (uint32_t)(synd[i] & 1) << b;
+                    if (i < m) r_sp |= synd_bit(a.synd, shot, m, i, a.synd_packed) << b;
                 }
             }
             osd_reg_bar(T);

@@ -74,6 +74,10 @@ class css_decode_sim:
 
         if self.seed == 0 or self.run_count != 0:   # a resumed run never replays its old stream (:135-136)
             self.seed = int(np.random.randint(low=1, high=2**32 - 1))
+            # multi-rank run: every rank must key Philox with the SAME seed (the stream is indexed by global shot), so
+            # rank 0's draw is the one that counts -- and the one its output file records
+            from .sharding import broadcast_from_rank0
+            self.seed = broadcast_from_rank0(self.seed)
         print(f"RNG Seed: {self.seed}")
 
         self.hx = sp.csr_matrix(hx).astype(np.uint8)
@@ -214,8 +218,13 @@ class css_decode_sim:
             c = np.zeros(8, dtype=np.int64)
             if cnt:
                 self._batch(self.run_count + lo, cnt, c)
+            # slot 7: "rank 0's save interval has elapsed".  The save / early-stop block below must be entered by every
+            # rank or by none (a rank that stops while another loops on would leave that one in a collective for ever),
+            # and wall clocks differ between ranks, so rank 0's clock decides and rides along with the counters.
+            c[7] = 1 if (rank == 0 and int(time.time() - save_time) > self.save_interval) else 0
             if world > 1:
                 c = all_reduce_vector(c, min_slots=(6,), device=self.bpd_x.device)
+            gate_open = bool(c[7])
             self.run_count += int(c[0])
             self.bp_converge_count_x += int(c[1]); self.bp_converge_count_z += int(c[2])
             self.bp_success_count += int(c[3]); self.osd0_success_count += int(c[4]); self.osdw_success_count += int(c[5])
@@ -230,7 +239,7 @@ class css_decode_sim:
                     f"{self.osdw_logical_error_rate_eb*100:.2g}%; OSD0: {self.osd0_logical_error_rate*100:.3g}±"
                     f"{self.osd0_logical_error_rate_eb*100:.2g}%;")
             now = time.time()
-            if int(now - save_time) > self.save_interval or self.run_count >= self.target_runs:
+            if gate_open or self.run_count >= self.target_runs:
                 self.runtime = (now - save_time) + self.runtime
                 save_time = now
                 self.runtime_readable = time.strftime("%H:%M:%S", time.gmtime(self.runtime))

@@ -23,7 +23,7 @@ import scipy.sparse as sp
 
 from . import _capi
 
-__all__ = ["BpOsdDecoder", "bposd_decoder", "BatchResult", "prob_thresholds"]
+__all__ = ["BpOsdDecoder", "bposd_decoder", "BatchResult", "prob_thresholds", "pack_bits", "unpack_bits"]
 
 _BP_NAMES = {
     "ps": _capi.BP_PRODUCT_SUM, "product_sum": _capi.BP_PRODUCT_SUM, "prod_sum": _capi.BP_PRODUCT_SUM,
@@ -45,15 +45,47 @@ def prob_thresholds(p) -> np.ndarray:
     return np.clip(t, 0, 4294967295).astype(np.uint32)
 
 
+def pack_bits(a):
+    """[B, k] 0/1 array (numpy or torch) -> [B, ceil(k/8)] uint8, bit i%8 of byte i/8 = entry i: the layout of the
+    ``packed=True`` interfaces (``numpy.packbits(..., bitorder="little")``)."""
+    try:
+        import torch
+        if isinstance(a, torch.Tensor):
+            B, k = a.shape
+            pad = (-k) % 8
+            x = (a & 1).to(torch.uint8) if a.dtype != torch.bool else a.to(torch.uint8)
+            if pad:
+                x = torch.nn.functional.pad(x, (0, pad))
+            w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.int32, device=a.device)
+            return (x.view(B, -1, 8).to(torch.int32) * w).sum(-1).to(torch.uint8)
+    except ImportError:  # pragma: no cover
+        pass
+    return np.packbits(np.asarray(a).astype(np.uint8) & 1, axis=1, bitorder="little")
+
+
+def unpack_bits(a, k):
+    """Inverse of :func:`pack_bits`: [B, ceil(k/8)] uint8 -> [B, k] uint8 of 0/1."""
+    try:
+        import torch
+        if isinstance(a, torch.Tensor):
+            sh = torch.arange(8, dtype=torch.uint8, device=a.device)
+            return ((a.unsqueeze(-1) >> sh) & 1).reshape(a.shape[0], -1)[:, :k].contiguous()
+    except ImportError:  # pragma: no cover
+        pass
+    return np.unpackbits(np.asarray(a, dtype=np.uint8), axis=1, bitorder="little")[:, :k]
+
+
 @dataclass
 class BatchResult:
-    """Outputs of ``decode_batch``; tensors live where the syndromes lived (CUDA or host)."""
+    """Outputs of ``decode_batch``; tensors live where the syndromes lived (CUDA or host).  With ``packed`` the three
+    decodings are bit-packed rows of ceil(n/8) bytes (see :func:`unpack_bits`)."""
     osdw_decoding: object
     osd0_decoding: object
     bp_decoding: object
     log_prob_ratios: object
     converge: object
     iter: object
+    packed: bool = False
 
 
 def _ptr(arr) -> Optional[int]:
@@ -64,7 +96,12 @@ class BpOsdDecoder:
     def __init__(self, parity_check_matrix, error_rate=None, channel_probs=None, max_iter=0,
                  bp_method="minimum_sum", ms_scaling_factor=1.0, osd_method="osd_0", osd_order=0,
                  error_channel=None, schedule="parallel", input_vector_type="syndrome",
-                 precision=64, device=None, **unused):
+                 precision=64, device=None, **ignored):
+        # keywords of ldpc's BpOsdDecoder that have no effect on the results of the parallel schedule are accepted and
+        # ignored; anything else is a spelling mistake and must not be swallowed
+        unknown = set(ignored) - {"omp_thread_count", "random_schedule_seed", "serial_schedule_order", "random_serial_schedule"}
+        if unknown:
+            raise TypeError(f"unexpected keyword argument(s): {sorted(unknown)}")
         if schedule not in ("parallel", 0, "0"):
             raise ValueError("only the parallel (flooding) BP schedule is implemented")
         if input_vector_type not in ("syndrome", 0, "0"):
@@ -182,6 +219,12 @@ class BpOsdDecoder:
         self._check(_capi.load().bposd_int32_peak(self._h, C.byref(v)))
         return float(v.value)
 
+    def smem_peak(self) -> float:
+        """Measured shared-memory bandwidth of the device in bytes/s (denominator of the BP roofline)."""
+        v = C.c_double()
+        self._check(_capi.load().bposd_smem_peak(self._h, C.byref(v)))
+        return float(v.value)
+
     def set_cluster_size(self, cluster_size=0):
         """Thread-block-cluster size of BP kernel 3 (0 = smallest that fits, else 2, 4, 8 or 16)."""
         self._check(_capi.load().bposd_set_cluster_size(self._h, int(cluster_size)))
@@ -279,9 +322,10 @@ class BpOsdDecoder:
         self._llr = value
 
     def _decode_host(self, synd_u8: np.ndarray, want_llr: bool = True, want_all: bool = True,
-                     out: Optional[dict] = None) -> BatchResult:
+                     out: Optional[dict] = None, packed: bool = False) -> BatchResult:
         B = synd_u8.shape[0]
         out = out or {}
+        nd = (self.n + 7) // 8 if packed else self.n
 
         def buf(key, shape, dtype, want=True):
             a = out.get(key)
@@ -291,19 +335,21 @@ class BpOsdDecoder:
                 raise ValueError(f"out['{key}'] must be a C-contiguous {np.dtype(dtype)} array of shape {tuple(shape)}")
             return a
 
-        osdw = buf("osdw", (B, self.n), np.uint8)
-        osd0 = buf("osd0", (B, self.n), np.uint8, want_all)
-        bp = buf("bp", (B, self.n), np.uint8, want_all)
+        osdw = buf("osdw", (B, nd), np.uint8)
+        osd0 = buf("osd0", (B, nd), np.uint8, want_all)
+        bp = buf("bp", (B, nd), np.uint8, want_all)
         llr = buf("llr", (B, self.n), self._real, want_llr)
         conv = buf("converge", (B,), np.uint8)
         it = buf("iter", (B,), np.int32)
-        self._check(_capi.load().bposd_decode_host(self._h, _ptr(synd_u8), B, _ptr(osdw), _ptr(osd0), _ptr(bp),
-                                                   _ptr(llr), _ptr(conv), _ptr(it)))
-        return BatchResult(osdw, osd0, bp, llr, None if conv is None else conv.astype(bool), it)
+        fn = _capi.load().bposd_decode_host_packed if packed else _capi.load().bposd_decode_host
+        self._check(fn(self._h, _ptr(synd_u8), B, _ptr(osdw), _ptr(osd0), _ptr(bp), _ptr(llr), _ptr(conv), _ptr(it)))
+        return BatchResult(osdw, osd0, bp, llr, None if conv is None else conv.astype(bool), it, packed)
 
     def decode_batch(self, syndromes, return_llr: bool = True, return_all: bool = True, priors=None, out=None,
-                     weights=None):
-        """Decode ``syndromes[B, m]``.
+                     weights=None, packed: bool = False):
+        """Decode ``syndromes[B, m]`` (``packed=True``: bit-packed rows ``[B, ceil(m/8)]`` in, bit-packed decodings
+        ``[B, ceil(n/8)]`` out -- :func:`pack_bits` / :func:`unpack_bits` give the layout; an eighth of the bytes over
+        PCIe for host arrays).
 
         A CUDA ``torch.Tensor`` (uint8/bool/int, 0/1) is decoded in place on its device and the
         result holds CUDA tensors; a numpy array goes through pinned-staging copies
@@ -320,17 +366,26 @@ class BpOsdDecoder:
             import torch
         except Exception:  # pragma: no cover
             torch = None
+        ms = (self.m + 7) // 8 if packed else self.m
+        nd = (self.n + 7) // 8 if packed else self.n
         if torch is not None and isinstance(syndromes, torch.Tensor):
             if not syndromes.is_cuda:
-                return self.decode_batch(syndromes.numpy(), return_llr, return_all, out=out)
-            if syndromes.dim() != 2 or syndromes.shape[1] != self.m:
-                raise ValueError(f"syndromes must have shape [B, {self.m}]")
+                if priors is not None or weights is not None:
+                    raise ValueError("per-shot priors / weights need CUDA syndromes (they are CUDA tensors)")
+                return self.decode_batch(syndromes.numpy(), return_llr, return_all, out=out, packed=packed)
+            if syndromes.dim() != 2 or syndromes.shape[1] != ms:
+                raise ValueError(f"syndromes must have shape [B, {ms}]")
             if syndromes.device.index != self.device:
                 raise ValueError(f"syndromes live on cuda:{syndromes.device.index}, decoder on cuda:{self.device}")
             s = syndromes
-            if s.dtype != torch.uint8:
-                s = (s != 0).to(torch.uint8)
-            s = s.contiguous()
+            if packed:
+                if s.dtype != torch.uint8:
+                    raise ValueError("bit-packed syndromes must be uint8")
+            elif s.dtype == torch.bool:
+                s = s.to(torch.uint8)
+            elif s.dtype != torch.uint8:
+                s = (s & 1).to(torch.uint8) if not s.dtype.is_floating_point else (s.to(torch.int64) & 1).to(torch.uint8)
+            s = s.contiguous()  # (uint8 entries are reduced mod 2 by the kernels, like every other integer type)
             B = s.shape[0]
             dev = s.device
             tdt = torch.float64 if self.precision == 64 else torch.float32
@@ -343,9 +398,9 @@ class BpOsdDecoder:
                     raise ValueError(f"out['{key}'] must be a contiguous {dtype} CUDA tensor of shape {tuple(shape)}")
                 return t
 
-            osdw = buf("osdw", (B, self.n), torch.uint8)
-            osd0 = buf("osd0", (B, self.n), torch.uint8, return_all)
-            bp = buf("bp", (B, self.n), torch.uint8, return_all)
+            osdw = buf("osdw", (B, nd), torch.uint8)
+            osd0 = buf("osd0", (B, nd), torch.uint8, return_all)
+            bp = buf("bp", (B, nd), torch.uint8, return_all)
             llr = buf("llr", (B, self.n), tdt, return_llr)
             conv = buf("converge", (B,), torch.uint8)
             it = buf("iter", (B,), torch.int32)
@@ -365,15 +420,22 @@ class BpOsdDecoder:
                           bp.data_ptr() if bp is not None else None,
                           llr.data_ptr() if llr is not None else None, conv.data_ptr(), it.data_ptr())
             stream = torch.cuda.current_stream(dev).cuda_stream
-            self._check(_capi.load().bposd_decode_batch(self._h, s.data_ptr(), B, C.byref(o),
-                                                        pri.data_ptr() if pri is not None else None,
-                                                        wts.data_ptr() if wts is not None else None, stream))
-            return BatchResult(osdw, osd0, bp, llr, conv.bool(), it)
+            fn = _capi.load().bposd_decode_batch_packed if packed else _capi.load().bposd_decode_batch
+            self._check(fn(self._h, s.data_ptr(), B, C.byref(o), pri.data_ptr() if pri is not None else None,
+                           wts.data_ptr() if wts is not None else None, stream))
+            return BatchResult(osdw, osd0, bp, llr, conv.bool(), it, packed)
+        if priors is not None or weights is not None:
+            raise ValueError("per-shot priors / weights need CUDA syndromes (they are CUDA tensors)")
         s = np.asarray(syndromes)
-        if s.ndim != 2 or s.shape[1] != self.m:
-            raise ValueError(f"syndromes must have shape [B, {self.m}]")
-        s = np.ascontiguousarray((s.astype(np.int64) & 1).astype(np.uint8)) if s.dtype != np.uint8 else np.ascontiguousarray(s)
-        return self._decode_host(s, want_llr=return_llr, want_all=return_all, out=out)
+        if s.ndim != 2 or s.shape[1] != ms:
+            raise ValueError(f"syndromes must have shape [B, {ms}]")
+        if packed:
+            if s.dtype != np.uint8:
+                raise ValueError("bit-packed syndromes must be uint8")
+            s = np.ascontiguousarray(s)
+        else:
+            s = np.ascontiguousarray((s.astype(np.int64) & 1).astype(np.uint8)) if s.dtype != np.uint8 else np.ascontiguousarray(s)
+        return self._decode_host(s, want_llr=return_llr, want_all=return_all, out=out, packed=packed)
 
     # ------------------------------------------------------------------ harness step on the device
     def set_error_channel(self, pz=None, px=None, py=None):
@@ -395,22 +457,37 @@ class BpOsdDecoder:
         ix = np.ascontiguousarray(l.indices, dtype=np.int32)
         self._check(_capi.load().bposd_set_logicals(self._h, _ptr(ip), _ptr(ix), int(l.shape[0])))
 
-    def sample_syndromes(self, seed: int, shot0: int, B: int, sector: int = 0, return_errors: bool = True):
-        """Device sampler + syndrome kernel; returns CUDA tensors (errors[B, n] or None, syndromes[B, m])."""
+    def sample_syndromes(self, seed: int, shot0: int, B: int, sector: int = 0, return_errors: bool = True,
+                         packed: bool = False):
+        """Device sampler + syndrome kernel; returns CUDA tensors (errors[B, n] or None, syndromes[B, m] -- or the
+        bit-packed syndromes[B, ceil(m/8)] with ``packed``)."""
         import torch
         dev = torch.device("cuda", self.device)
         err = torch.empty((B, self.n), dtype=torch.uint8, device=dev) if return_errors else None
-        syn = torch.empty((B, self.m), dtype=torch.uint8, device=dev)
+        syn = torch.empty((B, (self.m + 7) // 8 if packed else self.m), dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        self._check(_capi.load().bposd_sample_syndromes(self._h, int(seed), int(shot0), int(B), int(sector),
-                                                        err.data_ptr() if err is not None else None,
-                                                        syn.data_ptr(), stream))
+        fn = _capi.load().bposd_sample_syndromes_packed if packed else _capi.load().bposd_sample_syndromes
+        self._check(fn(self._h, int(seed), int(shot0), int(B), int(sector), err.data_ptr() if err is not None else None,
+                       syn.data_ptr(), stream))
         return err, syn
+
+    def _check_u8_cuda(self, t, name):
+        """The kernels read B*n bytes through the raw pointer: anything but a uint8 [B, n] tensor on this decoder's GPU
+        would be an out-of-bounds or illegal-address read, so it is a Python error here."""
+        import torch
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.dim() == 2 and t.shape[1] == self.n):
+            raise ValueError(f"{name} must be a CUDA uint8 tensor of shape [B, {self.n}]")
+        if t.device.index != self.device:
+            raise ValueError(f"{name} lives on cuda:{t.device.index}, decoder on cuda:{self.device}")
 
     def logical_check(self, errors, decodings, return_weight: bool = False):
         """fail[b] = ((L @ (e ^ d)) % 2).any() on the device for CUDA uint8 tensors [B, n];
         with ``return_weight`` also the Hamming weight of every residual (int32 [B])."""
         import torch
+        self._check_u8_cuda(errors, "errors")
+        self._check_u8_cuda(decodings, "decodings")
+        if errors.shape != decodings.shape:
+            raise ValueError("errors and decodings must have the same shape")
         B = errors.shape[0]
         fail = torch.empty(B, dtype=torch.uint8, device=errors.device)
         wt = torch.empty(B, dtype=torch.int32, device=errors.device) if return_weight else None
@@ -424,6 +501,7 @@ class BpOsdDecoder:
         """Per-shot priors / OSD weights of this decoder given the other sector's decoding (CUDA uint8 [B, n]).
         Returns (priors [B, n] in the decoder's precision, weights [B, n] float64) for ``decode_batch``."""
         import torch
+        self._check_u8_cuda(first_decoding, "first_decoding")
         d = first_decoding.contiguous()
         B = d.shape[0]
         p0 = np.ascontiguousarray(probs_if0, dtype=np.float64)
@@ -456,9 +534,13 @@ class BpOsdDecoder:
 
 
 class bposd_decoder(BpOsdDecoder):
-    """Legacy-signature class the reference re-exports (src/bposd/__init__.py:1; README.md:176-187)."""
+    """Legacy-signature class the reference re-exports (src/bposd/__init__.py:1; README.md:176-187).
 
-    def __init__(self, parity_check_matrix, error_rate=None, max_iter=0, bp_method="ms",
+    Defaults follow the v1 signature as far as it can be recalled (``bp_method`` 0 = product-sum, ``osd_order`` -1);
+    both reference call sites pass ``bp_method``, ``osd_method`` and ``osd_order`` explicitly (README.md:183-186;
+    css_decode_sim.py:448-451), so the defaults are never on the reference's path."""
+
+    def __init__(self, parity_check_matrix, error_rate=None, max_iter=0, bp_method="ps",
                  ms_scaling_factor=1.0, channel_probs=(None,), osd_order=-1, osd_method="osd0",
                  input_vector_type="syndrome", **kw):
         okey = str(osd_method).lower()

@@ -72,3 +72,18 @@ def all_reduce_vector(vec, min_slots=(), group=None, device=None) -> np.ndarray:
 def all_reduce_counters(counters, group=None, device=None) -> np.ndarray:
     """The path's single collective: the counter vector of ``sample_and_decode`` (slot 7 is a minimum)."""
     return all_reduce_vector(counters, min_slots=(MIN_SLOT,), group=group, device=device)
+
+
+def broadcast_from_rank0(value: int, group=None, device=None) -> int:
+    """Every rank returns rank 0's integer (the run's Philox seed, a stop decision...).  A no-op without an
+    initialised process group."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64)
+    if dist.get_backend(group) == "nccl":
+        t = t.to(torch.device("cuda", device) if isinstance(device, int) else (device or torch.device("cuda", torch.cuda.current_device())))
+    dist.broadcast(t, src=0, group=group)
+    return int(t.item())

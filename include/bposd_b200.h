@@ -64,7 +64,7 @@ typedef struct {
     int32_t bp_kernel;              /* 0 generic/global, 1 generic/smem, 2 in-place smem, 3 cluster DSMEM */
     int32_t bp_threads, bp_ctas_per_sm, bp_smem_bytes;
     int32_t osd_threads, osd_smem_bytes, sm_count;
-    int32_t osd_variant;            /* 3 panel kernel, 1 T-matrix kernel, 2 HBM-resident OSD-0 kernel, 0 OSD unsupported */
+    int32_t osd_variant;            /* 3 register kernel, 1 shared-memory kernel, 2 HBM-resident OSD-0 kernel, 0 OSD unsupported */
     int32_t bp_layout_excess;       /* kernel 2: shared-memory wavefronts per bit sweep above the conflict-free count;
                                        kernel 3: edges whose bit and check live in different CTAs, per mille */
     int32_t bp_cluster_size;        /* CTAs per cluster of kernel 3, else 1 */
@@ -122,6 +122,19 @@ int bposd_decode_host(bposd_t *h, const uint8_t *h_syndromes, int64_t B, uint8_t
                       uint8_t *h_osd0, uint8_t *h_bp, void *h_llr, uint8_t *h_converge,
                       int32_t *h_iter);
 
+/* Bit-packed forms of the two decode entry points (BASELINE.json north_star: "bit-packed H e mod 2 syndrome kernel").
+ * A syndrome row is ceil(m/8) bytes, a decoding row ceil(n/8) bytes, bit i%8 of byte i/8 = entry i -- the layout of
+ * numpy.packbits(x, axis=1, bitorder="little"); the reference forms both as byte arrays (`hz @ error % 2`,
+ * css_decode_sim.py:173-201; `osdw_decoding`, README.md:202), which is 8x the PCIe traffic the path needs.
+ * d_osdw / d_osd0 / d_bp of `out` (resp. the h_*_bits arguments) are packed, LLRs, converge flags and iteration
+ * counts are as in the byte forms.  The BP kernels read the packed syndromes directly; the decodings are packed by a
+ * streaming kernel before they leave the device. */
+int bposd_decode_batch_packed(bposd_t *h, const uint8_t *d_syndrome_bits, int64_t B, const bposd_out_t *out,
+                              const void *d_priors_per_shot, const double *d_weights_per_shot, void *stream);
+int bposd_decode_host_packed(bposd_t *h, const uint8_t *h_syndrome_bits, int64_t B, uint8_t *h_osdw_bits,
+                             uint8_t *h_osd0_bits, uint8_t *h_bp_bits, void *h_llr, uint8_t *h_converge,
+                             int32_t *h_iter);
+
 /* Device-side restatement of the harness step `_generate_error` + `H @ e % 2`
  * (css_decode_sim.py:465-498,173-201): Philox4x32-10, counter (j/4, 0, shot_lo, shot_hi),
  * key = seed, one 32-bit uniform r per qubit; r < t1 -> Z, t1 <= r < t2 -> X, t2 <= r < t3 -> Y
@@ -132,6 +145,9 @@ int bposd_set_channel_thresholds(bposd_t *h, const uint32_t *h_t1, const uint32_
                                  const uint32_t *h_t3);
 int bposd_sample_syndromes(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector,
                            uint8_t *d_errors, uint8_t *d_syndromes, void *stream);
+/* Same, syndromes written bit-packed ([B, ceil(m/8)], layout as above); d_errors stays one byte per qubit. */
+int bposd_sample_syndromes_packed(bposd_t *h, uint64_t seed, uint64_t shot0, int64_t B, int32_t sector,
+                                  uint8_t *d_errors, uint8_t *d_syndrome_bits, void *stream);
 
 /* Logical operators for the failure check (css_decode_sim.py:257-272): CSR, K rows. */
 int bposd_set_logicals(bposd_t *h, const int32_t *h_indptr, const int32_t *h_indices, int32_t K);
@@ -179,14 +195,17 @@ int bposd_get_stats(const bposd_t *h, bposd_stats_t *stats);
 int bposd_set_tuning(bposd_t *h, int32_t bp_kernel_plus1, int32_t bp_threads, int64_t workspace_bytes);
 /* Measured INT32 logic-op (LOP3) rate of the device in ops/s: the denominator of the OSD roofline. */
 int bposd_int32_peak(bposd_t *h, double *ops_per_s);
+/* Measured shared-memory bandwidth of the device in bytes/s (conflict-free 16-byte LDS + STS in equal parts, the access
+ * mix of the in-place BP kernels): the denominator of the BP roofline. */
+int bposd_smem_peak(bposd_t *h, double *bytes_per_s);
 /* Thread-block-cluster size of BP kernel variant 3 (messages split over the shared memory of 2, 4, 8 or
  * 16 CTAs, reached through distributed shared memory); 0 = smallest size that fits. */
 int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size);
-/* OSD kernel variant: 0 automatic, 1 T-matrix kernel (m x m row-operation matrix in shared memory, one
- * sweep per pivot; OSD-0/E/CS; the default when it fits), 3 panel kernel (pivot-block multiplier masks in
- * shared memory, left-looking replay with four-Russians tables; OSD-0/E/CS; same results, currently slower),
- * 2 HBM-resident left-looking kernel (OSD-0 only; chosen automatically when neither fits in shared memory,
- * BASELINE config 5).  workspace_bytes > 0 caps the HBM workspace
+/* OSD kernel variant: 0 automatic; 3 register kernel (the m x m row-operation matrix in registers, warp-specialised
+ * resolver / updater pipeline with one barrier per 16 sorted columns; OSD-0/E/CS; the default for m <= 1024);
+ * 1 shared-memory kernel (the same matrix in shared memory, one sweep and two barriers per pivot; OSD-0/E/CS; the
+ * fall-back for larger m while the matrix fits); 2 HBM-resident left-looking kernel (OSD-0 only; chosen
+ * automatically when nothing fits in shared memory, BASELINE config 5).  workspace_bytes > 0 caps the HBM workspace
  * of variant 2 (ceil(n/32) * m * 4 bytes per concurrently processed failed shot). */
 int bposd_set_osd_variant(bposd_t *h, int32_t variant, int64_t workspace_bytes);
 const char *bposd_last_error(const bposd_t *h);

@@ -104,3 +104,24 @@ def test_product_does_not_import_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "bposd_oracle" not in txt and "libbposd_oracle" not in txt, f
+
+
+def test_pack_unpack_bits_round_trip():
+    """Layout of the packed interfaces: bit i%8 of byte i/8 = entry i (numpy.packbits, bitorder="little")."""
+    import torch
+    from bp_osd_b200 import pack_bits, unpack_bits
+    rng = np.random.default_rng(3)
+    for k in (1, 7, 8, 9, 41, 961, 1922):
+        a = (rng.random((5, k)) < 0.4).astype(np.uint8)
+        p = pack_bits(a)
+        assert p.shape == (5, (k + 7) // 8) and p.dtype == np.uint8
+        assert (unpack_bits(p, k) == a).all()
+        assert all(((p[b, i >> 3] >> (i & 7)) & 1) == a[b, i] for b in range(5) for i in range(0, k, max(1, k // 9)))
+        pt = pack_bits(torch.from_numpy(a))
+        assert (pt.numpy() == p).all() and (unpack_bits(pt, k).numpy() == a).all()
+
+
+def test_decoder_rejects_misspelled_keywords_without_a_gpu():
+    from bp_osd_b200 import BpOsdDecoder
+    with pytest.raises(TypeError):
+        BpOsdDecoder(np.eye(3, dtype=np.uint8), error_rate=0.1, max_itre=3)

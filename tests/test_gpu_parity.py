@@ -666,3 +666,70 @@ def test_latency_path_small_host_batches(torch_cuda, oracle_mod, cfg_codes, cfg,
             assert d.converge == bool(ref["converge"][i]) and d.iter == int(ref["iter"][i])
         else:
             assert not ((H @ out) % 2 != syn[i]).any()
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_bit_packed_io_matches_byte_io(torch_cuda, oracle_mod, cfg_codes, precision):
+    """`packed=True` (bit-packed syndromes in, bit-packed decodings out: bposd_decode_batch_packed /
+    bposd_decode_host_packed / bposd_sample_syndromes_packed) gives exactly the bits of the byte-per-bit interface, on the
+    device path, the chunked host pipeline, the small-batch staging path and the single-shot latency path."""
+    from bp_osd_b200 import BpOsdDecoder, pack_bits, unpack_bits
+    torch = torch_cuda
+    code = cfg_codes(2)
+    H = code.hz
+    m, n = H.shape
+    kw = dict(max_iter=6, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=5)
+    d = BpOsdDecoder(H, error_rate=0.07, precision=precision, **kw)
+    d.set_error_channel(px=0.07)
+    # sampler: packed syndromes are the packed form of the byte syndromes of the same shots
+    e1, s_bytes = d.sample_syndromes(11, 1000, 40000)
+    e2, s_bits = d.sample_syndromes(11, 1000, 40000, packed=True)
+    assert s_bits.shape == (40000, (m + 7) // 8)
+    assert (e1 == e2).all() and (unpack_bits(s_bits, m) == s_bytes).all() and (pack_bits(s_bytes) == s_bits).all()
+    # device path
+    ref = d.decode_batch(s_bytes)
+    st_ref = d.stats()
+    got = d.decode_batch(s_bits, packed=True)
+    assert got.packed and got.osdw_decoding.shape == (40000, (n + 7) // 8)
+    for k in ("osdw_decoding", "osd0_decoding", "bp_decoding"):
+        assert (unpack_bits(getattr(got, k), n) == getattr(ref, k)).all(), k
+    assert (got.converge == ref.converge).all() and (got.iter == ref.iter).all()
+    assert torch.equal(got.log_prob_ratios, ref.log_prob_ratios)
+    assert d.stats()["osd_invocations"] == st_ref["osd_invocations"] > 1000
+    if precision == 64:
+        o = oracle_mod.OracleDecoder(H, error_rate=0.07, **kw).decode_batch(s_bytes[:3000].cpu().numpy())
+        assert (unpack_bits(got.osdw_decoding[:3000], n).cpu().numpy() == o["osdw"]).all()
+    # host paths: 40 000 shots take the double-buffered pipeline, 2 000 the staging block, 5 the latency kernel
+    hb, hp = s_bytes.cpu().numpy(), s_bits.cpu().numpy()
+    for B in (40000, 2000, 5, 1):
+        r = d.decode_batch(hp[:B], packed=True)
+        for k in ("osdw_decoding", "osd0_decoding", "bp_decoding"):
+            assert (unpack_bits(getattr(r, k), n) == getattr(ref, k)[:B].cpu().numpy()).all(), (B, k)
+        assert (r.converge == ref.converge[:B].cpu().numpy()).all() and (r.iter == ref.iter[:B].cpu().numpy()).all()
+        assert np.array_equal(r.log_prob_ratios, ref.log_prob_ratios[:B].cpu().numpy())
+        r2 = d.decode_batch(hp[:B], packed=True, return_llr=False, return_all=False)
+        assert r2.osd0_decoding is None and (r2.osdw_decoding == r.osdw_decoding).all()
+    with pytest.raises(ValueError):
+        d.decode_batch(hb[:10], packed=True)       # byte syndromes are not [B, ceil(m/8)]
+    with pytest.raises(ValueError):
+        d.decode_batch(hb[:10], priors=ref.log_prob_ratios[:10])   # per-shot priors need CUDA syndromes
+
+
+def test_tensor_arguments_are_validated(torch_cuda, cfg_codes):
+    """logical_check / channel_update hand raw pointers to kernels that read B*n bytes: wrong dtype, shape or residency is
+    a ValueError, never an out-of-bounds read."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    code = cfg_codes(1)
+    d = BpOsdDecoder(code.hz, error_rate=0.05, osd_method="osd0")
+    d.set_logicals(code.lz)
+    n = code.hz.shape[1]
+    good = torch.zeros((4, n), dtype=torch.uint8, device="cuda")
+    assert not d.logical_check(good, good).any()
+    for bad in (good.to(torch.int64), good.cpu(), good[:, :-1], good[0]):
+        with pytest.raises(ValueError):
+            d.logical_check(bad, good)
+        with pytest.raises(ValueError):
+            d.channel_update(bad, np.full(n, 0.1), np.full(n, 0.2))
+    with pytest.raises(ValueError):
+        d.logical_check(good, good[:2])

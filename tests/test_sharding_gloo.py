@@ -71,6 +71,14 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     start, count = sr(TOTAL, rank, world)
     total = all_reduce_counters(_counters_for(start, count))
+    # the two rank-0 decisions of the harness (css_decode_sim): the Philox seed of a run that draws its own, and the
+    # "save interval elapsed" flag that rides in a spare counter slot -- every rank must end up with rank 0's view
+    from bp_osd_b200.sharding import all_reduce_vector, broadcast_from_rank0
+    seed = broadcast_from_rank0(1000 + rank)
+    flag = np.zeros(8, dtype=np.int64)
+    flag[7] = 1 if rank == 0 else 0
+    gate = int(all_reduce_vector(flag, min_slots=(6,))[7])
+    total = np.concatenate([total, [seed, gate]])
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, total.tolist()))
@@ -90,5 +98,7 @@ def test_two_rank_counters_equal_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     want = _counters_for(0, TOTAL).tolist()
+    assert got[0][8:] == [1000, 1] and got[1][8:] == [1000, 1]   # rank 0's seed and gate flag on both ranks
+    got = {r: v[:8] for r, v in got.items()}
     assert got[0] == want and got[1] == want
     assert want[0] == TOTAL and 0 < want[4] <= TOTAL
