@@ -23,7 +23,11 @@ DBL_MAX = sys.float_info.max
 
 
 class SlowDecoder:
-    def __init__(self, h, probs, max_iter, bp_method, ms_scaling_factor, osd_method, osd_order):
+    def __init__(self, h, probs, max_iter, bp_method, ms_scaling_factor, osd_method, osd_order, tanh=None, log=None):
+        # tanh / log: the product-sum functions (default: the host libm, as ldpc calls them; the goldens pass the portable
+        # functions of include/bposd_math.h through oracle.oracle.lib() so that both restatements agree bit for bit)
+        self._tanh = tanh or math.tanh
+        self._log = log or (lambda x: float(np.log(np.float64(x))))
         h = sp.csr_matrix(h).astype(np.uint8)
         h.data %= 2
         h.eliminate_zeros()
@@ -56,14 +60,14 @@ class SlowDecoder:
                     t = 1.0
                     for j in self.rows[i]:
                         c2b[(i, j)] = t
-                        t *= math.tanh(b2c[(i, j)] / 2)
+                        t *= self._tanh(b2c[(i, j)] / 2)
                     t = 1.0
                     for j in reversed(self.rows[i]):
                         v = c2b[(i, j)] * t
                         sgn = -1.0 if synd[i] else 1.0
                         with np.errstate(divide="ignore", invalid="ignore"):
-                            c2b[(i, j)] = float(sgn * np.log(np.float64(1 + v) / np.float64(1 - v)))
-                        t *= math.tanh(b2c[(i, j)] / 2)
+                            c2b[(i, j)] = float(sgn * self._log(float(np.float64(1 + v) / np.float64(1 - v))))
+                        t *= self._tanh(b2c[(i, j)] / 2)
             else:
                 alpha = (1.0 - 2.0 ** (-it)) if self.alpha0 == 0.0 else self.alpha0
                 for i in range(m):

@@ -17,7 +17,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from bp_osd_b200 import codes  # noqa: E402
-from oracle.oracle import OracleDecoder  # noqa: E402
+from oracle.oracle import OracleDecoder, lib as oracle_lib  # noqa: E402
 from oracle.slow_ref import SlowDecoder  # noqa: E402
 
 CASES = {
@@ -25,13 +25,23 @@ CASES = {
     "d5_ms625_e8": dict(cfg=1, p=0.10, shots=200, kw=dict(max_iter=5, bp_method="ms", ms_scaling_factor=0.625, osd_method="osd_e", osd_order=8)),
     "hgp400_ms_cs7": dict(cfg=2, p=0.06, shots=40, kw=dict(max_iter=40, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=7)),
     "hgp400_ms_osd0": dict(cfg=2, p=0.07, shots=40, kw=dict(max_iter=25, bp_method="ms", ms_scaling_factor=0.9, osd_method="osd0", osd_order=0)),
+    # the bench code with the reference harness's default scaling (css_decode_sim.py:71): about half the shots reach OSD-CS
+    "hgp1922_ms625_cs7": dict(cfg=3, p=0.05, shots=24, kw=dict(max_iter=60, bp_method="ms", ms_scaling_factor=0.625, osd_method="osd_cs", osd_order=7)),
+    # product-sum + OSD-E 10 (tanh / log of include/bposd_math.h in the oracle and in slow_ref alike)
+    "lp882_ps_e10": dict(cfg=4, p=0.06, shots=24, kw=dict(max_iter=30, bp_method="ps", ms_scaling_factor=0, osd_method="osd_e", osd_order=10)),
+    # the large-H code (H beyond 228 KB): two shots that do not converge in 6 iterations -> HBM-resident OSD-0; the second
+    # restatement is pure Python and is skipped at this size 
+    "hgp40k_ms_osd0": dict(cfg=5, p=0.03, shots=2, slow=False, kw=dict(max_iter=6, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)),
 }
 
 
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    only = set(sys.argv[1:])  # optional: regenerate only the named cases
     for name, c in CASES.items():
-        H = codes.config_code(c["cfg"]).hz
+        if only and name not in only:
+            continue
+        H = codes.config_code(c["cfg"], logicals=False).hz
         n = H.shape[1]
         rng = np.random.default_rng(20251018)
         e = (rng.random((c["shots"], n)) < c["p"]).astype(np.uint8)
@@ -40,13 +50,14 @@ def main():
         o = OracleDecoder(H, error_rate=c["p"], **kw)
         ref = o.decode_batch(s)
         slow = SlowDecoder(H, [c["p"]] * n, kw["max_iter"], kw["bp_method"], kw["ms_scaling_factor"],
-                           "osd0" if kw["osd_method"] == "osd0" else kw["osd_method"], kw["osd_order"])
-        for b in range(c["shots"]):
+                           "osd0" if kw["osd_method"] == "osd0" else kw["osd_method"], kw["osd_order"],
+                           tanh=oracle_lib().oracle_math_tanh, log=oracle_lib().oracle_math_log)
+        for b in range(c["shots"] if c.get("slow", True) else 0):
             x = slow.decode(s[b])
             assert (np.array(x) == ref["osdw"][b]).all(), (name, b)
             assert (np.array(slow.osd0_decoding) == ref["osd0"][b]).all(), (name, b)
             assert (np.array(slow.bp_decoding) == ref["bp"][b]).all(), (name, b)
-            assert (np.array(slow.llr) == ref["llr"][b]).all(), (name, b)
+            assert np.array_equal(np.array(slow.llr), ref["llr"][b], equal_nan=True), (name, b)
             assert slow.converge == bool(ref["converge"][b]) and slow.iter == ref["iter"][b], (name, b)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), cfg=c["cfg"], p=c["p"],
                             kw=np.array(repr(kw)), syndromes=np.packbits(s, axis=1), m=H.shape[0],
