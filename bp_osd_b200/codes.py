@@ -20,6 +20,11 @@ __all__ = [
     "lifted_product_b1",
     "config_code",
     "load_alist_txt",
+    "save_dense_txt",
+    "save_code",
+    "load_code",
+    "example_seed",
+    "regenerate_example_codes",
 ]
 
 
@@ -132,11 +137,104 @@ _MKMN_16_4_6_ROWS = (
 )
 
 
-def mkmn_16_4_6() -> np.ndarray:
-    h = np.zeros((12, 16), dtype=np.uint8)
-    for i, cols in enumerate(_MKMN_16_4_6_ROWS):
+# the other two (3,4)-regular seeds of examples/codes/classical_seed_codes (mkmn_20_5_8.txt, mkmn_24_6_10.txt): the inputs
+# from which generate_codes.py:5-20 builds the [[625,25,8]] and [[900,36,10]] codes whose hx/hz files the reference
+# lists in .MISSING_LARGE_BLOBS:1-4.  Row supports, as above (data, not code).
+_MKMN_20_5_8_ROWS = (
+    (3, 4, 17, 19), (1, 6, 14, 19), (5, 9, 15, 16), (2, 6, 13, 16), (8, 9, 11, 18), (4, 10, 14, 15), (7, 9, 12, 17),
+    (1, 2, 3, 12), (5, 8, 12, 14), (7, 10, 11, 16), (3, 5, 7, 18), (0, 11, 13, 19), (0, 4, 6, 18), (0, 2, 8, 15),
+    (1, 10, 13, 17),
+)
+_MKMN_24_6_10_ROWS = (
+    (1, 14, 15, 18), (6, 7, 15, 22), (3, 8, 19, 23), (2, 11, 13, 23), (9, 11, 16, 19), (5, 8, 17, 22), (0, 1, 7, 16),
+    (5, 12, 13, 14), (0, 10, 18, 23), (4, 16, 21, 22), (1, 4, 6, 11), (3, 7, 14, 17), (8, 10, 20, 21), (0, 4, 19, 20),
+    (2, 5, 6, 10), (9, 13, 18, 21), (2, 12, 15, 17), (3, 9, 12, 20),
+)
+_SEEDS = {"mkmn_16_4_6": (_MKMN_16_4_6_ROWS, 16), "mkmn_20_5_8": (_MKMN_20_5_8_ROWS, 20), "mkmn_24_6_10": (_MKMN_24_6_10_ROWS, 24)}
+
+
+def example_seed(name: str) -> np.ndarray:
+    """One of the reference's classical seed codes by file stem ("mkmn_16_4_6", "mkmn_20_5_8", "mkmn_24_6_10")."""
+    rows, n = _SEEDS[name]
+    h = np.zeros((len(rows), n), dtype=np.uint8)
+    for i, cols in enumerate(rows):
         h[i, list(cols)] = 1
     return h
+
+
+def mkmn_16_4_6() -> np.ndarray:
+    return example_seed("mkmn_16_4_6")
+
+
+# ---- on-disk code formats (SURVEY.md section 8 row f3) ---------------------------------------------------------------
+def save_dense_txt(path, mat) -> None:
+    """Write a matrix the way the reference stores its example codes: ``np.savetxt`` of the dense matrix with the default
+    ``%.18e`` format (generate_codes.py:17-20; 1.9 MB for a 192 x 400 matrix).  Byte-identical to the shipped files."""
+    a = mat.toarray() if sp.issparse(mat) else np.asarray(mat)
+    np.savetxt(path, a.astype(np.float64))
+
+
+_CODE_KEYS = ("hx", "hz", "lx", "lz")
+
+
+def save_code(path, hx=None, hz=None, lx=None, lz=None, **meta) -> None:
+    """Compact form of a CSS code: one ``.npz`` holding every given matrix as CSR (``<name>_indptr``, ``<name>_indices``,
+    ``<name>_shape``; all entries are 1 over GF(2)) plus scalar metadata (``name``, ``N``, ``K``, ``D`` ...).
+    The [[400,16,6]] code takes 7 KB instead of the 4.2 MB of its four dense text files."""
+    out = {}
+    for key, mat in zip(_CODE_KEYS, (hx, hz, lx, lz)):
+        if mat is None:
+            continue
+        c = sp.csr_matrix(mat).astype(np.uint8)
+        c.data %= 2
+        c.eliminate_zeros()
+        c.sort_indices()
+        out[key + "_indptr"] = c.indptr.astype(np.int32)
+        out[key + "_indices"] = c.indices.astype(np.int32)
+        out[key + "_shape"] = np.asarray(c.shape, dtype=np.int64)
+    for k, v in meta.items():
+        out["meta_" + k] = np.asarray(v)
+    np.savez_compressed(path, **out)
+
+
+def load_code(path) -> dict:
+    """Read a code written by ``save_code`` (``.npz``) -- or, for a ``.txt`` path, one dense text matrix of the reference
+    (returned under the key ``"h"``).  Matrices come back as ``scipy.sparse.csr_matrix`` of uint8; metadata under its name."""
+    if str(path).endswith(".txt"):
+        return {"h": sp.csr_matrix(load_alist_txt(path))}
+    z = np.load(path)
+    out = {}
+    for key in _CODE_KEYS:
+        if key + "_indptr" in z.files:
+            ip, ix = z[key + "_indptr"], z[key + "_indices"]
+            out[key] = sp.csr_matrix((np.ones(ix.size, dtype=np.uint8), ix, ip), shape=tuple(int(x) for x in z[key + "_shape"]))
+    for f in z.files:
+        if f.startswith("meta_"):
+            v = z[f]
+            out[f[5:]] = v.item() if v.ndim == 0 else v
+    return out
+
+
+def regenerate_example_codes(out_dir, seeds=("mkmn_16_4_6", "mkmn_20_5_8", "mkmn_24_6_10"), dense_txt=True):
+    """What examples/codes/hgp_codes/generate_codes.py does, from the seeds kept in this module: ``hgp(seed,
+    compute_distance=True)`` + ``canonical_logicals()`` for each seed, written as ``hgp_<code_params>_{hx,hz,lx,lz}.txt``
+    (the reference's dense text, optional) and as one compact ``hgp_<code_params>.npz``.  Restores the four hx/hz files
+    the reference lists as missing (.MISSING_LARGE_BLOBS:1-4).  Returns the list of code_params strings."""
+    import os
+    from .hgp import hgp
+    os.makedirs(out_dir, exist_ok=True)
+    done = []
+    for name in seeds:
+        q = hgp(example_seed(name), compute_distance=True)
+        q.canonical_logicals()
+        params = q.code_params  # "(4,7)-[[400,16,6]]", the string the reference puts in its file names
+        base = os.path.join(out_dir, f"hgp_{params}")
+        if dense_txt:
+            for key, mat in (("hx", q.hx), ("hz", q.hz), ("lx", q.lx), ("lz", q.lz)):
+                save_dense_txt(f"{base}_{key}.txt", mat)
+        save_code(base + ".npz", q.hx, q.hz, q.lx, q.lz, name=f"hgp_{params}", N=q.N, K=q.K, D=q.D, seed=name)
+        done.append(params)
+    return done
 
 
 def config_code(cfg: int, logicals: bool = True):

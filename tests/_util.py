@@ -27,3 +27,29 @@ def random_syndromes(H, p, B, seed):
     e = (rng.random((B, H.shape[1])) < p).astype(np.uint8)
     s = np.asarray((H @ e.T) % 2, dtype=np.uint8).T.copy()
     return e, s
+
+
+# ---- the CPU oracle on all host cores (large parity samples) -----------------------------------
+_PW = {}
+
+
+def _par_init(H, p, kw):
+    from oracle.oracle import OracleDecoder
+    _PW["dec"] = OracleDecoder(H, error_rate=p, **kw)
+
+
+def _par_work(syn):
+    return _PW["dec"].decode_batch(syn, want_llr=_PW.get("llr", True))
+
+
+def oracle_decode_parallel(H, syn, p, kw, procs=None, chunk=None):
+    """OracleDecoder(H, error_rate=p, **kw).decode_batch(syn), the shots spread over `procs` forked workers."""
+    import multiprocessing as mp
+    from functools import partial
+    procs = procs or len(os.sched_getaffinity(0))
+    B = syn.shape[0]
+    chunk = chunk or max(1, min(2000, (B + 4 * procs - 1) // (4 * procs)))
+    parts = [syn[i:i + chunk] for i in range(0, B, chunk)]
+    with mp.get_context("fork").Pool(procs, initializer=partial(_par_init, H, p, kw)) as pool:
+        res = pool.map(_par_work, parts)
+    return {k: np.concatenate([r[k] for r in res]) for k in res[0]}

@@ -30,6 +30,14 @@ def main():
             assert a.shape == (int(K), int(N))
             out[f"{which}_{tag}"] = np.packbits(a, axis=1)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_hgp_logicals.npz"), **out)
+    # sha256 of every code file the reference ships (dense np.savetxt text, generate_codes.py:17-20): the on-disk format
+    # test (tests/test_host_codes.py::test_regenerated_code_files_match_the_shipped_ones) regenerates them byte for byte
+    import glob
+    import hashlib
+    import json
+    dig = {os.path.basename(f): hashlib.sha256(open(f, "rb").read()).hexdigest() for f in sorted(glob.glob(f"{REF}/hgp_codes/*.txt"))}
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_code_file_sha256.json"), "w") as fh:
+        json.dump(dig, fh, indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
