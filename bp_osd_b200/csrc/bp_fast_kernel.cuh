@@ -342,12 +342,14 @@ constexpr int kFastDummySlots = 8;
 constexpr int kFastZeroSlot = kFastDummySlots - 1; // irregular codes: the slot absent edges read, always 0.0
 
 template <typename real>
-static inline size_t fast_smem_bytes(const FastTables &t, int n, int m) {
+static inline size_t fast_smem_bytes(const FastTables &t, int n, int m, bool with_priors = true) {
     if (t.DC == 0) return (size_t)1 << 40;
     // the message array doubles as the staging area of the per-shot results ([n] reals + [n] bytes)
     size_t msgs = (std::max(((size_t)m * fast_row_stride(t.DC, (int)sizeof(real)) + kFastDummySlots) * sizeof(real), (size_t)n * (sizeof(real) + 1)) + 15) / 16 * 16;
     size_t meta = ((size_t)m * 4 + 15) / 16 * 16; // one 32-bit word per check (see the kernel)
-    size_t prior = ((size_t)n * sizeof(real) + 15) / 16 * 16; // copy of the priors when they are not uniform
+    // copy of the priors by thread position when they are not uniform (a uniform prior is one register: launches with
+    // uniform priors carve no such array, which is what lets a fourth CTA of the bench code fit on an SM)
+    size_t prior = with_priors ? ((size_t)n * sizeof(real) + 15) / 16 * 16 : 0;
     return msgs + meta + prior + 16;
 }
 
@@ -403,8 +405,54 @@ template <typename real> __device__ __forceinline__ real mag_min(real a, real b)
 // (`if (a < t) t = a`), which also reproduces its NaN propagation on shots whose sums overflowed.
 // (A shallower tree of compares for all-finite shots and two rows interleaved per thread were both built, verified
 // bit-exact and measured not faster: profiles/r03a_ab_probe.log, r03d_ab_probe.log.)
+// fp32 fast mode: sm_100a has a min-sum instruction -- min.xorsign.abs.f32 returns min(|a|, |b|) carrying sign(a) ^ sign(b)
+// (FMNMX with the xorsign modifier), so one instruction per prefix / suffix step yields the magnitude AND the sign product of
+// "all the other edges"; the fp64 form below needs DSETP + two selects per step plus separate sign-word arithmetic.
+#ifndef BPOSD_F32_XORSIGN
+#define BPOSD_F32_XORSIGN 1
+#endif
+__device__ __forceinline__ float min_xorsign_abs(float a, float b) {
+    float d;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
 template <typename real, int DC, bool REG>
 __device__ __forceinline__ void fast_check_compute(real (&v)[DC], real (&out)[DC], unsigned mt, real alpha, uint32_t alpha_w) {
+    if constexpr (sizeof(real) == 4 && BPOSD_F32_XORSIGN != 0 && DC > 1) {
+        float suf[DC];
+        suf[DC - 1] = v[DC - 1];
+#pragma unroll
+        for (int k = DC - 2; k >= 1; k--) suf[k] = min_xorsign_abs(v[k], suf[k + 1]);
+        float run = v[0];
+        out[0] = suf[1];
+#pragma unroll
+        for (int k = 1; k < DC - 1; k++) { out[k] = min_xorsign_abs(suf[k + 1], run); run = min_xorsign_abs(v[k], run); }
+        out[DC - 1] = run;
+        const float all_min = min_xorsign_abs(v[DC - 1], run);
+        if (fabsf(all_min) == 0.0f) {
+            // some message is +-0: "<= 0" counts +0 as negative, the sign bit does not -> exact path (as in the fp64 form)
+            int tot = (int)(mt >> 7);
+#pragma unroll
+            for (int k = 0; k < DC; k++) tot += ((sign_word(v[k]) >> 31) | (fabsf(v[k]) == 0.0f ? 1u : 0u)) ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < DC; k++) {
+                const int sg = tot + (((sign_word(v[k]) >> 31) | (fabsf(v[k]) == 0.0f ? 1u : 0u)) ? 1 : 0);
+                out[k] = fabsf(out[k]) * ((sg & 1) ? -alpha : alpha);
+            }
+        } else {
+            const float salpha = (mt & 0x80u) ? -alpha : alpha; // the syndrome bit flips every outgoing sign
+#pragma unroll
+            for (int k = 0; k < DC; k++) out[k] = out[k] * salpha;
+        }
+        if (!REG) {
+            const int deg = (mt >> 1) & 0x1f;
+#pragma unroll
+            for (int k = 0; k < DC; k++) out[k] = (k < deg) ? out[k] : real_max<real>();
+        }
+        (void)alpha_w;
+        return;
+    }
     // Magnitudes are never materialised: the compares take |a| < |b| and select the raw values, the final multiply
     // takes |min|, and sm_100a folds both into operand modifiers of DSETP / DMUL (FSETP / FMUL) -- 12 instructions
     // fewer per row of 6 than clearing the sign bits first.  Compare order and tie behaviour are the reference's.

@@ -66,6 +66,7 @@ struct bposd_handle {
     size_t scratch_bytes = 0;
     // launch geometry
     int bp_kernel = 1, bp_threads = 256, bp_ctas_per_sm = 1, bp_smem = 0, bp_grid = 0;
+    int bp_smem_uni = 0, bp_grid_uni = 0, bp_ctas_uni = 0; // fast kernel, launches with a uniform prior (no prior array in shared memory)
     int bp_geom = 1;                    // fast kernel geometry id (bp_fast_kernel.cuh: fast_geom)
     int lat_geom = -1, lat_threads = 0; // latency geometry of the fast kernel (-1: none; small host batches use it)
     long long lat_max_shots = 0;        // host batches up to this size take the latency path (0: disabled)
@@ -247,6 +248,12 @@ static int plan_geometry_t(bposd_handle *h) {
         if (threads * fast_vpt(n) < n) threads = fast_default_threads(n, m);
         CU_TRY(h, fast_set_smem_t<real>(h->fast, h->bp_geom, smem));
         CU_TRY(h, fast_occupancy_t<real>(h->fast, h->bp_geom, threads, smem, &occ));
+        {
+            const size_t smem_u = fast_smem_bytes<real>(h->fast, n, m, false);
+            int occ_u = 0;
+            CU_TRY(h, fast_occupancy_t<real>(h->fast, h->bp_geom, threads, smem_u, &occ_u));
+            h->bp_smem_uni = (int)smem_u; h->bp_ctas_uni = std::max(occ_u, 1); h->bp_grid_uni = h->bp_ctas_uni * h->sm_count;
+        }
         // latency geometry: one shot per SM, as many threads on it as the code has work for
         h->lat_geom = fast_geom(n, true);
         h->lat_threads = fast_default_threads_g(n, h->lat_geom, (int)rs);
@@ -580,7 +587,8 @@ extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
     info->max_iter = h->max_iter; info->bp_method = h->bp_method; info->osd_method = h->osd_method;
     info->osd_order = h->osd_order; info->precision = h->precision; info->device = h->device;
     info->bp_kernel = h->bp_kernel; info->bp_threads = h->bp_threads; info->bp_ctas_per_sm = h->bp_ctas_per_sm;
-    info->bp_smem_bytes = h->bp_smem; info->osd_threads = h->osd_threads; info->osd_smem_bytes = h->osd_smem;
+    info->bp_smem_bytes = h->bp_smem;
+    if (h->bp_kernel == 2 && h->uniform_prior) { info->bp_ctas_per_sm = h->bp_ctas_uni; info->bp_smem_bytes = h->bp_smem_uni; } info->osd_threads = h->osd_threads; info->osd_smem_bytes = h->osd_smem;
     info->sm_count = h->sm_count; info->ms_scaling_factor = h->alpha;
     info->osd_variant = !h->osd_supported ? 0 : (h->osd_large ? 2 : (h->osd_reg ? 3 : 1));
     if (h->osd_reg) { info->osd_threads = h->osdr_threads; info->osd_smem_bytes = h->osdr_smem; }
@@ -723,7 +731,11 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     if (h->bp_kernel == 3) {
         const int ncl = (int)std::min<long long>(Bc, h->clus_nclusters);
         CU_TRY(h, cluster_launch<real>(h->clus, a, ncl, h->bp_threads, (size_t)h->bp_smem, h->clus_flip_table, st));
-    } else if (h->bp_kernel == 2) fast_launch<real>(h->fast, h->bp_geom, a, grid, h->bp_threads, h->bp_smem, st);
+    } else if (h->bp_kernel == 2) {
+        if (a.uniform_prior) // no prior array in shared memory: smaller footprint, possibly one more CTA per SM
+            fast_launch<real>(h->fast, h->bp_geom, a, (int)std::min<long long>(Bc, h->bp_grid_uni), h->bp_threads, h->bp_smem_uni, st);
+        else fast_launch<real>(h->fast, h->bp_geom, a, grid, h->bp_threads, h->bp_smem, st);
+    }
     else if (h->bp_kernel == 1) bp_generic_kernel<real, true><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
     else bp_generic_kernel<real, false><<<grid, h->bp_threads, h->bp_smem, st>>>(a);
     CU_TRY(h, cudaGetLastError());
