@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libbposd_b200.so")
 _INC = os.path.join("..", "..", "include")
-HEADERS = ["bposd_kernels.cuh", "bp_fast_kernel.cuh", "bp_cluster_kernel.cuh", "osd_reg_kernel.cuh",
+HEADERS = ["bposd_kernels.cuh", "bp_fast_kernel.cuh", "bp_cluster_kernel.cuh", "osd_reg_kernel.cuh", "osd_cluster_kernel.cuh",
            os.path.join(_INC, "bposd_math.h"), os.path.join(_INC, "bposd_b200.h")]
 # headers each source actually includes (the object cache is keyed by their contents)
 DEPS = {"bposd_capi.cu": HEADERS,

@@ -1,19 +1,29 @@
 // bp_cluster_kernel.cuh -- min-sum BP for parity-check matrices whose messages exceed one SM's shared
 // memory (BASELINE config 5: 134 400 edges, 1.07 MB of fp64 messages): the in-place message array of
-// bp_fast_kernel is split over the CTAs of a thread-block cluster and the bit sweep reaches the other
-// CTAs' slices through distributed shared memory (ld/st/atom.shared::cluster).
+// bp_fast_kernel is split over the CTAs of a thread-block cluster, and the edges that cross CTAs are
+// exchanged through distributed shared memory in COALESCED blocks ("halo exchange").
 //
-//   * physical rows (checks) are partitioned over the CL CTAs of a cluster, rows_per_cta each; the check
-//     sweep is entirely local (the same fast_check_row as the single-CTA kernel, bit-exact in fp64);
-//   * bits are partitioned too (bits_per_cta each); the thread that owns a bit gathers / scatters its
-//     <= DV slots with 32-bit cluster-window addresses resolved once per CTA with `mapa`; the host
-//     partition pass (cluster_build) places bits and checks to keep as many edges CTA-local as it can;
-//   * one parity-mismatch bit per check, toggled with atom.shared::cluster.xor when a hard decision flips;
+//   * physical rows (checks) are partitioned over the CL CTAs of a cluster, rows_per_cta each, and so are the
+//     bits (bits_per_cta each); the host partition pass (cluster_build) places bits and checks to keep as many
+//     edges CTA-local as it can (config 5: 71 %);
+//   * an edge whose check lives in CTA A and whose bit lives in CTA B has TWO homes: its slot in the row of the
+//     check (in A) and an entry of B's mailbox.  The mailbox of B is ordered by (source CTA, source order), so
+//     the entries that A exchanges with B are contiguous in B;
+//   * the check sweep (fast_check_row, the single-CTA kernel's) and the bit sweep (fast_bit_sweep, likewise) only
+//     touch the CTA's own shared memory with plain LDS / STS; in between, A PUSHES the new check-to-bit values of
+//     its remote edges into the mailboxes (consecutive threads write consecutive remote addresses) and, after the
+//     bit sweep, PULLS the new bit-to-check values back into its rows (consecutive remote reads);
+//   * one parity-mismatch bit per check, toggled with red.shared::cluster.xor when a hard decision flips;
 //     every CTA votes with __syncthreads_and, the votes are exchanged through DSMEM and ride on the cluster
 //     barrier that separates the sweeps (two barrier.cluster per iteration);
 //   * persistent clusters pull shots from the same atomic queue as the other BP kernels.
-// A shot that needs all max_iter = n iterations costs tens of microseconds per iteration here instead
-// of the millisecond of the HBM-scratch kernel, which is what bounds config 5's tail.
+//
+// Why the exchange is blocked: ld/st.shared::cluster moves 32-byte sectors over the SM-to-SM crossbar (~20 B/clk
+// per SM).  The first version of this kernel let every bit gather / scatter its slots directly with 8-byte
+// ld/st.shared::cluster -- local slots included -- and ncu showed 28 sectors per warp request and 43 % of all
+// stall samples on the first use of a gathered value (profiles/r2f_cluster_hot_lines.txt): 1.3 TB/s of sector
+// traffic for 0.33 TB/s of payload.  Blocked, the crossbar carries each remote value once per direction in
+// fully used sectors, and 71 % of the edges never leave the SM.
 #pragma once
 #include "bp_fast_kernel.cuh"
 
@@ -24,7 +34,12 @@ namespace bposd {
 struct ClusterTables {
     int DC = 0, DV = 0, regular = 0;
     int CL = 0, rows_per_cta = 0, bits_per_cta = 0, elem_bytes = 0;
-    uint32_t *d_vslot = nullptr;  // [CL*bits_per_cta, DV] physical slot of the k-th edge of the bit at position q
+    int nbox_max = 0, nout_max = 0; // mailbox entries / exchange-list entries of the fullest CTA
+    uint32_t *d_vslot = nullptr;  // [CL*bits_per_cta, DV] slot (element index inside the owner CTA: row slots, then the mailbox) of the k-th edge of the bit at position q
+    uint32_t *d_flip = nullptr;   // [CL*bits_per_cta, DV] (CTA << 24 | local row) of that edge's check
+    uint32_t *d_xloc = nullptr;   // [CL, nout_max] exchange list: element index of the row slot in this CTA ...
+    uint32_t *d_xrem = nullptr;   // [CL, nout_max] ... and (CTA << 24 | element index) of its mailbox entry in the bit's CTA
+    int *d_nout = nullptr;        // [CL] entries of each CTA's exchange list
     uint8_t *d_cdeg = nullptr;    // [CL*rows_per_cta] degree of the check in physical row p (0: absent)
     uint32_t *d_row_of = nullptr; // [CL*rows_per_cta] original check of physical row p, BPC_NONE: absent
     uint32_t *d_bit_of = nullptr; // [CL*bits_per_cta] original bit at position q, BPC_NONE: absent
@@ -32,27 +47,44 @@ struct ClusterTables {
 };
 
 struct ClusterDev {
-    const uint32_t *vslot;
+    const uint32_t *vslot, *flip, *xloc, *xrem;
+    const int *nout;
     const uint8_t *cdeg;
     const uint32_t *row_of;
     const uint32_t *bit_of;
-    int rows_per_cta, bits_per_cta, CL;
+    int rows_per_cta, bits_per_cta, CL, nbox_max, nout_max;
     int flip_table; // 1: per-edge parity-flip descriptors live in shared memory (bits_per_cta * DV words)
 };
 
 static inline void cluster_free(ClusterTables &t) {
-    cudaFree(t.d_vslot); cudaFree(t.d_cdeg); cudaFree(t.d_row_of); cudaFree(t.d_bit_of);
-    t.d_vslot = nullptr; t.d_cdeg = nullptr; t.d_row_of = nullptr; t.d_bit_of = nullptr;
+    cudaFree(t.d_vslot); cudaFree(t.d_flip); cudaFree(t.d_xloc); cudaFree(t.d_xrem); cudaFree(t.d_nout);
+    cudaFree(t.d_cdeg); cudaFree(t.d_row_of); cudaFree(t.d_bit_of);
+    t.d_vslot = t.d_flip = t.d_xloc = t.d_xrem = nullptr; t.d_nout = nullptr;
+    t.d_cdeg = nullptr; t.d_row_of = nullptr; t.d_bit_of = nullptr;
     t.CL = 0;
 }
 
+// Shared-memory layout of one CTA, the same arithmetic on host and device.
+struct ClusterLayout { size_t o_meta, o_prior, o_xl, o_flip, total; };
+__host__ __device__ inline ClusterLayout cluster_layout(int RS, int elem, int rpc, int bpc, int nbox_max, int nout_max, int DV, int flip_table) {
+    ClusterLayout L;
+    auto al = [](size_t x) { return (x + 15) / 16 * 16; };
+    size_t o = al(((size_t)rpc * RS + nbox_max + kFastDummySlots) * elem); // row slots | mailbox | dummy / zero slots
+    L.o_meta = o; o = al(o + (size_t)rpc);                                 // one byte per check
+    L.o_prior = o; o = al(o + (size_t)bpc * elem);                         // priors by position (non-uniform channels)
+    L.o_xl = o; o = al(o + (size_t)(nout_max > 0 ? nout_max : 1) * 8);     // exchange list (byte offset, cluster address)
+    L.o_flip = o; o = al(o + (flip_table ? (size_t)bpc * DV * 4 : 0));     // parity-flip descriptors
+    L.total = o + 16;
+    return L;
+}
 template <typename real>
-static inline size_t cluster_smem_bytes(int DC, int rows_per_cta, int bits_per_cta, bool with_priors, int DV = 0) {
-    size_t msgs = ((size_t)rows_per_cta * fast_row_stride(DC, (int)sizeof(real)) * sizeof(real) + 15) / 16 * 16;
-    size_t meta = ((size_t)rows_per_cta + 15) / 16 * 16;
-    size_t prior = with_priors ? ((size_t)bits_per_cta * sizeof(real) + 15) / 16 * 16 : 0;
-    size_t flip = (size_t)bits_per_cta * DV * 4; // DV > 0: with the parity-flip descriptor table
-    return msgs + meta + prior + flip + 16;
+static inline size_t cluster_smem_need(const ClusterTables &t, int flip_table) {
+    return cluster_layout(fast_row_stride(t.DC, (int)sizeof(real)), (int)sizeof(real), t.rows_per_cta, t.bits_per_cta, t.nbox_max, t.nout_max, t.DV, flip_table).total;
+}
+// lower bound before the partition is known (no mailbox, no exchange list): filters cluster sizes that cannot fit
+template <typename real>
+static inline size_t cluster_smem_min(int DC, int rows_per_cta, int bits_per_cta) {
+    return cluster_layout(fast_row_stride(DC, (int)sizeof(real)), (int)sizeof(real), rows_per_cta, bits_per_cta, 0, 0, 0, 0).total;
 }
 
 // Host partition pass: alternate "every bit goes to the CTA that holds most of its checks" and "every check
@@ -107,31 +139,63 @@ static inline cudaError_t cluster_build(ClusterTables &t, int CL, int m, int n, 
     for (int i = 0; i < m; i++) prow[i] = best_row[i] * rpc + cnt[best_row[i]]++;
     std::fill(cnt.begin(), cnt.end(), 0);
     for (int j = 0; j < n; j++) pos[j] = best_bit[j] * bpc + cnt[best_bit[j]]++;
-    std::vector<uint32_t> vs((size_t)CL * bpc * t.DV, BPC_NONE), rowof((size_t)CL * rpc, BPC_NONE), bitof((size_t)CL * bpc, BPC_NONE);
+    // exchange lists: the remote edges of every CTA's rows, ordered by (CTA of the bit, row slot); the mailbox of a CTA
+    // is filled source CTA by source CTA in that order, so what two CTAs exchange is contiguous on the mailbox side
+    struct Rem { int B, loc, e; };
+    std::vector<std::vector<Rem>> out(CL);
+    for (int i = 0; i < m; i++)
+        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
+            const int A = best_row[i], B = best_bit[col_idx[e]];
+            if (A != B) out[A].push_back(Rem{B, (prow[i] % rpc) * RS + (e - row_ptr[i]), e});
+        }
+    std::vector<int> box_cnt(CL, 0), box_of_edge(std::max(E, 1), -1);
+    int nout_max = 0;
+    for (int A = 0; A < CL; A++) {
+        std::sort(out[A].begin(), out[A].end(), [](const Rem &x, const Rem &y) { return x.B != y.B ? x.B < y.B : x.loc < y.loc; });
+        for (const Rem &r : out[A]) box_of_edge[r.e] = box_cnt[r.B]++;
+        nout_max = std::max(nout_max, (int)out[A].size());
+    }
+    int nbox_max = 0;
+    for (int c = 0; c < CL; c++) nbox_max = std::max(nbox_max, box_cnt[c]);
+    nbox_max = (nbox_max + 1) & ~1; // keeps the areas behind the mailbox 16-byte aligned in fp64
+    t.nbox_max = nbox_max; t.nout_max = nout_max;
+    if ((size_t)rpc * RS + nbox_max + kFastDummySlots >= (1u << 24)) return cudaErrorInvalidValue;
+    std::vector<uint32_t> vs((size_t)CL * bpc * t.DV, BPC_NONE), fl((size_t)CL * bpc * t.DV, BPC_NONE), rowof((size_t)CL * rpc, BPC_NONE),
+        bitof((size_t)CL * bpc, BPC_NONE), xloc((size_t)CL * std::max(nout_max, 1), BPC_NONE), xrem((size_t)CL * std::max(nout_max, 1), BPC_NONE);
+    std::vector<int> nout(CL, 0);
     std::vector<uint8_t> cd((size_t)CL * rpc, 0);
     for (int i = 0; i < m; i++) { rowof[prow[i]] = (uint32_t)i; cd[prow[i]] = (uint8_t)(row_ptr[i + 1] - row_ptr[i]); }
     for (int j = 0; j < n; j++) {
         bitof[pos[j]] = (uint32_t)j;
         for (int q = col_ptr[j]; q < col_ptr[j + 1]; q++) {
             const int i = row_idx[q], e = csc_slot[q];
-            vs[(size_t)pos[j] * t.DV + (q - col_ptr[j])] = (uint32_t)(prow[i] * RS + (e - row_ptr[i]));
+            const size_t at = (size_t)pos[j] * t.DV + (q - col_ptr[j]);
+            vs[at] = (best_row[i] == best_bit[j]) ? (uint32_t)((prow[i] % rpc) * RS + (e - row_ptr[i])) : (uint32_t)(rpc * RS + box_of_edge[e]);
+            fl[at] = ((uint32_t)best_row[i] << 24) | (uint32_t)(prow[i] % rpc);
         }
     }
-    cudaError_t e = cudaMalloc((void **)&t.d_vslot, vs.size() * 4);
-    if (e != cudaSuccess) return e;
-    e = cudaMalloc((void **)&t.d_cdeg, cd.size());
-    if (e != cudaSuccess) return e;
-    e = cudaMalloc((void **)&t.d_row_of, rowof.size() * 4);
-    if (e != cudaSuccess) return e;
-    e = cudaMalloc((void **)&t.d_bit_of, bitof.size() * 4);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpy(t.d_vslot, vs.data(), vs.size() * 4, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpy(t.d_row_of, rowof.data(), rowof.size() * 4, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpy(t.d_bit_of, bitof.data(), bitof.size() * 4, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(t.d_cdeg, cd.data(), cd.size(), cudaMemcpyHostToDevice);
+    for (int A = 0; A < CL; A++) {
+        nout[A] = (int)out[A].size();
+        for (size_t x = 0; x < out[A].size(); x++) {
+            xloc[(size_t)A * nout_max + x] = (uint32_t)out[A][x].loc;
+            xrem[(size_t)A * nout_max + x] = ((uint32_t)out[A][x].B << 24) | (uint32_t)(rpc * RS + box_of_edge[out[A][x].e]);
+        }
+    }
+    auto up = [](auto **dst, const auto &src) -> cudaError_t {
+        using T = typename std::remove_reference<decltype(src)>::type::value_type;
+        cudaError_t e = cudaMalloc((void **)dst, std::max<size_t>(src.size(), 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        return src.empty() ? cudaSuccess : cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+    };
+    cudaError_t e;
+    if ((e = up(&t.d_vslot, vs)) != cudaSuccess) return e;
+    if ((e = up(&t.d_flip, fl)) != cudaSuccess) return e;
+    if ((e = up(&t.d_xloc, xloc)) != cudaSuccess) return e;
+    if ((e = up(&t.d_xrem, xrem)) != cudaSuccess) return e;
+    if ((e = up(&t.d_nout, nout)) != cudaSuccess) return e;
+    if ((e = up(&t.d_cdeg, cd)) != cudaSuccess) return e;
+    if ((e = up(&t.d_row_of, rowof)) != cudaSuccess) return e;
+    return up(&t.d_bit_of, bitof);
 }
 
 // ---- distributed-shared-memory primitives -------------------------------------------------------
@@ -154,7 +218,7 @@ __device__ __forceinline__ void st_dsmem_u32(uint32_t a, uint32_t v) { asm volat
 __device__ __forceinline__ void st_dsmem_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 __device__ __forceinline__ void xor_dsmem_u32(uint32_t a, uint32_t v) { asm volatile("red.shared::cluster.xor.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-// Register-frugal form of the check update (row a4) for CTAs of up to 1024 threads (64 registers each):
+// Register-frugal form of the check update (row a4) for CTAs of more than 640 threads (64 registers each):
 // pass 1 streams the row once for (smallest, second smallest, position of the smallest, sign parity), pass 2
 // streams it again and overwrites every slot with "minimum over the other edges" = second smallest at the
 // position of the smallest, smallest elsewhere -- the same values as the prefix/suffix form of
@@ -193,46 +257,53 @@ __device__ __forceinline__ void cluster_check_row(real *row, unsigned mt, real a
     }
 }
 
-// MAXT (a multiple of 128 >= blockDim.x) sets the register budget: 65536 / MAXT per thread, so that the per-thread
-// slot addresses never spill -- a spill costs an L2 round trip per iteration here, because barrier.cluster
-// invalidates L1.
+// MAXT (a multiple of 128 >= blockDim.x) sets the register budget: 65536 / MAXT per thread.  Up to 640 threads (96+
+// registers) the check update is the single-CTA kernel's prefix/suffix form (fewer instructions, a row in registers);
+// bigger CTAs fall back to the two-pass form above.
+#ifndef BPOSD_CLUSTER_FASTROW_MAXT
+#define BPOSD_CLUSTER_FASTROW_MAXT 640
+#endif
 template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
 __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, ClusterDev t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int m = a.g.m, n = a.g.n;
-    const int tid = threadIdx.x, T = blockDim.x;
+    const int n = a.g.n;
+    const int tid = threadIdx.x;
+    int T;
+    asm volatile("mov.u32 %0, %%ntid.x;" : "=r"(T));
     const int rpc = t.rows_per_cta, bpc = t.bits_per_cta, CL = t.CL;
     const uint32_t rank = cluster_ctarank();
-    constexpr int RS = fast_row_stride(DC, (int)sizeof(real));                                 // row stride in elements
-    real *msg = reinterpret_cast<real *>(smem_raw);                                            // [rpc * RS] this CTA's rows
-    uint8_t *meta = smem_raw + ((size_t)rpc * RS * sizeof(real) + 15) / 16 * 16;               // bit0 mismatch, bits1-5 degree, bit7 syndrome
-    real *prior_s = reinterpret_cast<real *>(meta + ((size_t)rpc + 15) / 16 * 16);             // [bpc] priors by position (non-uniform only)
-    uint32_t *flip_desc = reinterpret_cast<uint32_t *>(prior_s + ((size_t)bpc * sizeof(real) + 15) / 16 * 16 / sizeof(real)); // [bpc * DV]
+    constexpr int RS = fast_row_stride(DC, (int)sizeof(real)); // row stride in elements
+    const ClusterLayout L = cluster_layout(RS, (int)sizeof(real), rpc, bpc, t.nbox_max, t.nout_max, DV, t.flip_table);
+    const unsigned nslot = (unsigned)rpc * RS + (unsigned)t.nbox_max;      // row slots, then the mailbox; dummy / zero slots follow
+    real *msg = reinterpret_cast<real *>(smem_raw);
+    uint8_t *meta = smem_raw + L.o_meta;                                   // bit0 mismatch, bits1-5 degree, bit7 syndrome
+    real *prior_s = reinterpret_cast<real *>(smem_raw + L.o_prior);        // [bpc] priors by position (non-uniform only)
+    uint2 *xl = reinterpret_cast<uint2 *>(smem_raw + L.o_xl);              // [nout] (byte offset of the row slot, cluster address of the mailbox entry)
+    uint32_t *flip_desc = reinterpret_cast<uint32_t *>(smem_raw + L.o_flip); // [bpc * DV]
     __shared__ long long sh_shot;
     __shared__ int sh_slot;
     __shared__ unsigned sh_vote[2][16];
     const uint32_t msg_s = smem_u32(msg), meta_s = smem_u32(meta);
-    const unsigned slots_per_cta = (unsigned)rpc * RS;
+    const int nout = t.nout[rank];
+    for (int x = tid; x < nout; x += T) {
+        const uint32_t loc = t.xloc[(size_t)rank * t.nout_max + x], rem = t.xrem[(size_t)rank * t.nout_max + x];
+        xl[x] = make_uint2(loc * (unsigned)sizeof(real), mapa_u32(msg_s + (rem & 0xFFFFFFu) * (unsigned)sizeof(real), rem >> 24));
+    }
     // A hard-decision flip toggles the parity-mismatch bit of every neighbouring check, wherever it lives.  The
     // cluster address of that check's meta word (4-byte aligned) and its byte lane (low two bits) are resolved once
     // per CTA; doing it at flip time costs a global load per edge that always misses L1 (barrier.cluster invalidates
     // it), and flips are frequent on the shots that matter for the tail (BP that oscillates for thousands of passes).
+    auto flip_descriptor = [&](uint32_t f) -> uint32_t {
+        if (f == BPC_NONE) return 0u;
+        const uint32_t lp = f & 0xFFFFFFu;
+        return mapa_u32(meta_s + (lp & ~3u), f >> 24) | (lp & 3u);
+    };
     if (t.flip_table)
-        for (int e = tid; e < bpc * DV; e += T) {
-            const uint32_t s = t.vslot[(size_t)rank * bpc * DV + e];
-            uint32_t d = 0;
-            if (s != BPC_NONE) {
-                const uint32_t prow = s / (unsigned)RS, lp = prow % (unsigned)rpc;
-                d = mapa_u32(meta_s + (lp & ~3u), prow / (unsigned)rpc) | (lp & 3u);
-            }
-            flip_desc[e] = d;
-        }
-    __syncthreads();
+        for (int e = tid; e < bpc * DV; e += T) flip_desc[e] = flip_descriptor(t.flip[(size_t)rank * bpc * DV + e]);
 
-    // cluster-window addresses of the slots of this thread's bits (shot independent).  Local and remote slots are
-    // addressed alike: splitting them (plain ld/st.shared for CTA-local slots) was measured and made no difference,
-    // the extra predicates and selects cost as much as the narrower path saves (profiles/r01k_cluster_probe.log).
-    uint32_t off[VPT][DV];
+    // byte offsets (inside this CTA's shared memory) of the slots of this thread's bits: a row slot for an edge whose
+    // check lives here, a mailbox entry otherwise (shot independent)
+    unsigned off[VPT][DV];
     int dj[VPT];
     unsigned valid = 0;
 #pragma unroll
@@ -245,17 +316,41 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
 #pragma unroll
         for (int k = 0; k < DV; k++) {
             const uint32_t s = have ? t.vslot[q * DV + k] : BPC_NONE;
-            off[r][k] = 0;
-            if (s != BPC_NONE) {
-                off[r][k] = mapa_u32(msg_s + (s % slots_per_cta) * (unsigned)sizeof(real), s / slots_per_cta);
-                dj[r]++;
-            }
+            off[r][k] = s * (unsigned)sizeof(real);
+            dj[r] += (s != BPC_NONE) ? 1 : 0;
+            if (REG && !have) off[r][k] = (nslot + (unsigned)k) * (unsigned)sizeof(real);               // dummy slots
+            if (!REG && s == BPC_NONE) off[r][k] = (nslot + (unsigned)kFastZeroSlot) * (unsigned)sizeof(real); // the constant-zero slot
         }
     }
     unsigned long long n_conv = 0, n_iter = 0;
     const bool uniform = a.uniform_prior != 0;
     const real prior_u = a.prior[0];
-    (void)m;
+    __syncthreads();
+
+    // remote halves of the exchange: rows -> mailboxes (push, after a check sweep), mailboxes -> rows (pull, after a bit sweep)
+    auto push_rows = [&]() {
+        for (int x = tid; x < nout; x += T) {
+            const uint2 d = xl[x];
+            st_dsmem(d.y, *reinterpret_cast<const real *>(smem_raw + d.x));
+        }
+    };
+    auto pull_rows = [&]() {
+        constexpr int U = 4; // independent remote loads in flight per thread
+        for (int x0 = tid; x0 < nout; x0 += U * T) {
+            real v[U];
+            unsigned o[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int x = x0 + u * T;
+                const uint2 d = x < nout ? xl[x] : make_uint2(0xFFFFFFFFu, 0u);
+                o[u] = d.x;
+                v[u] = (x < nout) ? ld_dsmem(d.y, (real)0) : (real)0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (o[u] != 0xFFFFFFFFu) *reinterpret_cast<real *>(smem_raw + o[u]) = v[u];
+        }
+    };
 
     for (;;) {
         if (rank == 0 && tid == 0) {
@@ -275,6 +370,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
             if (!REG)
                 for (int k = (int)deg; k < DC; k++) msg[p * RS + k] = real_max<real>();
         }
+        if (!REG && tid == 0) msg[nslot + kFastZeroSlot] = (real)0;
         real llr[VPT];
         unsigned dprev = 0;
 #pragma unroll
@@ -287,10 +383,12 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                 llr[r] = pj;
 #pragma unroll
                 for (int k = 0; k < DV; k++)
-                    if (REG || k < dj[r]) st_dsmem(off[r][k], pj);
+                    if (REG || k < dj[r]) *reinterpret_cast<real *>(smem_raw + off[r][k]) = pj;
             }
         }
-        cluster_sync_all();
+        cluster_sync_all(); // every mailbox holds the priors of its bits
+        pull_rows();
+        __syncthreads();
 
         bool conv = false;
         int iters = 0;
@@ -299,56 +397,27 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
             const bool last = it > a.max_iter;
             pow2 *= (real)0.5;
             const real alpha = (a.alpha0 == (real)0) ? (real)1 - pow2 : a.alpha0;
+            const uint32_t alpha_w = sign_word(alpha);
             bool ok = true;
             // ---- check sweep over this CTA's rows (a4) + local convergence vote for the previous pass (a7)
             for (int p = tid; p < rpc; p += T) {
                 const unsigned mt = meta[p];
                 if (mt & 1u) ok = false;
                 if (last) continue;
-                cluster_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha);
+                if constexpr (MAXT <= BPOSD_CLUSTER_FASTROW_MAXT) fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w);
+                else cluster_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha);
             }
             const int cta_ok = __syncthreads_and(ok ? 1 : 0);
+            if (!last) push_rows(); // new check-to-bit values of the remote edges into the mailboxes of their bits
             if (tid < CL) st_dsmem_u32(mapa_u32(smem_u32(&sh_vote[it & 1][rank]), tid), (uint32_t)cta_ok);
             cluster_sync_all();
             int all_ok = 1;
             for (int c = 0; c < CL; c++) all_ok &= (int)sh_vote[it & 1][c];
             if (it > 1 && all_ok) { conv = true; iters = it - 1; break; }
             if (last) { iters = a.max_iter; break; }
-            // ---- bit sweep (a6 + a8) through distributed shared memory
-            // remote loads take ~200 cycles: issue the gathers of four bits back to back before using any
-            unsigned dnow = 0;
-            constexpr int BATCH = VPT < 4 ? VPT : 4;
-#pragma unroll
-            for (int r0 = 0; r0 < VPT; r0 += BATCH) {
-                real c[BATCH][DV];
-#pragma unroll
-                for (int u = 0; u < BATCH; u++) {
-                    const int r = r0 + u;
-#pragma unroll
-                    for (int k = 0; k < DV; k++)
-                        c[u][k] = (r < VPT && ((valid >> r) & 1u) && (REG || k < dj[r])) ? ld_dsmem(off[r][k], (real)0) : (real)0;
-                }
-#pragma unroll
-                for (int u = 0; u < BATCH; u++) {
-                    const int r = r0 + u;
-                    if (r < VPT && ((valid >> r) & 1u)) {
-                        real pre[DV];
-                        real tt = uniform ? prior_u : prior_s[tid + r * T];
-#pragma unroll
-                        for (int k = 0; k < DV; k++)
-                            if (REG || k < dj[r]) { pre[k] = tt; tt += c[u][k]; }
-                        llr[r] = tt;
-                        dnow |= ((tt <= 0) ? 1u : 0u) << r;
-                        real sfx = 0;
-#pragma unroll
-                        for (int k = DV - 1; k >= 0; k--)
-                            if (REG || k < dj[r]) {
-                                st_dsmem(off[r][k], (REG && k == DV - 1) ? pre[k] : pre[k] + sfx);
-                                sfx = (REG && k == DV - 1) ? c[u][k] : sfx + c[u][k];
-                            }
-                    }
-                }
-            }
+            // ---- bit sweep (a6 + a8): rows and mailbox of this CTA only
+            const unsigned dnow = valid & (uniform ? fast_bit_sweep<real, DV, VPT, REG, true>(smem_raw, off, dj, llr, prior_u, prior_s, tid, T, bpc)
+                                                   : fast_bit_sweep<real, DV, VPT, REG, false>(smem_raw, off, dj, llr, prior_u, prior_s, tid, T, bpc));
             if (dnow != dprev) {
                 // a hard decision flipped (rare): toggle the parity-mismatch bit of every neighbouring check
                 unsigned flip = dnow ^ dprev;
@@ -356,20 +425,16 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
 #pragma unroll
                 for (int r = 0; r < VPT; r++)
                     if ((flip >> r) & 1u) {
-                        const size_t q = (size_t)rank * bpc + tid + r * T;
+                        const int lq = tid + r * T;
                         for (int k = 0; k < dj[r]; k++) {
-                            if (t.flip_table) {
-                                const uint32_t d = flip_desc[(tid + r * T) * DV + k];
-                                xor_dsmem_u32(d & ~3u, 1u << ((d & 3u) * 8u));
-                            } else {
-                                const uint32_t prow = t.vslot[q * DV + k] / (unsigned)RS;
-                                const uint32_t lp = prow % (unsigned)rpc;
-                                xor_dsmem_u32(mapa_u32(meta_s + (lp & ~3u), prow / (unsigned)rpc), 1u << ((lp & 3u) * 8u));
-                            }
+                            const uint32_t d = t.flip_table ? flip_desc[lq * DV + k] : flip_descriptor(t.flip[((size_t)rank * bpc + lq) * DV + k]);
+                            xor_dsmem_u32(d & ~3u, 1u << ((d & 3u) * 8u));
                         }
                     }
             }
             cluster_sync_all();
+            pull_rows(); // new bit-to-check values of the remote edges back into the rows
+            __syncthreads();
         }
 
         // ---- results ----
@@ -508,8 +573,10 @@ template <typename real>
 static inline cudaError_t cluster_launch(const ClusterTables &t, const BpArgs<real> &a, int nclusters, int threads, size_t smem,
                                          int flip_table, cudaStream_t st) {
     ClusterDev d;
-    d.vslot = t.d_vslot; d.cdeg = t.d_cdeg; d.row_of = t.d_row_of; d.bit_of = t.d_bit_of;
+    d.vslot = t.d_vslot; d.flip = t.d_flip; d.xloc = t.d_xloc; d.xrem = t.d_xrem; d.nout = t.d_nout;
+    d.cdeg = t.d_cdeg; d.row_of = t.d_row_of; d.bit_of = t.d_bit_of;
     d.rows_per_cta = t.rows_per_cta; d.bits_per_cta = t.bits_per_cta; d.CL = t.CL;
+    d.nbox_max = t.nbox_max; d.nout_max = t.nout_max;
     d.flip_table = flip_table;
     cudaError_t e = cudaSuccess;
     BPOSD_FAST_CLASS(t, (e = ClusterInst<real, DC, DV>::launch(t, a, d, nclusters, threads, smem, st)));

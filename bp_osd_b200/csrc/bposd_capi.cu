@@ -9,6 +9,7 @@
 #include "bp_fast_kernel.cuh"
 #include "bp_cluster_kernel.cuh"
 #include "osd_reg_kernel.cuh"
+#include "osd_cluster_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -82,6 +83,12 @@ struct bposd_handle {
     uint32_t *d_osdl_mask = nullptr;
     int *d_osdl_order = nullptr, *d_osdl_piv_row = nullptr, *d_osdl_piv_pos = nullptr, *d_osdl_pstart = nullptr;
     int osdl_alloc_grid = 0;
+    // large-H OSD-0, one thread-block cluster per failed shot (osd_cluster_kernel.cuh): rows split over the cluster, masks TMA-streamed
+    bool osd_clus = false;
+    int osdc_CL = 0, osdc_rpc = 0, osdc_npanels = 0, osdc_smem = 0, osdc_nclusters = 0, osdc_alloc = 0;
+    unsigned long long *d_osdc_mask = nullptr, *d_osdc_key = nullptr;
+    unsigned *d_osdc_idx = nullptr;
+    OsdcPivot *d_osdc_piv = nullptr;
     int force_kernel = 0, force_threads = 0, force_cluster = 0;
     bool geometry_ready = false;
     // harness
@@ -209,7 +216,7 @@ static int plan_geometry_t(bposd_handle *h) {
         for (int c : {2, 4, 8, 16}) {
             if (h->force_cluster > 0 && c != h->force_cluster) continue;
             const int rpc = (m + c - 1) / c, bpc = (n + c - 1) / c;
-            if (cluster_smem_bytes<real>(DCc, rpc, bpc, true) > (size_t)h->smem_optin || cluster_vpt(bpc) == 0) continue;
+            if (cluster_smem_min<real>(DCc, rpc, bpc) > (size_t)h->smem_optin || cluster_vpt(bpc) == 0) continue;
             cand.push_back(c);
         }
         bool done = false;
@@ -219,12 +226,13 @@ static int plan_geometry_t(bposd_handle *h) {
                 if (e != cudaSuccess) return fail(h, BPOSD_ECUDA, std::string("cluster_build: ") + cudaGetErrorString(e));
             }
             const int ct = cluster_threads(h->clus.bits_per_cta);
-            size_t csmem = cluster_smem_bytes<real>(h->clus.DC, h->clus.rows_per_cta, h->clus.bits_per_cta, true, h->clus.DV);
+            size_t csmem = cluster_smem_need<real>(h->clus, 1);
             h->clus_flip_table = 1; // parity-flip descriptors in shared memory when they fit
             if (csmem > (size_t)h->smem_optin) {
-                csmem = cluster_smem_bytes<real>(h->clus.DC, h->clus.rows_per_cta, h->clus.bits_per_cta, true);
+                csmem = cluster_smem_need<real>(h->clus, 0);
                 h->clus_flip_table = 0;
             }
+            if (csmem > (size_t)h->smem_optin) continue; // rows + mailbox + exchange list of the fullest CTA do not fit: next size
             int ncl = 0;
             cudaError_t e = (ct > 0 && ct <= 1024) ? cluster_prepare<real>(h->clus, ct, csmem, &ncl) : cudaErrorInvalidConfiguration;
             if (e == cudaSuccess && ncl >= 1) {
@@ -318,6 +326,39 @@ static int plan_geometry_t(bposd_handle *h) {
         h->osdl_grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, h->osdl_ws_cap / (long long)std::max<size_t>(per_cta, 1)));
         h->osd_supported = true;
     }
+    // cluster OSD-0 (variant 4): preferred over the single-CTA HBM kernel whenever T does not fit in shared memory
+    h->osd_clus = false;
+    if (h->osd_order == 0 && m >= 2 && (h->osd_variant == 4 || (h->osd_variant == 0 && (h->osd_large || !h->osd_supported)))) {
+        const int CL = m >= 4096 ? 16 : (m >= 1024 ? 8 : (m >= 256 ? 4 : 2));
+        h->osdc_CL = CL;
+        h->osdc_rpc = (((m + CL - 1) / CL) + 1) & ~1;
+        h->osdc_npanels = (n + 63) / 64;
+        h->osdc_smem = (int)osdc_layout(h->osdc_rpc, h->osdc_npanels).total;
+        bool ok = (size_t)h->osdc_smem <= (size_t)h->smem_optin;
+        int ncl = 0;
+        if (ok) {
+            auto kern = osd0_cluster_kernel<real>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->osdc_smem);
+            if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(CL, 1, 1); cfg.blockDim = dim3(kOsdcThreads, 1, 1); cfg.dynamicSmemBytes = h->osdc_smem;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+            }
+            if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); ok = false; }
+        }
+        if (ok) {
+            const size_t per_cluster = (size_t)h->osdc_npanels * h->osdc_rpc * CL * 8 + (size_t)osd_reg_np2(n) * 12 + (size_t)std::min(m, n) * sizeof(OsdcPivot);
+            h->osdc_nclusters = (int)std::max<long long>(1, std::min<long long>(ncl, h->osdl_ws_cap / (long long)std::max<size_t>(per_cluster, 1)));
+            h->osd_clus = true; h->osd_large = false; h->osd_supported = true;
+        } else if (h->osd_variant == 4)
+            return fail(h, BPOSD_EUNSUP, "the cluster OSD-0 kernel cannot be launched for this matrix");
+    } else if (h->osd_variant == 4)
+        return fail(h, BPOSD_EUNSUP, "the cluster OSD kernel handles OSD-0 (osd_order 0) only");
     // register kernel (default whenever it applies): T in registers, one barrier per 16 sorted columns
     {
         const int Sw = (m + 31) / 32;
@@ -331,7 +372,7 @@ static int plan_geometry_t(bposd_handle *h) {
             return fail(h, BPOSD_EUNSUP, "the register OSD kernel needs m <= 1024, n < 65535, fewer than 65536 edges and column degrees up to 8");
         h->osd_reg = reg_ok && (h->osd_variant == 3 || h->osd_variant == 0);
         if (h->osd_reg) {
-            h->osd_large = false;
+            h->osd_large = false; h->osd_clus = false;
             h->osd_supported = true;
             int occ4 = 0;
 #define BPOSD_OSDR_SETUP(Wv, KDv)                                                                                                         \
@@ -352,7 +393,7 @@ static int plan_geometry_t(bposd_handle *h) {
             h->osd_ctas_per_sm = std::max(1, occ4);
         }
     }
-    if (h->osd_supported && !h->osd_large && !h->osd_reg) {
+    if (h->osd_supported && !h->osd_large && !h->osd_reg && !h->osd_clus) {
         CU_TRY(h, cudaFuncSetAttribute(osd_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osd_smem));
         int occ2 = 0;
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, osd_kernel<real>, h->osd_threads, osd_smem));
@@ -391,6 +432,7 @@ extern "C" void bposd_destroy(bposd_t *h) {
     }
     cudaFree(h->d_scratch); cudaFree(h->d_scratch_dec);
     cudaFree(h->d_osdl_mask); cudaFree(h->d_osdl_order); cudaFree(h->d_osdl_piv_row); cudaFree(h->d_osdl_piv_pos); cudaFree(h->d_osdl_pstart);
+    cudaFree(h->d_osdc_mask); cudaFree(h->d_osdc_key); cudaFree(h->d_osdc_idx); cudaFree(h->d_osdc_piv);
     cudaFree(h->d_t1); cudaFree(h->d_t2); cudaFree(h->d_t3); cudaFree(h->d_l_ptr); cudaFree(h->d_l_idx);
     cudaFree(h->d_counters); cudaFree(h->d_minw); cudaFree(h->d_cu_tab);
     if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -571,7 +613,7 @@ extern "C" int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size) {
 
 extern "C" int bposd_set_osd_variant(bposd_t *h, int32_t variant, int64_t workspace_bytes) {
     if (!h) return BPOSD_EINVAL;
-    if (variant < 0 || variant > 3) return fail(h, BPOSD_EINVAL, "osd variant must be 0 (auto), 1 (T matrix in shared memory), 2 (HBM resident) or 3 (T matrix in registers)");
+    if (variant < 0 || variant > 4) return fail(h, BPOSD_EINVAL, "osd variant must be 0 (auto), 1 (T matrix in shared memory), 2 (HBM resident, one CTA per shot), 3 (T matrix in registers) or 4 (HBM resident, one cluster per shot)");
     CU_TRY(h, cudaSetDevice(h->device));
     const int old = h->osd_variant;
     h->osd_variant = variant;
@@ -590,7 +632,8 @@ extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
     info->bp_smem_bytes = h->bp_smem;
     if (h->bp_kernel == 2 && h->uniform_prior) { info->bp_ctas_per_sm = h->bp_ctas_uni; info->bp_smem_bytes = h->bp_smem_uni; } info->osd_threads = h->osd_threads; info->osd_smem_bytes = h->osd_smem;
     info->sm_count = h->sm_count; info->ms_scaling_factor = h->alpha;
-    info->osd_variant = !h->osd_supported ? 0 : (h->osd_large ? 2 : (h->osd_reg ? 3 : 1));
+    info->osd_variant = !h->osd_supported ? 0 : (h->osd_clus ? 4 : (h->osd_large ? 2 : (h->osd_reg ? 3 : 1)));
+    if (h->osd_clus) { info->osd_threads = kOsdcThreads; info->osd_smem_bytes = h->osdc_smem; }
     if (h->osd_reg) { info->osd_threads = h->osdr_threads; info->osd_smem_bytes = h->osdr_smem; }
     info->bp_layout_excess = h->bp_kernel == 3 ? (int32_t)(1000 * h->clus.remote_edges / std::max<long long>(h->clus.total_edges, 1))
                                                : (int32_t)h->fast.conflicts_after;
@@ -611,6 +654,39 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
                       const int *d_fail_count, const int *d_fail_list, uint8_t *d_osd0, uint8_t *d_osdw,
                       unsigned long long *d_stat, long long Bc, bool per_shot_priors, const double *d_weights, int *launches) {
     const int n = h->n, m = h->m;
+    if (h->osd_clus) {
+        const int CL = h->osdc_CL, ncl = (int)std::min<long long>(Bc, h->osdc_nclusters);
+        const int np2 = osd_reg_np2(n);
+        if (h->osdc_alloc < ncl) {
+            cudaFree(h->d_osdc_mask); cudaFree(h->d_osdc_key); cudaFree(h->d_osdc_idx); cudaFree(h->d_osdc_piv);
+            h->d_osdc_mask = h->d_osdc_key = nullptr; h->d_osdc_idx = nullptr; h->d_osdc_piv = nullptr;
+            h->osdc_alloc = 0;
+            const size_t gsz = (size_t)ncl;
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_mask, gsz * h->osdc_npanels * h->osdc_rpc * CL * 8));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_key, gsz * np2 * 8));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_idx, gsz * np2 * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_piv, gsz * std::max<size_t>(std::min(m, n), 1) * sizeof(OsdcPivot)));
+            h->osdc_alloc = ncl;
+        }
+        OsdClusterArgs<real> o;
+        o.g = g;
+        o.synd = d_synd; o.synd_packed = synd_packed;
+        o.llr = llr; o.llr_by_shot = llr_by_shot;
+        o.fail_count = d_fail_count; o.fail_list = d_fail_list;
+        o.osd0 = d_osd0; o.osdw = d_osdw;
+        o.stat = d_stat;
+        o.maxrank = h->rank; o.npanels = h->osdc_npanels; o.CL = CL; o.rpc = h->osdc_rpc; o.np2 = np2;
+        o.ws_mask = h->d_osdc_mask; o.ws_key = h->d_osdc_key; o.ws_idx = h->d_osdc_idx; o.ws_piv = h->d_osdc_piv;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ncl * CL, 1, 1); cfg.blockDim = dim3(kOsdcThreads, 1, 1); cfg.dynamicSmemBytes = h->osdc_smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CU_TRY(h, cudaLaunchKernelEx(&cfg, osd0_cluster_kernel<real>, o));
+        (*launches)++;
+        return BPOSD_OK;
+    }
     if (h->osd_large) {
         const int ogrid = (int)std::min<long long>(Bc, h->osdl_grid);
         if (h->osdl_alloc_grid < ogrid) {
@@ -1034,7 +1110,7 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
         if (rc || taken) return rc;
     }
     const bool need_ws = h->osd_method != BPOSD_OSD_OFF && !h_llr;
-    const bool pipelined = h->bp_kernel != 0 && !h->osd_large && B >= 2 * h->host_chunk_min;
+    const bool pipelined = h->bp_kernel != 0 && !h->osd_large && !h->osd_clus && B >= 2 * h->host_chunk_min;
     long long chunk = B;
     if (pipelined) chunk = std::min<long long>(std::max<long long>((B + 15) / 16, h->host_chunk_min), h->host_chunk_max);
     if (need_ws) chunk = std::min(chunk, h->fail_cap);

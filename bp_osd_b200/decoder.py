@@ -230,7 +230,8 @@ class BpOsdDecoder:
         self._check(_capi.load().bposd_set_cluster_size(self._h, int(cluster_size)))
 
     def set_osd_variant(self, variant=None, workspace_bytes=0):
-        """variant: None (auto), 3 panel kernel, 1 T-matrix kernel, 2 HBM-resident OSD-0 kernel (large H)."""
+        """variant: None (auto), 3 register kernel, 1 shared-memory T-matrix kernel, 4 / 2 HBM-resident OSD-0 kernels for
+        large H (one thread-block cluster per failed shot with TMA-streamed masks / one CTA per failed shot)."""
         self._check(_capi.load().bposd_set_osd_variant(self._h, 0 if variant is None else int(variant),
                                                        int(workspace_bytes)))
 

@@ -64,7 +64,7 @@ typedef struct {
     int32_t bp_kernel;              /* 0 generic/global, 1 generic/smem, 2 in-place smem, 3 cluster DSMEM */
     int32_t bp_threads, bp_ctas_per_sm, bp_smem_bytes;
     int32_t osd_threads, osd_smem_bytes, sm_count;
-    int32_t osd_variant;            /* 3 register kernel, 1 shared-memory kernel, 2 HBM-resident OSD-0 kernel, 0 OSD unsupported */
+    int32_t osd_variant;            /* 3 register kernel, 1 shared-memory kernel, 4 / 2 HBM-resident OSD-0 kernels (cluster / single CTA), 0 OSD unsupported */
     int32_t bp_layout_excess;       /* kernel 2: shared-memory wavefronts per bit sweep above the conflict-free count;
                                        kernel 3: edges whose bit and check live in different CTAs, per mille */
     int32_t bp_cluster_size;        /* CTAs per cluster of kernel 3, else 1 */
@@ -204,9 +204,12 @@ int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size);
 /* OSD kernel variant: 0 automatic; 3 register kernel (the m x m row-operation matrix in registers, warp-specialised
  * resolver / updater pipeline with one barrier per 16 sorted columns; OSD-0/E/CS; the default for m <= 1024);
  * 1 shared-memory kernel (the same matrix in shared memory, one sweep and two barriers per pivot; OSD-0/E/CS; the
- * fall-back for larger m while the matrix fits); 2 HBM-resident left-looking kernel (OSD-0 only; chosen
- * automatically when nothing fits in shared memory, BASELINE config 5).  workspace_bytes > 0 caps the HBM workspace
- * of variant 2 (ceil(n/32) * m * 4 bytes per concurrently processed failed shot). */
+ * fall-back for larger m while the matrix fits); 4 HBM-resident left-looking cluster kernel (OSD-0 only; one thread-block
+ * cluster per failed shot, checks split over its CTAs, 64-column panels, row-operation masks streamed from HBM with
+ * cp.async.bulk + mbarrier, pivot rows exchanged through distributed shared memory; chosen automatically when nothing
+ * fits in shared memory, BASELINE config 5); 2 the single-CTA form of it (32-column panels, one CTA per failed shot).
+ * workspace_bytes > 0 caps the HBM workspace of variants 4 / 2 (ceil(n/64) * m * 8 bytes per concurrently processed
+ * failed shot). */
 int bposd_set_osd_variant(bposd_t *h, int32_t variant, int64_t workspace_bytes);
 const char *bposd_last_error(const bposd_t *h);
 const char *bposd_version(void);

@@ -43,7 +43,9 @@ def assert_exact(out, ref, llr_exact=True):
     assert (out["converge"] == ref["converge"].astype(bool)).all()
     assert (out["iter"] == ref["iter"]).all()
     if llr_exact:
-        assert (out["llr"] == ref["llr"]).all(), "log_prob_ratios not bit-exact"
+        # equal_nan: product-sum shots whose sums overflowed hold NaN in the same places (x86 and sm_100a generate different
+        # quiet-NaN payloads, the one thing that legitimately differs); every other value is compared bit for bit
+        assert np.array_equal(out["llr"], ref["llr"], equal_nan=True), "log_prob_ratios not bit-exact"
 
 
 def test_g1_readme_known_answer_on_gpu(torch_cuda):
@@ -67,6 +69,8 @@ def test_g1_readme_known_answer_on_gpu(torch_cuda):
 @pytest.mark.parametrize("kernel", [0, 1, 2, 3])
 def test_golden_fixtures(torch_cuda, cfg_codes, name, kernel):
     g = load_golden(name)
+    if g["kw"]["bp_method"] == "ps" and kernel in (2, 3):
+        pytest.skip("the in-place and the cluster kernel are min-sum kernels; product-sum runs on the two-array kernels")
     H = cfg_codes(g["cfg"]).hz
     d, out = gpu_decode(torch_cuda, H, g["syndromes"], kernel=kernel, error_rate=g["p"], **g["kw"])
     assert_exact(out, g)
@@ -340,9 +344,11 @@ def test_fp32_fast_mode_is_statistically_equivalent(torch_cuda, oracle_mod, cfg_
 # ------------------------------------------------------------------------------------------------
 # Large-H path (BASELINE config 5): HBM-resident OSD-0 kernel, BP with messages outside shared memory
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cfg,p,max_iter", [(1, 0.12, 2), (2, 0.08, 4)])
-def test_hbm_osd0_kernel_matches_shared_memory_kernel_and_oracle(torch_cuda, oracle_mod, cfg_codes, cfg, p, max_iter):
-    """Variant 2 (left-looking panel elimination in HBM) forced on codes that also fit variant 1."""
+@pytest.mark.parametrize("variant", [2, 4])
+@pytest.mark.parametrize("cfg,p,max_iter", [(1, 0.12, 2), (2, 0.08, 4), (3, 0.06, 6)])
+def test_hbm_osd0_kernel_matches_shared_memory_kernel_and_oracle(torch_cuda, oracle_mod, cfg_codes, cfg, p, max_iter, variant):
+    """Variants 2 and 4 (left-looking panel elimination with the row operations in HBM: one CTA per shot / one cluster per
+    shot with TMA-streamed masks) forced on codes that also fit the shared-memory and register kernels."""
     from bp_osd_b200 import BpOsdDecoder
     torch = torch_cuda
     H = cfg_codes(cfg).hz
@@ -351,8 +357,8 @@ def test_hbm_osd0_kernel_matches_shared_memory_kernel_and_oracle(torch_cuda, ora
     ref = oracle_mod.OracleDecoder(H, error_rate=p, **kw).decode_batch(syn)
     assert (~ref["converge"].astype(bool)).sum() > 50
     d = BpOsdDecoder(H, error_rate=p, **kw)
-    d.set_osd_variant(2)
-    assert d.info()["osd_variant"] == 2
+    d.set_osd_variant(variant)
+    assert d.info()["osd_variant"] == variant
     r = d.decode_batch(torch.tensor(syn, device="cuda"))
     assert (r.osd0_decoding.cpu().numpy() == ref["osd0"]).all()
     assert (r.osdw_decoding.cpu().numpy() == ref["osdw"]).all()
@@ -360,13 +366,14 @@ def test_hbm_osd0_kernel_matches_shared_memory_kernel_and_oracle(torch_cuda, ora
     # the HBM kernel does OSD-0 only
     d2 = BpOsdDecoder(H, error_rate=p, **dict(kw, osd_method="osd_cs", osd_order=3))
     with pytest.raises(NotImplementedError):
-        d2.set_osd_variant(2)
+        d2.set_osd_variant(variant)
     assert d2.info()["osd_variant"] == 3  # the failed request left the automatic choice (register kernel) in place
 
 
 def test_large_h_standin_selects_hbm_osd(torch_cuda, oracle_mod):
     """[[3600,144]] HGP of a (3,4)-regular 36x48 seed: T = 1728 x 1728 bits (373 KB) exceeds shared memory,
-    so the HBM-resident kernel is chosen automatically; rank-deficient H (redundant checks) included."""
+    so the HBM-resident cluster kernel (variant 4) is chosen automatically and the single-CTA one (variant 2) stays
+    selectable; rank-deficient H (redundant checks) included."""
     from bp_osd_b200 import BpOsdDecoder
     torch = torch_cuda
     code = hgp(codes.regular_ldpc(36, 48, 3, 4, seed=11), compute_logicals=False)
@@ -378,11 +385,13 @@ def test_large_h_standin_selects_hbm_osd(torch_cuda, oracle_mod):
     ref = oracle_mod.OracleDecoder(H, error_rate=0.06, **kw).decode_batch(syn)
     nfail = int((~ref["converge"].astype(bool)).sum())
     assert nfail >= 8
-    for kernel in (None, 0, 3):   # auto (shared-memory BP), the HBM/L2-scratch BP and the cluster (DSMEM) BP of config 5
+    for kernel, variant in ((None, 4), (0, 4), (3, 4), (None, 2)):   # auto (shared-memory BP), the HBM/L2-scratch BP and the cluster (DSMEM) BP of config 5
         d = BpOsdDecoder(H, error_rate=0.06, **kw)
         if kernel is not None:
             d.set_tuning(bp_kernel=kernel)
-        assert d.info()["osd_variant"] == 2
+        if variant != 4:
+            d.set_osd_variant(variant)
+        assert d.info()["osd_variant"] == variant
         r = d.decode_batch(torch.tensor(syn, device="cuda"))
         out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
                    llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
@@ -407,7 +416,7 @@ def test_config5_full_size(torch_cuda, oracle_mod, cfg_codes):
     d = BpOsdDecoder(H, error_rate=p, **kw)
     info = d.info()
     # messages (1.07 MB in fp64) exceed one SM: the cluster kernel splits them over distributed shared memory
-    assert info["bp_kernel"] == 3 and info["bp_cluster_size"] in (8, 16) and info["osd_variant"] == 2
+    assert info["bp_kernel"] == 3 and info["bp_cluster_size"] in (8, 16) and info["osd_variant"] == 4
     r = d.decode_batch(torch.tensor(syn, device="cuda"))
     osd0 = r.osd0_decoding.cpu().numpy()
     conv = r.converge.cpu().numpy()

@@ -58,7 +58,8 @@ def test_oracle_matches_golden(oracle_mod, cfg_codes, name):
     out = oracle_mod.OracleDecoder(H, error_rate=g["p"], **g["kw"]).decode_batch(g["syndromes"])
     for k in ("osdw", "osd0", "bp", "converge", "iter"):
         assert (out[k] == g[k]).all(), k
-    assert (out["llr"] == g["llr"]).all()
+    # NaN where the reference arithmetic itself gives inf - inf (product-sum without clipping): same places
+    assert np.array_equal(out["llr"], g["llr"], equal_nan=True)
 
 
 CASES = [
