@@ -85,7 +85,10 @@ struct bposd_handle {
     int osdl_alloc_grid = 0;
     // large-H OSD-0, one thread-block cluster per failed shot (osd_cluster_kernel.cuh): rows split over the cluster, masks TMA-streamed
     bool osd_clus = false;
-    int osdc_CL = 0, osdc_rpc = 0, osdc_npanels = 0, osdc_smem = 0, osdc_nclusters = 0, osdc_alloc = 0;
+    struct OsdcCfg { int CL, rpc, smem, ncl; };
+    std::vector<OsdcCfg> osdc; // cluster sizes, largest first: a few failed shots take the big clusters, many the small ones
+    int osdc_npanels = 0;
+    size_t osdc_alloc_mask = 0, osdc_alloc_shots = 0;
     unsigned long long *d_osdc_mask = nullptr, *d_osdc_key = nullptr;
     unsigned *d_osdc_idx = nullptr;
     OsdcPivot *d_osdc_piv = nullptr;
@@ -328,35 +331,44 @@ static int plan_geometry_t(bposd_handle *h) {
     }
     // cluster OSD-0 (variant 4): preferred over the single-CTA HBM kernel whenever T does not fit in shared memory
     h->osd_clus = false;
+    h->osdc.clear();
     if (h->osd_order == 0 && m >= 2 && (h->osd_variant == 4 || (h->osd_variant == 0 && (h->osd_large || !h->osd_supported)))) {
-        const int CL = m >= 4096 ? 16 : (m >= 1024 ? 8 : (m >= 256 ? 4 : 2));
-        h->osdc_CL = CL;
-        h->osdc_rpc = (((m + CL - 1) / CL) + 1) & ~1;
+        const int CL0 = m >= 4096 ? 16 : (m >= 1024 ? 8 : (m >= 256 ? 4 : 2));
         h->osdc_npanels = (n + 63) / 64;
-        h->osdc_smem = (int)osdc_layout(h->osdc_rpc, h->osdc_npanels).total;
-        bool ok = (size_t)h->osdc_smem <= (size_t)h->smem_optin;
-        int ncl = 0;
-        if (ok) {
-            auto kern = osd0_cluster_kernel<real>;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->osdc_smem);
-            if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-            if (e == cudaSuccess) {
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(CL, 1, 1); cfg.blockDim = dim3(kOsdcThreads, 1, 1); cfg.dynamicSmemBytes = h->osdc_smem;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                cfg.attrs = at; cfg.numAttrs = 1;
-                e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
-            }
-            if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); ok = false; }
+        auto kern = osd0_cluster_kernel<real>;
+        int smem_max = 0;
+        for (int CL = CL0; CL >= 2 && CL >= CL0 / 4; CL >>= 1) {
+            bposd_handle::OsdcCfg c;
+            c.CL = CL;
+            c.rpc = (((m + CL - 1) / CL) + 1) & ~1;
+            c.smem = (int)osdc_layout(c.rpc, h->osdc_npanels).total;
+            c.ncl = 0;
+            if ((size_t)c.smem > (size_t)h->smem_optin) continue;
+            smem_max = std::max(smem_max, c.smem);
+            h->osdc.push_back(c);
         }
-        if (ok) {
-            const size_t per_cluster = (size_t)h->osdc_npanels * h->osdc_rpc * CL * 8 + (size_t)osd_reg_np2(n) * 12 + (size_t)std::min(m, n) * sizeof(OsdcPivot);
-            h->osdc_nclusters = (int)std::max<long long>(1, std::min<long long>(ncl, h->osdl_ws_cap / (long long)std::max<size_t>(per_cluster, 1)));
-            h->osd_clus = true; h->osd_large = false; h->osd_supported = true;
-        } else if (h->osd_variant == 4)
-            return fail(h, BPOSD_EUNSUP, "the cluster OSD-0 kernel cannot be launched for this matrix");
+        if (!h->osdc.empty()) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+            if (e == cudaSuccess && CL0 > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) { cudaGetLastError(); h->osdc.clear(); }
+        }
+        for (size_t k = 0; k < h->osdc.size();) {
+            bposd_handle::OsdcCfg &c = h->osdc[k];
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(c.CL, 1, 1); cfg.blockDim = dim3(kOsdcThreads, 1, 1); cfg.dynamicSmemBytes = c.smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = c.CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+            const size_t per_cluster = (size_t)h->osdc_npanels * c.rpc * c.CL * 8 + (size_t)osd_reg_np2(n) * 12 + (size_t)std::min(m, n) * sizeof(OsdcPivot);
+            if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); h->osdc.erase(h->osdc.begin() + k); continue; }
+            c.ncl = (int)std::max<long long>(1, std::min<long long>(ncl, h->osdl_ws_cap / (long long)std::max<size_t>(per_cluster, 1)));
+            k++;
+        }
+        if (!h->osdc.empty()) { h->osd_clus = true; h->osd_large = false; h->osd_supported = true; }
+        else if (h->osd_variant == 4) return fail(h, BPOSD_EUNSUP, "the cluster OSD-0 kernel cannot be launched for this matrix");
     } else if (h->osd_variant == 4)
         return fail(h, BPOSD_EUNSUP, "the cluster OSD kernel handles OSD-0 (osd_order 0) only");
     // register kernel (default whenever it applies): T in registers, one barrier per 16 sorted columns
@@ -633,7 +645,7 @@ extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
     if (h->bp_kernel == 2 && h->uniform_prior) { info->bp_ctas_per_sm = h->bp_ctas_uni; info->bp_smem_bytes = h->bp_smem_uni; } info->osd_threads = h->osd_threads; info->osd_smem_bytes = h->osd_smem;
     info->sm_count = h->sm_count; info->ms_scaling_factor = h->alpha;
     info->osd_variant = !h->osd_supported ? 0 : (h->osd_clus ? 4 : (h->osd_large ? 2 : (h->osd_reg ? 3 : 1)));
-    if (h->osd_clus) { info->osd_threads = kOsdcThreads; info->osd_smem_bytes = h->osdc_smem; }
+    if (h->osd_clus) { info->osd_threads = kOsdcThreads; info->osd_smem_bytes = h->osdc[0].smem; }
     if (h->osd_reg) { info->osd_threads = h->osdr_threads; info->osd_smem_bytes = h->osdr_smem; }
     info->bp_layout_excess = h->bp_kernel == 3 ? (int32_t)(1000 * h->clus.remote_edges / std::max<long long>(h->clus.total_edges, 1))
                                                : (int32_t)h->fast.conflicts_after;
@@ -655,36 +667,51 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
                       unsigned long long *d_stat, long long Bc, bool per_shot_priors, const double *d_weights, int *launches) {
     const int n = h->n, m = h->m;
     if (h->osd_clus) {
-        const int CL = h->osdc_CL, ncl = (int)std::min<long long>(Bc, h->osdc_nclusters);
         const int np2 = osd_reg_np2(n);
-        if (h->osdc_alloc < ncl) {
+        size_t need_mask = 0, need_shots = 0;
+        for (const auto &c : h->osdc) {
+            const size_t ncl = (size_t)std::min<long long>(Bc, c.ncl);
+            need_mask = std::max(need_mask, ncl * h->osdc_npanels * c.rpc * c.CL);
+            need_shots = std::max(need_shots, ncl);
+        }
+        if (h->osdc_alloc_mask < need_mask || h->osdc_alloc_shots < need_shots) {
             cudaFree(h->d_osdc_mask); cudaFree(h->d_osdc_key); cudaFree(h->d_osdc_idx); cudaFree(h->d_osdc_piv);
             h->d_osdc_mask = h->d_osdc_key = nullptr; h->d_osdc_idx = nullptr; h->d_osdc_piv = nullptr;
-            h->osdc_alloc = 0;
-            const size_t gsz = (size_t)ncl;
-            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_mask, gsz * h->osdc_npanels * h->osdc_rpc * CL * 8));
-            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_key, gsz * np2 * 8));
-            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_idx, gsz * np2 * 4));
-            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_piv, gsz * std::max<size_t>(std::min(m, n), 1) * sizeof(OsdcPivot)));
-            h->osdc_alloc = ncl;
+            h->osdc_alloc_mask = h->osdc_alloc_shots = 0;
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_mask, need_mask * 8));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_key, need_shots * np2 * 8));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_idx, need_shots * np2 * 4));
+            CU_TRY(h, cudaMalloc((void **)&h->d_osdc_piv, need_shots * std::max<size_t>(std::min(m, n), 1) * sizeof(OsdcPivot)));
+            h->osdc_alloc_mask = need_mask; h->osdc_alloc_shots = need_shots;
         }
-        OsdClusterArgs<real> o;
-        o.g = g;
-        o.synd = d_synd; o.synd_packed = synd_packed;
-        o.llr = llr; o.llr_by_shot = llr_by_shot;
-        o.fail_count = d_fail_count; o.fail_list = d_fail_list;
-        o.osd0 = d_osd0; o.osdw = d_osdw;
-        o.stat = d_stat;
-        o.maxrank = h->rank; o.npanels = h->osdc_npanels; o.CL = CL; o.rpc = h->osdc_rpc; o.np2 = np2;
-        o.ws_mask = h->d_osdc_mask; o.ws_key = h->d_osdc_key; o.ws_idx = h->d_osdc_idx; o.ws_piv = h->d_osdc_piv;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(ncl * CL, 1, 1); cfg.blockDim = dim3(kOsdcThreads, 1, 1); cfg.dynamicSmemBytes = h->osdc_smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        CU_TRY(h, cudaLaunchKernelEx(&cfg, osd0_cluster_kernel<real>, o));
-        (*launches)++;
+        // one launch per cluster size; each takes the chunk only if the failed-shot count (known on the device) is in its range
+        int lo = 0;
+        for (size_t k = 0; k < h->osdc.size(); k++) {
+            const auto &c = h->osdc[k];
+            const int ncl = (int)std::min<long long>(Bc, c.ncl);
+            const bool lastcfg = k + 1 == h->osdc.size();
+            const int hi = lastcfg ? 0x7fffffff : c.ncl; // up to one shot per resident cluster: the big clusters; beyond: smaller ones
+            if (!lastcfg && lo > hi) continue;
+            OsdClusterArgs<real> o;
+            o.g = g;
+            o.synd = d_synd; o.synd_packed = synd_packed;
+            o.llr = llr; o.llr_by_shot = llr_by_shot;
+            o.fail_count = d_fail_count; o.fail_list = d_fail_list;
+            o.osd0 = d_osd0; o.osdw = d_osdw;
+            o.stat = d_stat;
+            o.maxrank = h->rank; o.npanels = h->osdc_npanels; o.CL = c.CL; o.rpc = c.rpc; o.np2 = np2;
+            o.nfail_lo = lo; o.nfail_hi = hi;
+            o.ws_mask = h->d_osdc_mask; o.ws_key = h->d_osdc_key; o.ws_idx = h->d_osdc_idx; o.ws_piv = h->d_osdc_piv;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ncl * c.CL, 1, 1); cfg.blockDim = dim3(kOsdcThreads, 1, 1); cfg.dynamicSmemBytes = c.smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = c.CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CU_TRY(h, cudaLaunchKernelEx(&cfg, osd0_cluster_kernel<real>, o));
+            (*launches)++;
+            lo = hi == 0x7fffffff ? hi : hi + 1;
+        }
         return BPOSD_OK;
     }
     if (h->osd_large) {

@@ -46,6 +46,9 @@ struct OsdClusterArgs {
     int npanels;  // ceil(n / 64)
     int CL, rpc;  // cluster size, rows per CTA (even)
     int np2;      // n rounded up to a power of two
+    int nfail_lo, nfail_hi; // this launch handles the chunk only if its failed-shot count lies in [lo, hi]: the host enqueues one
+                            // launch per cluster size (big clusters for a few failed shots: latency; small ones for many:
+                            // throughput) and the others return at once, so no host synchronisation is needed to choose
     // per-cluster workspaces
     unsigned long long *ws_mask; // [nclusters][npanels][rpc * CL]
     unsigned long long *ws_key;  // [nclusters][np2]
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(kOsdcThreads, 1) osd0_cluster_kernel(OsdCluste
     };
 
     const int nfail = *a.fail_count;
+    if (nfail < a.nfail_lo || nfail > a.nfail_hi) return; // another cluster size takes this chunk (uniform over the grid)
     for (int f = cid; f < nfail; f += nclusters) {
         const long long shot = a.fail_list[f];
         const real *llr = a.llr + (a.llr_by_shot ? shot : (long long)f) * n;
