@@ -37,6 +37,7 @@ namespace bposd {
 struct FastTables {
     int DC = 0, DV = 0;            // degree class (upper bounds, compile-time in the kernel)
     int regular = 0;               // every row has exactly DC entries and every column exactly DV
+    int ps = 0;                    // product-sum check update (rows keep their edges in ascending-column order: products are order dependent)
     int elem_bytes = 8;
     uint16_t *d_vslot = nullptr;   // [n, DV] message slot of the k-th edge (ascending row) of the bit at position q, 0xFFFF = none
     uint8_t *d_cdeg = nullptr;     // [m] degree of the check stored in physical row p
@@ -46,6 +47,8 @@ struct FastTables {
 };
 
 static inline bool fast_supported(int max_col_deg, int max_row_deg, int method) {
+    if (method == 0) // product-sum: instantiated for the degree classes up to (8, 4) (a row's tanh / log chain lives in registers)
+        return max_col_deg >= 1 && max_col_deg <= 4 && max_row_deg >= 1 && max_row_deg <= 8;
     return method == 1 && max_col_deg >= 1 && max_col_deg <= 8 && max_row_deg >= 1 && max_row_deg <= 16;
 }
 
@@ -124,11 +127,17 @@ static inline int fast_maxt(int n) { return fast_maxt_g(fast_geom(n, false)); }
 #ifndef BPOSD_REGCAP64_SMALL
 #define BPOSD_REGCAP64_SMALL 80
 #endif
-template <typename real, int MAXT, int DC, int DV, int VPT, bool REG>
-constexpr bool kFastSmallClass = sizeof(real) == 8 && MAXT == BPOSD_MID_MAXT && VPT == BPOSD_MID_VPT && MAXT == 256 && DC <= 6 && DV <= 3 && REG &&
+// product-sum in fp64: the kernel is bound by instruction issue (tanh / log / three IEEE divisions per edge), so resident
+// warps matter more than spills of the six interleaved chains
+#ifndef BPOSD_REGCAP64_PS
+#define BPOSD_REGCAP64_PS 64 // measured on B200 (profiles/r2n_ps_ab.log, cfg 4): 128 -> 36.6, 80 -> 46.1, 64 -> 52.6 M shot-iterations/s
+#endif
+template <typename real, int MAXT, int DC, int DV, int VPT, bool REG, bool PS = false>
+constexpr bool kFastSmallClass = sizeof(real) == 8 && MAXT == BPOSD_MID_MAXT && VPT == BPOSD_MID_VPT && MAXT == 256 && DC <= 6 && DV <= 3 && REG && !PS &&
                                  BPOSD_REGCAP64_SMALL < BPOSD_REGCAP64; // regular codes only: the irregular form spills twice as much (unmeasured)
-template <typename real, int MAXT, int DC = 16, int DV = 8, int VPT = 0, bool REG = false> constexpr int fast_minb() {
-    constexpr int cap = sizeof(real) == 8 ? (kFastSmallClass<real, MAXT, DC, DV, VPT, REG> ? BPOSD_REGCAP64_SMALL : BPOSD_REGCAP64) : BPOSD_REGCAP32;
+template <typename real, int MAXT, int DC = 16, int DV = 8, int VPT = 0, bool REG = false, bool PS = false> constexpr int fast_minb() {
+    constexpr int cap = sizeof(real) == 8 ? (PS ? BPOSD_REGCAP64_PS : (kFastSmallClass<real, MAXT, DC, DV, VPT, REG, PS> ? BPOSD_REGCAP64_SMALL : BPOSD_REGCAP64))
+                                          : BPOSD_REGCAP32;
     return (65536 / (MAXT * cap)) < 1 ? 1 : (65536 / (MAXT * cap));
 }
 
@@ -189,7 +198,7 @@ struct LayoutResult {
 // positions of two bits.  Downhill and sideways moves are taken (the plateaus are wide).
 static inline LayoutResult fast_layout_search(int m, int n, int DC, int DV, int elem_bytes, const std::vector<int> &row_ptr,
                                               const std::vector<int> &col_idx, const std::vector<int> &col_ptr,
-                                              const std::vector<int> &csc_slot) {
+                                              const std::vector<int> &csc_slot, bool keep_row_order = false) {
     const int E = row_ptr[m];
     LayoutOpt L;
     L.m = m; L.n = n; L.DC = DC; L.DV = DV; L.RS = fast_row_stride(DC, elem_bytes);
@@ -227,7 +236,8 @@ static inline LayoutResult fast_layout_search(int m, int n, int DC, int DV, int 
         if ((iter & 0xFFFF) == 0xFFFF && std::chrono::steady_clock::now() > t_end) break;
         const int e0 = (int)(rng() % (unsigned)E);
         if (L.cell(e0) <= 1) continue; // anchor moves at a conflicting edge
-        const unsigned mv = rng() % 3u;
+        unsigned mv = rng() % 3u;
+        if (keep_row_order && mv == 1) mv = (rng() & 1u) ? 0u : 2u; // product-sum: the edges of a row stay in ascending-column order
         if (mv == 0) {
             const int i1 = L.edge_row[e0], i2 = (int)(rng() % (unsigned)m);
             if (i1 == i2) continue;
@@ -272,12 +282,13 @@ static inline LayoutResult fast_layout_search(int m, int n, int DC, int DV, int 
 static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vector<int> &row_ptr,
                                      const std::vector<int> &col_idx, const std::vector<int> &col_ptr,
                                      const std::vector<int> &row_idx, const std::vector<int> &csc_slot,
-                                     int elem_bytes) {
+                                     int elem_bytes, int method = 1) {
     int mr = 0, mc = 0, minr = 1 << 30, minc = 1 << 30;
     for (int i = 0; i < m; i++) { int d = row_ptr[i + 1] - row_ptr[i]; mr = std::max(mr, d); minr = std::min(minr, d); }
     for (int j = 0; j < n; j++) { int d = col_ptr[j + 1] - col_ptr[j]; mc = std::max(mc, d); minc = std::min(minc, d); }
     fast_class(mc, mr, &t.DC, &t.DV);
     t.elem_bytes = elem_bytes;
+    t.ps = method == 0 ? 1 : 0;
     t.regular = (m > 0 && minr == t.DC && mr == t.DC && minc == t.DV && mc == t.DV) ? 1 : 0;
     const int RS = fast_row_stride(t.DC, elem_bytes);
     if ((long long)m * RS >= 0xFFFF || m == 0 || n >= 0xFFFF) { t.DC = 0; return cudaSuccess; } // slots and bits must fit in 16 bits
@@ -286,7 +297,7 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
     static std::map<std::string, LayoutResult> cache;
     std::string key;
     {
-        const int head[5] = {m, n, t.DC, t.DV, elem_bytes};
+        const int head[6] = {m, n, t.DC, t.DV, elem_bytes, t.ps};
         key.append(reinterpret_cast<const char *>(head), sizeof(head));
         key.append(reinterpret_cast<const char *>(row_ptr.data()), row_ptr.size() * sizeof(int));
         key.append(reinterpret_cast<const char *>(col_idx.data()), col_idx.size() * sizeof(int));
@@ -297,7 +308,7 @@ static inline cudaError_t fast_build(FastTables &t, int m, int n, const std::vec
         auto it = cache.find(key);
         if (it == cache.end()) {
             if (cache.size() > 64) cache.clear();
-            it = cache.emplace(key, fast_layout_search(m, n, t.DC, t.DV, elem_bytes, row_ptr, col_idx, col_ptr, csc_slot)).first;
+            it = cache.emplace(key, fast_layout_search(m, n, t.DC, t.DV, elem_bytes, row_ptr, col_idx, col_ptr, csc_slot, t.ps != 0)).first;
         }
         L = it->second;
     }
@@ -493,11 +504,40 @@ __device__ __forceinline__ void fast_check_compute(real (&v)[DC], real (&out)[DC
     }
 }
 
+// Product-sum form of the check update (row a5), the reference's own sequence: tanh of every incoming message once;
+// forward pass c2b[e_t] = prod_{u<t} tanh (from 1.0, ascending column); reverse pass x = c2b[e_t] * prod_{u>t} tanh
+// (accumulated from the last edge backwards), c2b[e_t] = (syndrome ? -1 : +1) * log((1 + x) / (1 - x)).  The layout pass
+// keeps a row's edges in ascending-column order for product-sum (products round differently in another order); the pads
+// of short rows hold +max, whose tanh is exactly 1.
 template <typename real, int DC, bool REG>
+__device__ __forceinline__ void fast_check_compute_ps(real (&v)[DC], real (&out)[DC], unsigned mt) {
+    real th[DC];
+#pragma unroll
+    for (int k = 0; k < DC; k++) th[k] = r_tanh(v[k] / 2);
+    real t = 1;
+#pragma unroll
+    for (int k = 0; k < DC; k++) { out[k] = t; t *= th[k]; }
+    t = 1;
+    const real sgn = (mt & 0x80u) ? (real)-1 : (real)1;
+#pragma unroll
+    for (int k = DC - 1; k >= 0; k--) {
+        const real x = ps_clamp(out[k] * t);
+        out[k] = sgn * r_log((1 + x) / (1 - x));
+        t *= th[k];
+    }
+    if (!REG) {
+        const int deg = (mt >> 1) & 0x1f;
+#pragma unroll
+        for (int k = 0; k < DC; k++) out[k] = (k < deg) ? out[k] : real_max<real>();
+    }
+}
+
+template <typename real, int DC, bool REG, bool PS = false>
 __device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alpha, uint32_t alpha_w) {
     real v[DC], out[DC];
     RowIO<real, DC>::load(row, v);
-    fast_check_compute<real, DC, REG>(v, out, mt, alpha, alpha_w);
+    if constexpr (PS) fast_check_compute_ps<real, DC, REG>(v, out, mt);
+    else fast_check_compute<real, DC, REG>(v, out, mt, alpha, alpha_w);
     RowIO<real, DC>::store(row, out);
 }
 
@@ -603,8 +643,8 @@ __device__ __forceinline__ unsigned fast_bit_sweep(unsigned char *smem_raw, cons
     return dnow;
 }
 
-template <typename real, int DC, int DV, int VPT, int MAXT, bool REG>
-__global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG>())) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
+template <typename real, int DC, int DV, int VPT, int MAXT, bool REG, bool PS = false>
+__global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG, PS>())) bp_fast_kernel(BpArgs<real> a, const uint16_t *__restrict__ vslot_tab,
                                                        const uint8_t *__restrict__ cdeg_tab,
                                                        const uint16_t *__restrict__ row_of_tab,
                                                        const uint16_t *__restrict__ bit_of_tab) {
@@ -713,7 +753,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG>
                 const unsigned mt = meta[p];
                 if (mt & 1u) ok = false;
                 if (last) continue;
-                fast_check_row<real, DC, REG>(msg + (size_t)p * RS, mt, alpha, alpha_w);
+                fast_check_row<real, DC, REG, PS>(msg + (size_t)p * RS, mt, alpha, alpha_w);
             }
             const int all_ok = __syncthreads_and(ok ? 1 : 0);
             if (it > 1 && all_ok) { conv = true; iters = it - 1; break; }
@@ -734,7 +774,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG>
                                 unsigned o = off[r][k];
                                 // register-capped class: keep the slot -> row arithmetic inside this branch (left alone, the
                                 // compiler hoists it out of the pass loop and parks one address per edge in a register)
-                                if constexpr (kFastSmallClass<real, MAXT, DC, DV, VPT, REG> && BPOSD_FLIP_NOHOIST != 0) asm volatile("" : "+r"(o));
+                                if constexpr (kFastSmallClass<real, MAXT, DC, DV, VPT, REG, PS> && BPOSD_FLIP_NOHOIST != 0) asm volatile("" : "+r"(o));
                                 const unsigned p = o / (unsigned)(RS * sizeof(real));
                                 atomicXor(&meta[p], 1u);
                             }
@@ -800,15 +840,26 @@ struct FastInst {
 };
 
 #ifdef BPOSD_FAST_INSTANTIATE
-#define BPOSD_FAST_REG(EXPR) do { if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } while (0)
+#define BPOSD_FAST_REG1(EXPR) do { if (reg__) { constexpr bool REG = true; EXPR; } else { constexpr bool REG = false; EXPR; } } while (0)
+// product-sum kernels exist for the throughput geometries of the degree classes up to (8, 4) (fast_supported)
+#define BPOSD_FAST_REG(EXPR)                                                                     \
+    do {                                                                                         \
+        if constexpr (DC <= 8) {                                                                 \
+            if (ps__) { constexpr bool PS = true; BPOSD_FAST_REG1(EXPR); break; }                \
+        }                                                                                        \
+        { constexpr bool PS = false; BPOSD_FAST_REG1(EXPR); }                                    \
+    } while (0)
+#define BPOSD_FAST_REG_MS(EXPR) do { constexpr bool PS = false; BPOSD_FAST_REG1(EXPR); } while (0)
 #define BPOSD_FAST_GEOM(t, geom, EXPR)                                                           \
     do {                                                                                         \
         const int geom__ = (geom);                                                               \
         const bool reg__ = t.regular != 0;                                                       \
+        const bool ps__ = t.ps != 0;                                                             \
+        (void)ps__;                                                                              \
         if (geom__ == 0) { constexpr int VPT = 2, MAXT = 128; BPOSD_FAST_REG(EXPR); }            \
         else if (geom__ == 1) { constexpr int VPT = BPOSD_MID_VPT, MAXT = BPOSD_MID_MAXT; BPOSD_FAST_REG(EXPR); } \
         else if (geom__ == 4) { constexpr int VPT = sizeof(real) == 8 ? BPOSD_LAT_VPT64 : BPOSD_LAT_VPT32,               \
-                                              MAXT = sizeof(real) == 8 ? BPOSD_LAT_MAXT64 : BPOSD_LAT_MAXT32; BPOSD_FAST_REG(EXPR); } \
+                                              MAXT = sizeof(real) == 8 ? BPOSD_LAT_MAXT64 : BPOSD_LAT_MAXT32; BPOSD_FAST_REG_MS(EXPR); } \
         else if (geom__ == 2) { constexpr int VPT = 8, MAXT = 512; BPOSD_FAST_REG(EXPR); }       \
         else { constexpr int VPT = 8, MAXT = 1024; BPOSD_FAST_REG(EXPR); }                       \
     } while (0)
@@ -816,18 +867,18 @@ struct FastInst {
 template <typename real, int DC, int DV>
 cudaError_t FastInst<real, DC, DV>::set_smem(const FastTables &t, int geom, size_t smem) {
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_GEOM(t, geom, e = cudaFuncSetAttribute(bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BPOSD_FAST_GEOM(t, geom, e = cudaFuncSetAttribute(bp_fast_kernel<real, DC, DV, VPT, MAXT, REG, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return e;
 }
 template <typename real, int DC, int DV>
 cudaError_t FastInst<real, DC, DV>::occupancy(const FastTables &t, int geom, int threads, size_t smem, int *occ) {
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_GEOM(t, geom, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bp_fast_kernel<real, DC, DV, VPT, MAXT, REG>, threads, smem));
+    BPOSD_FAST_GEOM(t, geom, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bp_fast_kernel<real, DC, DV, VPT, MAXT, REG, PS>, threads, smem));
     return e;
 }
 template <typename real, int DC, int DV>
 void FastInst<real, DC, DV>::launch(const FastTables &t, int geom, const BpArgs<real> &a, int grid, int threads, int smem, cudaStream_t st) {
-    BPOSD_FAST_GEOM(t, geom, (bp_fast_kernel<real, DC, DV, VPT, MAXT, REG><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg, t.d_row_of, t.d_bit_of)));
+    BPOSD_FAST_GEOM(t, geom, (bp_fast_kernel<real, DC, DV, VPT, MAXT, REG, PS><<<grid, threads, smem, st>>>(a, t.d_vslot, t.d_cdeg, t.d_row_of, t.d_bit_of)));
 }
 #endif // BPOSD_FAST_INSTANTIATE
 

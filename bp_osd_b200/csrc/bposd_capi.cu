@@ -85,7 +85,7 @@ struct bposd_handle {
     int osdl_alloc_grid = 0;
     // large-H OSD-0, one thread-block cluster per failed shot (osd_cluster_kernel.cuh): rows split over the cluster, masks TMA-streamed
     bool osd_clus = false;
-    struct OsdcCfg { int CL, rpc, smem, ncl; };
+    struct OsdcCfg { int CL, rpc, smem, ncl, stages; };
     std::vector<OsdcCfg> osdc; // cluster sizes, largest first: a few failed shots take the big clusters, many the small ones
     int osdc_npanels = 0;
     size_t osdc_alloc_mask = 0, osdc_alloc_shots = 0;
@@ -210,7 +210,7 @@ static int plan_geometry_t(bposd_handle *h) {
     }
     if (want == 0) { kernel = 0; smem = (size_t)m + 16; }
     // cluster kernel: min-sum, supported degrees, and either forced or nothing smem-resident fits
-    if ((want == 3 || (want < 0 && kernel == 0)) && fast_supported(h->max_col_deg, h->max_row_deg, h->bp_method) && m > 0) {
+    if ((want == 3 || (want < 0 && kernel == 0)) && h->bp_method == 1 && fast_supported(h->max_col_deg, h->max_row_deg, h->bp_method) && m > 0) {
         int DCc = 0, DVc = 0;
         fast_class(h->max_col_deg, h->max_row_deg, &DCc, &DVc);
         // candidate cluster sizes: the smallest cluster whose per-CTA slice fits in shared memory first (fewer remote
@@ -275,6 +275,7 @@ static int plan_geometry_t(bposd_handle *h) {
             h->lat_geom = h->bp_geom; h->lat_threads = threads;
         }
         h->lat_max_shots = h->sm_count;
+        if (h->bp_method != 1) { h->lat_geom = -1; h->lat_max_shots = 0; } // the latency geometry is instantiated for min-sum only
     } else if (kernel == 1) {
         CU_TRY(h, cudaFuncSetAttribute(bp_generic_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bp_generic_kernel<real, true>, threads, smem));
@@ -341,8 +342,10 @@ static int plan_geometry_t(bposd_handle *h) {
             bposd_handle::OsdcCfg c;
             c.CL = CL;
             c.rpc = (((m + CL - 1) / CL) + 1) & ~1;
-            c.smem = (int)osdc_layout(c.rpc, h->osdc_npanels).total;
             c.ncl = 0;
+            c.stages = kOsdcMaxStages; // as deep a TMA ring as fits
+            while (c.stages > 2 && osdc_layout(c.rpc, h->osdc_npanels, c.stages).total > (size_t)h->smem_optin) c.stages--;
+            c.smem = (int)osdc_layout(c.rpc, h->osdc_npanels, c.stages).total;
             if ((size_t)c.smem > (size_t)h->smem_optin) continue;
             smem_max = std::max(smem_max, c.smem);
             h->osdc.push_back(c);
@@ -535,7 +538,7 @@ extern "C" int bposd_create(const int32_t *indptr, const int32_t *indices, int32
     CR_TRY(cudaMalloc((void **)&h->d_counters, 8 * sizeof(unsigned long long)));
     CR_TRY(cudaMalloc((void **)&h->d_minw, sizeof(int)));
     if (fast_supported(h->max_col_deg, h->max_row_deg, bp_method)) {
-        cudaError_t e = fast_build(h->fast, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot, precision / 8);
+        cudaError_t e = fast_build(h->fast, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot, precision / 8, bp_method);
         if (e != cudaSuccess) { h->err = std::string("fast_build: ") + cudaGetErrorString(e); return die(BPOSD_ECUDA); }
     }
     int rc = plan_geometry(h);
@@ -670,7 +673,7 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
         const int np2 = osd_reg_np2(n);
         size_t need_mask = 0, need_shots = 0;
         for (const auto &c : h->osdc) {
-            const size_t ncl = (size_t)std::min<long long>(Bc, c.ncl);
+            const size_t ncl = (size_t)c.ncl; // for every resident cluster, once (no re-allocation when the batch size changes)
             need_mask = std::max(need_mask, ncl * h->osdc_npanels * c.rpc * c.CL);
             need_shots = std::max(need_shots, ncl);
         }
@@ -700,7 +703,7 @@ static int launch_osd(bposd_handle *h, cudaStream_t st, const GraphDev &g, const
             o.osd0 = d_osd0; o.osdw = d_osdw;
             o.stat = d_stat;
             o.maxrank = h->rank; o.npanels = h->osdc_npanels; o.CL = c.CL; o.rpc = c.rpc; o.np2 = np2;
-            o.nfail_lo = lo; o.nfail_hi = hi;
+            o.nfail_lo = lo; o.nfail_hi = hi; o.stages = c.stages;
             o.ws_mask = h->d_osdc_mask; o.ws_key = h->d_osdc_key; o.ws_idx = h->d_osdc_idx; o.ws_piv = h->d_osdc_piv;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(ncl * c.CL, 1, 1); cfg.blockDim = dim3(kOsdcThreads, 1, 1); cfg.dynamicSmemBytes = c.smem; cfg.stream = st;

@@ -46,6 +46,7 @@ struct OsdClusterArgs {
     int npanels;  // ceil(n / 64)
     int CL, rpc;  // cluster size, rows per CTA (even)
     int np2;      // n rounded up to a power of two
+    int stages;   // TMA ring depth of this launch (2 .. kOsdcMaxStages)
     int nfail_lo, nfail_hi; // this launch handles the chunk only if its failed-shot count lies in [lo, hi]: the host enqueues one
                             // launch per cluster size (big clusters for a few failed shots: latency; small ones for many:
                             // throughput) and the others return at once, so no host synchronisation is needed to choose
@@ -56,16 +57,17 @@ struct OsdClusterArgs {
     OsdcPivot *ws_piv;           // [nclusters][min(m, n)]
 };
 
-constexpr int kOsdcStages = 3;   // TMA ring depth
+constexpr int kOsdcMaxStages = 8; // TMA ring depth: as many replays ahead as shared memory allows, at most 8 (masks come from HBM once
+                                  // several clusters run: ~2 us away, a replay takes ~1 us)
 constexpr int kOsdcThreads = 512;
 
 struct OsdcLayout { size_t o_ring, o_tab, o_gath, o_rk, o_candp, o_candr, o_cands, o_plane, o_used, o_sbit, o_red, o_mbar, o_plist, o_prow, o_mjs, o_cs, total; };
-__host__ __device__ inline OsdcLayout osdc_layout(int rpc, int npanels) {
+__host__ __device__ inline OsdcLayout osdc_layout(int rpc, int npanels, int stages) {
     OsdcLayout L;
     auto al = [](size_t x) { return (x + 15) / 16 * 16; };
     const size_t pw = (size_t)(rpc + 31) / 32;
     size_t o = al((size_t)rpc * 8);                                   // P: the panel word of every local check
-    L.o_ring = o; o = al(o + (size_t)kOsdcStages * rpc * 8);          // multiplier masks of replayed panels (TMA destinations)
+    L.o_ring = o; o = al(o + (size_t)stages * rpc * 8);               // multiplier masks of replayed panels (TMA destinations)
     L.o_tab = o; o = al(o + 8 * 256 * 8);                             // XOR tables
     L.o_gath = o; o = al(o + 2 * 64 * 8);                             // gathered pivot-row words, double buffered
     L.o_rk = o; o = al(o + 64 * 8);                                   // resolved pivot words
@@ -76,7 +78,7 @@ __host__ __device__ inline OsdcLayout osdc_layout(int rpc, int npanels) {
     L.o_used = o; o = al(o + pw * 4);
     L.o_sbit = o; o = al(o + pw * 4);
     L.o_red = o; o = al(o + 32 * 4);
-    L.o_mbar = o; o = al(o + kOsdcStages * 8);
+    L.o_mbar = o; o = al(o + kOsdcMaxStages * 8);
     L.o_plist = o; o = al(o + ((size_t)npanels + 1) * 4 * 2);         // panels that hold pivots; first pivot of each
     L.o_prow = o; o = al(o + 64 * 4);                                 // checks of this panel's pivots
     L.o_mjs = o; o = al(o + 64 * 8);                                  // their multiplier masks
@@ -116,7 +118,8 @@ __global__ void __launch_bounds__(kOsdcThreads, 1) osd0_cluster_kernel(OsdCluste
     const int base = rank * rpc, nloc = max(0, min(rpc, m - base));
     const long long gt = (long long)rank * T + tid, GT = (long long)CL * T; // cluster-wide thread index
     const int mpad = rpc * CL;
-    const OsdcLayout L = osdc_layout(rpc, a.npanels);
+    const int kOsdcStages = a.stages;
+    const OsdcLayout L = osdc_layout(rpc, a.npanels, kOsdcStages);
     unsigned long long *P = reinterpret_cast<unsigned long long *>(smem_raw);
     unsigned long long *ring = reinterpret_cast<unsigned long long *>(smem_raw + L.o_ring);
     unsigned long long *tab = reinterpret_cast<unsigned long long *>(smem_raw + L.o_tab);

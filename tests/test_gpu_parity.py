@@ -69,8 +69,8 @@ def test_g1_readme_known_answer_on_gpu(torch_cuda):
 @pytest.mark.parametrize("kernel", [0, 1, 2, 3])
 def test_golden_fixtures(torch_cuda, cfg_codes, name, kernel):
     g = load_golden(name)
-    if g["kw"]["bp_method"] == "ps" and kernel in (2, 3):
-        pytest.skip("the in-place and the cluster kernel are min-sum kernels; product-sum runs on the two-array kernels")
+    if g["kw"]["bp_method"] == "ps" and kernel == 3:
+        pytest.skip("the cluster kernel is a min-sum kernel; product-sum runs on the in-place and the two-array kernels")
     H = cfg_codes(g["cfg"]).hz
     d, out = gpu_decode(torch_cuda, H, g["syndromes"], kernel=kernel, error_rate=g["p"], **g["kw"])
     assert_exact(out, g)
@@ -119,11 +119,32 @@ def test_product_sum_lifted_product(torch_cuda, oracle_mod, cfg_codes):
     _, syn = random_syndromes(H, 0.05, 300, seed=12345)
     ref = oracle_mod.OracleDecoder(H, error_rate=0.05, **kw).decode_batch(syn)
     assert (ref["iter"] > 100).sum() >= 20  # long-running shots are part of the comparison
-    for kernel in (0, 1):
-        _, out = gpu_decode(torch_cuda, H, syn, kernel=kernel, error_rate=0.05, **kw)
+    for kernel in (None, 0, 1, 2):   # None: the automatic choice, the in-place kernel (2)
+        d, out = gpu_decode(torch_cuda, H, syn, kernel=kernel, error_rate=0.05, **kw)
+        assert d.info()["bp_kernel"] == (2 if kernel is None else kernel)
         assert_exact(out, ref, llr_exact=False)
         # NaN payloads are the one thing that legitimately differs (x86 and sm_100a generate different quiet NaNs)
         assert np.array_equal(out["llr"], ref["llr"], equal_nan=True), "log_prob_ratios not bit-exact"
+
+
+@pytest.mark.parametrize("cfg,p,B", [(1, 0.08, 800), (2, 0.06, 500)])
+def test_product_sum_in_place_kernel_other_degree_classes(torch_cuda, oracle_mod, cfg_codes, cfg, p, B):
+    """Product-sum on the in-place kernel for the (4, 2) class and for an IRREGULAR code of the (8, 4) class (rows of 7 in
+    slots of 8: the pads hold +max, whose tanh is exactly 1; bits of 3 and 4 edges), with non-uniform priors on the second:
+    bit for bit against the oracle and against the two-array kernel."""
+    H = cfg_codes(cfg).hz
+    n = H.shape[1]
+    kw = dict(max_iter=0, bp_method="ps", ms_scaling_factor=0, osd_method="osd_cs", osd_order=5)
+    rng = np.random.default_rng(3 + cfg)
+    probs = np.full(n, p) if cfg == 1 else rng.uniform(0.5 * p, 1.5 * p, size=n)
+    e = (rng.random((B, n)) < probs).astype(np.uint8)
+    syn = np.asarray((H @ e.T) % 2, dtype=np.uint8).T.copy()
+    ref = oracle_mod.OracleDecoder(H, channel_probs=probs, **kw).decode_batch(syn)
+    assert (ref["converge"] == 0).sum() >= 3
+    for kernel in (2, 1):
+        d, out = gpu_decode(torch_cuda, H, syn, kernel=kernel, probs=probs, **kw)
+        assert d.info()["bp_kernel"] == kernel
+        assert_exact(out, ref)
 
 
 def test_nonuniform_and_zero_probabilities(torch_cuda, oracle_mod, cfg_codes):

@@ -164,8 +164,8 @@ def _ulps(got, want):
 
 def test_shared_math_is_pinned_to_glibc(oracle_mod):
     """include/bposd_math.h (compiled into the oracle AND the CUDA kernels) against the host libm: the portable tanh / log
-    stay within 3 / 1 ulp of glibc's on the ranges product-sum BP visits (both are fdlibm-class algorithms with a
-    < 2.5 ulp / < 1 ulp error bound, measured against long double: 2.17 vs 2.15 and 0.89 vs 0.52 ulp), and agree on
+    stay within 4 / 1 ulp of glibc's on the ranges product-sum BP visits (classical algorithms with a
+    < 2.5 ulp / < 0.85 ulp error measured against long double; glibc: 2.15 / 0.52 ulp), and agree on
     every special value."""
     import math
     L = oracle_mod.lib()
@@ -189,7 +189,7 @@ def test_shared_math_is_pinned_to_glibc(oracle_mod):
         lw = math.log(y)
         if lw != 0.0:
             worst_l = max(worst_l, _ulps(L.oracle_math_log(y), lw))
-    assert worst_t <= 3.0, worst_t
+    assert worst_t <= 4.0, worst_t
     assert worst_l <= 1.0, worst_l
     inf, nan = float("inf"), float("nan")
     assert L.oracle_math_tanh(inf) == 1.0 and L.oracle_math_tanh(-inf) == -1.0 and math.isnan(L.oracle_math_tanh(nan))
