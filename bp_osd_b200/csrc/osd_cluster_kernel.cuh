@@ -61,7 +61,7 @@ constexpr int kOsdcMaxStages = 8; // TMA ring depth: as many replays ahead as sh
                                   // several clusters run: ~2 us away, a replay takes ~1 us)
 constexpr int kOsdcThreads = 512;
 
-struct OsdcLayout { size_t o_ring, o_tab, o_gath, o_rk, o_candp, o_candr, o_cands, o_plane, o_used, o_sbit, o_red, o_mbar, o_plist, o_prow, o_mjs, o_cs, total; };
+struct OsdcLayout { size_t o_ring, o_tab, o_gath, o_rk, o_cf, o_candp, o_candr, o_cands, o_plane, o_used, o_sbit, o_red, o_mbar, o_plist, o_prow, o_mjs, o_cs, total; };
 __host__ __device__ inline OsdcLayout osdc_layout(int rpc, int npanels, int stages) {
     OsdcLayout L;
     auto al = [](size_t x) { return (x + 15) / 16 * 16; };
@@ -71,6 +71,7 @@ __host__ __device__ inline OsdcLayout osdc_layout(int rpc, int npanels, int stag
     L.o_tab = o; o = al(o + 8 * 256 * 8);                             // XOR tables
     L.o_gath = o; o = al(o + 2 * 64 * 8);                             // gathered pivot-row words, double buffered
     L.o_rk = o; o = al(o + 64 * 8);                                   // resolved pivot words
+    L.o_cf = o; o = al(o + 64 * (8 + 8 + 4));                         // C / F rows and checks of the replayed panel's pivots
     L.o_candp = o; o = al(o + 2 * 16 * 8);                            // pivot proposals: panel word ...
     L.o_candr = o; o = al(o + 2 * 16 * 4);                            // ... check ...
     L.o_cands = o; o = al(o + 2 * 16 * 4);                            // ... syndrome bit
@@ -125,6 +126,8 @@ __global__ void __launch_bounds__(kOsdcThreads, 1) osd0_cluster_kernel(OsdCluste
     unsigned long long *tab = reinterpret_cast<unsigned long long *>(smem_raw + L.o_tab);
     unsigned long long *gath = reinterpret_cast<unsigned long long *>(smem_raw + L.o_gath);
     unsigned long long *Rk = reinterpret_cast<unsigned long long *>(smem_raw + L.o_rk);
+    unsigned long long *cfC = reinterpret_cast<unsigned long long *>(smem_raw + L.o_cf), *cfF = cfC + 64;
+    int *cfRow = reinterpret_cast<int *>(cfF + 64);
     unsigned long long *candp = reinterpret_cast<unsigned long long *>(smem_raw + L.o_candp);
     unsigned *candr = reinterpret_cast<unsigned *>(smem_raw + L.o_candr);
     unsigned *cands = reinterpret_cast<unsigned *>(smem_raw + L.o_cands);
@@ -149,7 +152,8 @@ __global__ void __launch_bounds__(kOsdcThreads, 1) osd0_cluster_kernel(OsdCluste
         for (int s = 0; s < kOsdcStages; s++) osdc_mbar_init(mbar0 + 8u * s, 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    unsigned issued = 0, consumed = 0; // bulk copies issued / waited for (ring stage = count % stages, parity = (count / stages) & 1)
+    // ring bookkeeping: stage of the next bulk copy to issue / to wait for, and the mbarrier phase parity of the latter
+    uint32_t ist = 0, cst = 0, cpar = 0;
 
     // push one value into the same shared-memory location of every CTA of the cluster
     auto push_all_u64 = [&](void *local, unsigned long long v) {
@@ -216,10 +220,9 @@ __global__ void __launch_bounds__(kOsdcThreads, 1) osd0_cluster_kernel(OsdCluste
             const int npairs = np_cnt;
             if (tid == 0) // first replays' masks into the ring
                 for (int s = 0; s < npairs && s < kOsdcStages; s++) {
-                    const uint32_t st = issued % kOsdcStages;
-                    osdc_mbar_expect(mbar0 + 8u * st, ring_bytes);
-                    osdc_bulk_g2s(smem_u32(ring + (size_t)st * rpc), maskbase + (size_t)plist[s] * mpad + base, ring_bytes, mbar0 + 8u * st);
-                    issued++;
+                    osdc_mbar_expect(mbar0 + 8u * ist, ring_bytes);
+                    osdc_bulk_g2s(smem_u32(ring + (size_t)ist * rpc), maskbase + (size_t)plist[s] * mpad + base, ring_bytes, mbar0 + 8u * ist);
+                    ist = ist + 1 == (uint32_t)kOsdcStages ? 0u : ist + 1;
                 }
             OsdcPivot rec{0ull, 0ull, -1, 0};
             if (npairs > 0 && tid < 64) {
@@ -232,29 +235,42 @@ __global__ void __launch_bounds__(kOsdcThreads, 1) osd0_cluster_kernel(OsdCluste
                 const int par = pairstep & 1;
                 pairstep++;
                 // owners hand the current words of panel q's pivot rows to every CTA
-                if (tid < cnt) {
-                    const int li = rec.row - base;
-                    if (li >= 0 && li < nloc) push_all_u64(&gath[par * 64 + tid], P[li]);
-                }
-                cluster_sync_all();
                 if (tid < 64) {
-                    unsigned long long R = 0, fin = 0;
+                    cfC[tid] = rec.C; cfF[tid] = rec.F; cfRow[tid] = rec.row;
                     if (tid < cnt) {
-                        const unsigned long long C = rec.C, F = rec.F;
-                        for (int k2 = 0; k2 < cnt; k2++) {
-                            const unsigned long long gv = gath[par * 64 + k2];
-                            R ^= ((C >> k2) & 1ull) ? gv : 0ull;
-                            fin ^= ((F >> k2) & 1ull) ? gv : 0ull;
-                        }
                         const int li = rec.row - base;
-                        if (li >= 0 && li < nloc) P[li] = fin; // the apply below skips pivot rows of q (their stored mask is 0)
+                        if (li >= 0 && li < nloc) push_all_u64(&gath[par * 64 + tid], P[li]);
                     }
-                    Rk[tid] = R;
                     // the next replay's pivots (global, L2): in flight during the rest of this one
                     rec = OsdcPivot{0ull, 0ull, -1, 0};
                     if (s + 1 < npairs) {
                         const int ps2 = pfirst[s + 1], cnt2 = pfirst[s + 2] - ps2;
                         if (tid < cnt2) rec = piv[ps2 + tid];
+                    }
+                }
+                cluster_sync_all();
+                {
+                    // R = C g and the final pivot rows F g: pivot k = tid / 8, eight threads (lanes of one warp) share its 64 terms
+                    const int k = tid >> 3, sl = tid & 7;
+                    unsigned long long R = 0, fin = 0;
+                    if (k < cnt && 8 * sl < cnt) {
+                        const unsigned cb = (unsigned)(cfC[k] >> (8 * sl)) & 255u, fb = (unsigned)(cfF[k] >> (8 * sl)) & 255u;
+                        const unsigned long long *gp = gath + par * 64 + 8 * sl;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const unsigned long long gv = gp[j];
+                            R ^= ((cb >> j) & 1u) ? gv : 0ull;
+                            fin ^= ((fb >> j) & 1u) ? gv : 0ull;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) { R ^= osdc_shfl_xor64(R, o); fin ^= osdc_shfl_xor64(fin, o); }
+                    if (sl == 0 && k < 64) {
+                        Rk[k] = (k < cnt) ? R : 0ull;
+                        if (k < cnt) {
+                            const int li = cfRow[k] - base;
+                            if (li >= 0 && li < nloc) P[li] = fin; // the apply below skips pivot rows of q (their stored mask is 0)
+                        }
                     }
                 }
                 __syncthreads();
@@ -266,25 +282,26 @@ __global__ void __launch_bounds__(kOsdcThreads, 1) osd0_cluster_kernel(OsdCluste
                     for (int b = 0; b < 8; b++) v ^= ((e >> b) & 1) ? Rk[b0 + b] : 0ull;
                     tab[e] = v;
                 }
-                const uint32_t st = consumed % kOsdcStages;
-                osdc_mbar_wait(mbar0 + 8u * st, (consumed / kOsdcStages) & 1u);
-                consumed++;
+                osdc_mbar_wait(mbar0 + 8u * cst, cpar);
                 __syncthreads();
-                const unsigned long long *Mq = ring + (size_t)st * rpc;
+                const unsigned long long *Mq = ring + (size_t)cst * rpc;
                 for (int i = tid; i < nloc; i += T) {
                     const unsigned long long mk = Mq[i];
                     if (mk) {
                         unsigned long long v = 0;
-                        for (int b = 0; b < ntab; b++) v ^= tab[b * 256 + (int)((mk >> (8 * b)) & 255ull)];
+#pragma unroll
+                        for (int b = 0; b < 8; b++)
+                            if (b < ntab) v ^= tab[b * 256 + (int)((mk >> (8 * b)) & 255ull)];
                         P[i] ^= v;
                     }
                 }
+                cst++;
+                if (cst == (uint32_t)kOsdcStages) { cst = 0; cpar ^= 1u; }
                 __syncthreads();
                 if (tid == 0 && s + kOsdcStages < npairs) { // the ring stage is free again: next replay's masks
-                    const uint32_t st2 = issued % kOsdcStages;
-                    osdc_mbar_expect(mbar0 + 8u * st2, ring_bytes);
-                    osdc_bulk_g2s(smem_u32(ring + (size_t)st2 * rpc), maskbase + (size_t)plist[s + kOsdcStages] * mpad + base, ring_bytes, mbar0 + 8u * st2);
-                    issued++;
+                    osdc_mbar_expect(mbar0 + 8u * ist, ring_bytes);
+                    osdc_bulk_g2s(smem_u32(ring + (size_t)ist * rpc), maskbase + (size_t)plist[s + kOsdcStages] * mpad + base, ring_bytes, mbar0 + 8u * ist);
+                    ist = ist + 1 == (uint32_t)kOsdcStages ? 0u : ist + 1;
                 }
             }
             __syncthreads();

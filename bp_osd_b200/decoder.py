@@ -28,6 +28,9 @@ __all__ = ["BpOsdDecoder", "bposd_decoder", "BatchResult", "prob_thresholds", "p
 _BP_NAMES = {
     "ps": _capi.BP_PRODUCT_SUM, "product_sum": _capi.BP_PRODUCT_SUM, "prod_sum": _capi.BP_PRODUCT_SUM,
     "0": _capi.BP_PRODUCT_SUM, 0: _capi.BP_PRODUCT_SUM,
+    # the pre-v2 "log-domain" spellings: ldpc v2 runs every BP variant in the log domain, so they name the same two updates
+    "ps_log": _capi.BP_PRODUCT_SUM, "psl": _capi.BP_PRODUCT_SUM, "product_sum_log": _capi.BP_PRODUCT_SUM,
+    "ms_log": _capi.BP_MINIMUM_SUM, "msl": _capi.BP_MINIMUM_SUM, "minimum_sum_log": _capi.BP_MINIMUM_SUM,
     "ms": _capi.BP_MINIMUM_SUM, "minimum_sum": _capi.BP_MINIMUM_SUM, "min_sum": _capi.BP_MINIMUM_SUM,
     "1": _capi.BP_MINIMUM_SUM, 1: _capi.BP_MINIMUM_SUM,
 }
@@ -104,8 +107,13 @@ class BpOsdDecoder:
             raise TypeError(f"unexpected keyword argument(s): {sorted(unknown)}")
         if schedule not in ("parallel", 0, "0"):
             raise ValueError("only the parallel (flooding) BP schedule is implemented")
-        if input_vector_type not in ("syndrome", 0, "0"):
-            raise ValueError("only input_vector_type='syndrome' is implemented")
+        ivt = {"syndrome": 0, 0: 0, "0": 0, "received_vector": 1, 1: 1, "1": 1, "auto": 2, 2: 2, "2": 2}.get(
+            input_vector_type.lower() if isinstance(input_vector_type, str) else input_vector_type)
+        if ivt is None:
+            raise ValueError("input_vector_type must be 'syndrome', 'received_vector' or 'auto'")
+        # 'received_vector' (ldpc v2 option, not reachable from the reference): decode(r) decodes the syndrome H r and returns
+        # r + decoding, the corrected word; 'auto' picks by the length of the input (ambiguous when m == n)
+        self._input_vector_type = ivt
         h = parity_check_matrix
         if not sp.issparse(h):
             h = np.asarray(h)
@@ -260,6 +268,27 @@ class BpOsdDecoder:
         written straight to pinned host memory).  ``osd0_decoding``, ``bp_decoding`` and ``log_prob_ratios`` are
         converted to the caller's dtype when they are first read, not here."""
         s = syndrome if type(syndrome) is np.ndarray else np.asarray(syndrome)
+        if self._input_vector_type != 0:
+            if s.ndim != 1:
+                raise ValueError("input vector must be one-dimensional")
+            received = self._input_vector_type == 1
+            if self._input_vector_type == 2:
+                if self.m == self.n:
+                    raise ValueError("input_vector_type='auto' is ambiguous for a square parity-check matrix")
+                received = s.shape[0] == self.n
+            if received:
+                if s.shape[0] != self.n:
+                    raise ValueError(f"received vector must have length {self.n}")
+                r = (s.astype(np.int64) & 1).astype(np.uint8)
+                self._input_vector_type, keep = 0, self._input_vector_type
+                try:
+                    self.decode(np.asarray(self._pcm @ r) % 2)
+                finally:
+                    self._input_vector_type = keep
+                self.osdw_decoding = (self.osdw_decoding ^ r.astype(self.osdw_decoding.dtype))
+                self._osd0 = self.osd0_decoding ^ r.astype(self.osdw_decoding.dtype)
+                self._bp = self.bp_decoding ^ r.astype(self.osdw_decoding.dtype)
+                return self.osdw_decoding
         if s.ndim != 1 or s.shape[0] != self.m:
             raise ValueError(f"syndrome must have length {self.m}")
         kind = s.dtype.kind

@@ -147,6 +147,36 @@ def test_product_sum_in_place_kernel_other_degree_classes(torch_cuda, oracle_mod
         assert_exact(out, ref)
 
 
+def test_received_vector_input_and_method_aliases(torch_cuda, oracle_mod, cfg_codes):
+    """SURVEY row f4 (ldpc options the reference never reaches): input_vector_type='received_vector' decodes the syndrome of
+    the received word and returns the corrected word r + decoding; 'auto' picks by length; the pre-v2 spellings 'ms_log' /
+    'ps_log' name the same two updates.  The serial schedule stays rejected."""
+    from bp_osd_b200 import BpOsdDecoder
+    H = cfg_codes(2).hz
+    m, n = H.shape
+    kw = dict(max_iter=20, ms_scaling_factor=0, osd_method="osd_cs", osd_order=4)
+    rng = np.random.default_rng(5)
+    r = (rng.random(n) < 0.05).astype(np.uint8)
+    syn = np.asarray(H @ r) % 2
+    ref = oracle_mod.OracleDecoder(H, error_rate=0.05, bp_method="ms", **kw)
+    ref.decode(syn)
+    for ivt, vec in (("received_vector", r), ("auto", r), ("auto", syn), ("syndrome", syn)):
+        d = BpOsdDecoder(H, error_rate=0.05, bp_method="ms_log", input_vector_type=ivt, **kw)
+        out = d.decode(vec)
+        want = ref.osdw_decoding ^ r if len(vec) == n else ref.osdw_decoding
+        assert (out == want).all(), ivt
+        if len(vec) == n:
+            assert not (np.asarray(H @ out) % 2).any()   # the corrected word has a zero syndrome
+            assert (d.osd0_decoding == (ref.osd0_decoding ^ r)).all() and (d.bp_decoding == (ref.bp_decoding ^ r)).all()
+    ps = oracle_mod.OracleDecoder(H, error_rate=0.05, bp_method="ps", **kw)
+    ps.decode(syn)
+    assert (BpOsdDecoder(H, error_rate=0.05, bp_method="ps_log", **kw).decode(syn) == ps.osdw_decoding).all()
+    with pytest.raises(ValueError):
+        BpOsdDecoder(H, error_rate=0.05, bp_method="ms", schedule="serial", **kw)
+    with pytest.raises(ValueError):
+        BpOsdDecoder(H, error_rate=0.05, bp_method="ms", input_vector_type="codeword", **kw)
+
+
 def test_nonuniform_and_zero_probabilities(torch_cuda, oracle_mod, cfg_codes):
     """Soft OSD weights in ascending-index fp64 order, and p = 0 entries (prior +inf, weight inf) without NaN."""
     H = cfg_codes(2).hz
