@@ -244,6 +244,11 @@ def run_reference(args, cfg, c):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args, cfg, c):
+    # stdout carries exactly one JSON line: whatever libraries print while the job runs (NCCL's version banner, warnings of
+    # the process-group backend) is sent to stderr at the file-descriptor level; the line is written to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from bp_osd_b200 import codes, BpOsdDecoder
@@ -468,7 +473,8 @@ def run_gpu(args, cfg, c):
                              "logical_failures_last_step": int(counters[1].item()) if have_logicals else None,
                              "shots_last_step": int(counters[0].item())},
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

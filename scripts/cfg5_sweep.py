@@ -22,6 +22,9 @@ ap.add_argument("--chunk", type=int, default=16384)
 ap.add_argument("--precision", type=int, default=64)
 ap.add_argument("--cfg", type=int, default=5)
 a = ap.parse_args()
+sys.stdout.flush()
+REAL_STDOUT = os.dup(1)   # JSON lines go here; whatever libraries print (NCCL banner) goes to stderr
+os.dup2(2, 1)
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -40,7 +43,8 @@ out = {"osdw": torch.empty((a.chunk, nb), dtype=torch.uint8, device=dev), "conve
 
 
 def run(B, shot0):
-    lo, hi = shard_range(B, rank, world)
+    lo, cnt = shard_range(B, rank, world)   # (start, count) of this rank's share of the batch
+    hi = lo + cnt
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = conv = osd = 0
     ms_bp = ms_osd = 0.0
@@ -72,11 +76,11 @@ for B in a.batches:
     (ms, ms_bp, ms_osd), (iters, conv, osd, shots) = run(B, shot0)
     shot0 += B
     if rank == 0:
-        print(json.dumps({"config": 5 if a.cfg == 5 else a.cfg, "n_gpus": world, "batch": B, "ms": ms, "shots_per_s": B / (ms * 1e-3),
+        os.write(REAL_STDOUT, (json.dumps({"config": 5 if a.cfg == 5 else a.cfg, "n_gpus": world, "batch": B, "ms": ms, "shots_per_s": B / (ms * 1e-3),
                           "bp_ms_max_rank": ms_bp, "osd_ms_max_rank": ms_osd, "mean_iterations": iters / max(shots, 1),
                           "bp_converged_frac": conv / max(shots, 1), "osd_shots": osd,
-                          "bp_shot_iterations_per_s": iters / (ms_bp * 1e-3) / world * world if ms_bp > 0 else None,
+                          "bp_shot_iterations_per_s": iters / (ms_bp * 1e-3) if ms_bp > 0 else None,
                           "p": a.p, "precision": a.precision, "bp_kernel": info["bp_kernel"], "bp_cluster_size": info["bp_cluster_size"],
-                          "osd_variant": info["osd_variant"]}), flush=True)
+                          "osd_variant": info["osd_variant"]}) + "\n").encode())
 if world > 1:
     dist.destroy_process_group()
