@@ -61,6 +61,7 @@ struct bposd_handle {
     } slot[2];
     long long fail_cap = 0; // shots per chunk the failed-shot workspace can hold
     long long workspace_bytes = 2ll << 30;
+    bool workspace_user_set = false;
     long long host_chunk_min = 16384, host_chunk_max = 131072; // shots per chunk of the host-buffer pipeline
     void *d_scratch = nullptr; // global-mode BP scratch
     uint8_t *d_scratch_dec = nullptr;
@@ -414,8 +415,16 @@ static int plan_geometry_t(bposd_handle *h) {
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, osd_kernel<real>, h->osd_threads, osd_smem));
         h->osd_ctas_per_sm = std::max(1, occ2);
     }
-    // failed-shot LLR workspace capacity (shots per chunk)
+    // failed-shot LLR workspace capacity (shots per chunk).  Large codes (config 5: 320 KB of LLRs per shot) get a bigger
+    // workspace unless the caller set one: their OSD launch is latency bound (~0.3 s for up to a cluster-load of failed
+    // shots), so it should see the failed shots of as many decoded shots as memory allows
     const long long per_shot = (long long)n * (long long)rs;
+    if (!h->workspace_user_set && per_shot >= (64 << 10)) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            h->workspace_bytes = std::max<long long>(2ll << 30, std::min<long long>(16ll << 30, (long long)(free_b / 4)));
+        else cudaGetLastError();
+    }
     h->fail_cap = std::max<long long>(1024, h->workspace_bytes / std::max<long long>(per_shot, 1));
     h->geometry_ready = true;
     return BPOSD_OK;
@@ -562,7 +571,7 @@ extern "C" int bposd_set_tuning(bposd_t *h, int32_t kernel_plus1, int32_t thread
     CU_TRY(h, cudaSetDevice(h->device));
     h->force_kernel = kernel_plus1;
     h->force_threads = threads;
-    if (workspace_bytes > 0) h->workspace_bytes = workspace_bytes;
+    if (workspace_bytes > 0) { h->workspace_bytes = workspace_bytes; h->workspace_user_set = true; }
     return plan_geometry(h);
 }
 

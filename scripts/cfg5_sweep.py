@@ -18,7 +18,7 @@ from bp_osd_b200.sharding import shard_range
 ap = argparse.ArgumentParser()
 ap.add_argument("--batches", type=int, nargs="*", default=[1, 8, 64, 512, 4096, 32768, 262144, 1048576])
 ap.add_argument("--p", type=float, default=0.02)
-ap.add_argument("--chunk", type=int, default=16384)
+ap.add_argument("--chunk", type=int, default=49152)
 ap.add_argument("--precision", type=int, default=64)
 ap.add_argument("--cfg", type=int, default=5)
 a = ap.parse_args()
