@@ -522,7 +522,7 @@ __device__ __forceinline__ void fast_check_compute_ps(real (&v)[DC], real (&out)
 #pragma unroll
     for (int k = DC - 1; k >= 0; k--) {
         const real x = ps_clamp(out[k] * t);
-        out[k] = sgn * r_log((1 + x) / (1 - x));
+        out[k] = sgn * r_log(ps_ratio(x));
         t *= th[k];
     }
     if (!REG) {

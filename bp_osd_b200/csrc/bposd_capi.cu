@@ -599,6 +599,30 @@ extern "C" int bposd_int32_peak(bposd_t *h, double *ops_per_s) {
     return BPOSD_OK;
 }
 
+extern "C" int bposd_fp64_peak(bposd_t *h, double *fma_per_s) {
+    if (!h || !fma_per_s) return BPOSD_EINVAL;
+    CU_TRY(h, cudaSetDevice(h->device));
+    double *d_out = nullptr;
+    CU_TRY(h, cudaMalloc((void **)&d_out, 8));
+    const int iters = 1 << 14, grid = h->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CU_TRY(h, cudaEventCreate(&e0));
+    CU_TRY(h, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) { // first repetition warms up
+        CU_TRY(h, cudaEventRecord(e0, nullptr));
+        dfma_peak_kernel<<<grid, threads>>>(d_out, iters);
+        CU_TRY(h, cudaEventRecord(e1, nullptr));
+        CU_TRY(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *fma_per_s = 8.0 * iters * (double)grid * threads / (best * 1e-3);
+    return BPOSD_OK;
+}
+
 extern "C" int bposd_smem_peak(bposd_t *h, double *bytes_per_s) {
     if (!h || !bytes_per_s) return BPOSD_EINVAL;
     CU_TRY(h, cudaSetDevice(h->device));
@@ -623,6 +647,25 @@ extern "C" int bposd_smem_peak(bposd_t *h, double *bytes_per_s) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
     // per trip and thread: four 16-byte loads + four 16-byte stores
     *bytes_per_s = 128.0 * iters * (double)grid * threads / (best * 1e-3);
+    return BPOSD_OK;
+}
+
+// fn: 0 a / b by bpm_div, 1 tanh(a), 2 log(a), 3 (1 + a) / (1 - a) by ps_ratio -- the device side of include/bposd_math.h,
+// evaluated element-wise so that tests can compare it bit for bit with the host side of the same header.
+__global__ void math_probe_kernel(int fn, const double *a, const double *b, double *out, long long count) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const double x = a[i];
+        out[i] = fn == 0 ? bpm_div(x, b[i]) : fn == 1 ? r_tanh(x) : fn == 2 ? r_log(x) : ps_ratio(x);
+    }
+}
+
+extern "C" int bposd_math_probe(bposd_t *h, int32_t fn, const double *a, const double *b, double *out, int64_t count) {
+    if (!h || !a || !out || count < 0 || fn < 0 || fn > 3 || (fn == 0 && !b)) return BPOSD_EINVAL;
+    if (count == 0) return BPOSD_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    math_probe_kernel<<<h->sm_count * 8, 256>>>(fn, a, b, out, (long long)count);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaDeviceSynchronize());
     return BPOSD_OK;
 }
 

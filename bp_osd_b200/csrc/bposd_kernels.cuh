@@ -79,6 +79,13 @@ __device__ __forceinline__ float ms_alpha(float alpha0, int it) {
 __device__ __forceinline__ double ps_clamp(double x) { return x; }
 __device__ __forceinline__ float ps_clamp(float x) { return fminf(fmaxf(x, -0.99999994f), 0.99999994f); }
 // fp64: the portable FMA-free functions the oracle also compiles (include/bposd_math.h) -- same bits on both sides
+// (1 + x) / (1 - x) of the product-sum update (the reference's one division per edge).  fp64: the in-range IEEE sequence
+// of include/bposd_math.h (1 +- x lie in {0} U [2^-53, 2]); a saturated product x = 1 divides by zero: +inf, as on the host.
+__device__ __forceinline__ double ps_ratio(double x) {
+    const double a = 1 + x, b = 1 - x, q = bpm_div(a, b);
+    return b == 0 ? __longlong_as_double(0x7ff0000000000000ll) : q;
+}
+__device__ __forceinline__ float ps_ratio(float x) { return (1 + x) / (1 - x); }
 __device__ __forceinline__ double r_tanh(double x) { return bpm_tanh(x); }
 __device__ __forceinline__ float r_tanh(float x) { return tanhf(x); }
 __device__ __forceinline__ double r_log(double x) { return bpm_log(x); }
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(BpArgs<real> a) {
                         const real sgn = synd_s[i] ? (real)-1 : (real)1;
                         for (int e = end - 1; e >= beg; e--) {
                             real x = ps_clamp(c2b[e] * t);
-                            c2b[e] = sgn * r_log((1 + x) / (1 - x));
+                            c2b[e] = sgn * r_log(ps_ratio(x));
                             t *= b2c[e];
                         }
                     }
@@ -1000,6 +1007,23 @@ __global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t *out, int iters
 #pragma unroll
     for (int j = 0; j < 8; j++) r ^= a[j];
     if (r == 0x12345678u) out[0] = r; // keeps the chains alive
+}
+
+// fp64 calibration for the product-sum roofline: eight independent DFMA chains per thread, 8 * iters fused multiply-adds
+// per thread (product-sum spends its instructions on tanh / log / divisions, i.e. on the fp64 pipe, not on memory).
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters) {
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = 1.0 + 1e-9 * (threadIdx.x + 8 * j + blockIdx.x);
+    const double m = 0.99999999, c = 1e-9 * threadIdx.x;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = __fma_rn(a[j], m, c); // one DFMA each
+    }
+    double r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r += a[j];
+    if (r == 0.123456789) out[0] = r; // keeps the chains alive
 }
 
 // Shared-memory bandwidth calibration for the BP roofline: the message traffic of the in-place BP kernels is 16-byte

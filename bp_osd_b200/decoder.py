@@ -233,6 +233,28 @@ class BpOsdDecoder:
         self._check(_capi.load().bposd_smem_peak(self._h, C.byref(v)))
         return float(v.value)
 
+    def fp64_peak(self) -> float:
+        """Measured fp64 fused-multiply-add rate of the device in DFMA/s (denominator of the product-sum roofline)."""
+        v = C.c_double()
+        self._check(_capi.load().bposd_fp64_peak(self._h, C.byref(v)))
+        return float(v.value)
+
+    def math_probe(self, fn: str, a, b=None):
+        """Test hook: the device side of include/bposd_math.h on CUDA float64 tensors.  fn: "div" (a / b by the in-range
+        division sequence), "tanh", "log", "ratio" ((1 + a) / (1 - a) as the product-sum update forms it)."""
+        import torch
+        code = {"div": 0, "tanh": 1, "log": 2, "ratio": 3}[fn]
+        for t in (a, b):
+            if t is not None and not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64
+                                      and t.is_contiguous() and t.device.index == self.device):
+                raise ValueError("math_probe takes contiguous float64 tensors on the decoder's device")
+        if code == 0 and (b is None or b.numel() != a.numel()):
+            raise ValueError("div needs b with as many elements as a")
+        out = torch.empty_like(a)
+        self._check(_capi.load().bposd_math_probe(self._h, code, a.data_ptr(), b.data_ptr() if b is not None else None,
+                                                  out.data_ptr(), a.numel()))
+        return out
+
     def set_cluster_size(self, cluster_size=0):
         """Thread-block-cluster size of BP kernel 3 (0 = smallest that fits, else 2, 4, 8 or 16)."""
         self._check(_capi.load().bposd_set_cluster_size(self._h, int(cluster_size)))

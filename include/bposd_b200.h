@@ -198,6 +198,13 @@ int bposd_int32_peak(bposd_t *h, double *ops_per_s);
 /* Measured shared-memory bandwidth of the device in bytes/s (conflict-free 16-byte LDS + STS in equal parts, the access
  * mix of the in-place BP kernels): the denominator of the BP roofline. */
 int bposd_smem_peak(bposd_t *h, double *bytes_per_s);
+/* Measured fp64 fused-multiply-add rate of the device in DFMA/s (thread-level operations): the denominator of the
+ * product-sum roofline (that update is bound by the fp64 pipe: tanh, log and three divisions per edge). */
+int bposd_fp64_peak(bposd_t *h, double *fma_per_s);
+/* Test hook: the device side of include/bposd_math.h evaluated element-wise on device arrays of `count` doubles, so that
+ * the tests can compare it bit for bit with the host side (the oracle).  fn: 0 out = a / b (the in-range division
+ * sequence), 1 tanh(a), 2 log(a), 3 (1 + a) / (1 - a) as the product-sum update forms it; b is read for fn = 0 only. */
+int bposd_math_probe(bposd_t *h, int32_t fn, const double *a, const double *b, double *out, int64_t count);
 /* Thread-block-cluster size of BP kernel variant 3 (messages split over the shared memory of 2, 4, 8 or
  * 16 CTAs, reached through distributed shared memory); 0 = smallest size that fits. */
 int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size);

@@ -67,6 +67,11 @@ void oracle_set_math(oracle_t *o, int mode) { o->math_mode = mode; }
 double oracle_math_tanh(double x) { return bpm_tanh(x); }
 double oracle_math_log(double x) { return bpm_log(x); }
 double oracle_math_expm1(double x) { return bpm_expm1(x); }
+/* element-wise forms for the device-vs-host comparison of the shared header (fn: 0 a / b, 1 tanh, 2 log, 3 (1 + a) / (1 - a)) */
+void oracle_math_map(int fn, const double *a, const double *b, double *out, long long count) {
+    for (long long i = 0; i < count; i++)
+        out[i] = fn == 0 ? bpm_div(a[i], b[i]) : fn == 1 ? bpm_tanh(a[i]) : fn == 2 ? bpm_log(a[i]) : (1 + a[i]) / (1 - a[i]);
+}
 
 /* ------------------------------------------------------------------ helpers */
 

@@ -53,12 +53,22 @@ def lib():
         for name in ("tanh", "log", "expm1"):
             f = getattr(L, "oracle_math_" + name)
             f.restype, f.argtypes = C.c_double, [C.c_double]
+        L.oracle_math_map.restype, L.oracle_math_map.argtypes = None, [C.c_int, P, P, P, C.c_longlong]
         L.oracle_philox.argtypes = [P, P, P]
         L.oracle_sample_errors.argtypes = [C.c_uint64, C.c_uint64, C.c_long, C.c_int, P, P, P, P, P]
         L.oracle_syndrome.argtypes = [P, P, C.c_long, P]
         L.oracle_logical_fail.argtypes = [P, P, C.c_int, C.c_int, P, P, C.c_long, P]
         _lib = L
     return _lib
+
+
+def math_map(fn, a, b=None):
+    """Host side of include/bposd_math.h element-wise: fn "div" (a / b), "tanh", "log", "ratio" ((1 + a) / (1 - a))."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+    out = np.empty_like(a)
+    lib().oracle_math_map({"div": 0, "tanh": 1, "log": 2, "ratio": 3}[fn], _ptr(a), _ptr(b), _ptr(out), a.size)
+    return out
 
 
 def _ptr(a):

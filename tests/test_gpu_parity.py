@@ -127,6 +127,47 @@ def test_product_sum_lifted_product(torch_cuda, oracle_mod, cfg_codes):
         assert np.array_equal(out["llr"], ref["llr"], equal_nan=True), "log_prob_ratios not bit-exact"
 
 
+def test_device_math_is_the_host_math(torch_cuda, oracle_mod, cfg_codes):
+    """include/bposd_math.h, device side against host side, element by element and bit for bit: the in-range division
+    sequence the kernels use instead of the compiler's out-of-line fp64 division (against the host's IEEE `/`), tanh, log
+    and the (1 + x) / (1 - x) of the product-sum update, on 2^22 arguments each drawn from the ranges the check update
+    produces plus the special values."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    d = BpOsdDecoder(cfg_codes(1).hz, error_rate=0.05, bp_method="ps", osd_method="osd0")
+    rng = np.random.default_rng(2024)
+    N = 1 << 22
+    sign = lambda k: np.where(rng.random(k) < 0.5, -1.0, 1.0)
+    logu = lambda k, lo, hi: np.exp2(rng.uniform(lo, hi, k)) * sign(k)
+    dev = lambda a: torch.tensor(a, device="cuda", dtype=torch.float64)
+
+    def same(fn, a, b=None):
+        got = d.math_probe(fn, dev(a), None if b is None else dev(b)).cpu().numpy()
+        ref = oracle_mod.math_map(fn, a, b)
+        bad = np.flatnonzero((got.view(np.uint64) != ref.view(np.uint64)) & ~(np.isnan(got) & np.isnan(ref)))
+        assert bad.size == 0, f"{fn}: {bad.size} of {a.size} differ, first a={a[bad[0]]!r} device={got[bad[0]]!r} host={ref[bad[0]]!r}"
+
+    # division: generic operands over the whole range the header allows, then the three shapes that occur
+    same("div", logu(N, -60, 70), logu(N, -60, 70))
+    u = np.expm1(rng.uniform(-2, 44, N))
+    same("div", np.where(u > 1, 2.0, -u), u + 2.0)                      # inside tanh
+    f = rng.uniform(np.sqrt(0.5) - 1, np.sqrt(2) - 1, N)
+    f[:1000] = 0.0
+    same("div", f, 2.0 + f)                                             # inside log
+    x = np.tanh(logu(N, -30, 5))
+    x[:8] = [1.0, -1.0, 0.0, -0.0, np.nan, 1 - 2.0 ** -53, -1 + 2.0 ** -53, 0.5]
+    same("div", 1 + x[8:], 1 - x[8:])
+    same("ratio", x)                                                    # x = 1: division by zero -> +inf
+    # tanh over the message range, tiny and huge arguments, specials
+    t = np.concatenate([rng.uniform(-25, 25, N // 2), logu(N // 2 - 8, -40, 8),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-300, 22.0, 1.7976931348623157e308]])
+    same("tanh", t)
+    # log over the quotient range [2^-54, 2^54], near 1, specials (0 -> -inf, inf, NaN, negative, subnormal)
+    q = np.concatenate([np.abs(logu(N // 2, -54, 54)), 1 + rng.uniform(-0.3, 0.45, N // 2 - 8),
+                        [0.0, np.inf, np.nan, -1.0, 5e-324, 1.0, 2.0 ** -54, 2.0 ** 54]])
+    same("log", q)
+
+
 @pytest.mark.parametrize("cfg,p,B", [(1, 0.08, 800), (2, 0.06, 500)])
 def test_product_sum_in_place_kernel_other_degree_classes(torch_cuda, oracle_mod, cfg_codes, cfg, p, B):
     """Product-sum on the in-place kernel for the (4, 2) class and for an IRREGULAR code of the (8, 4) class (rows of 7 in
