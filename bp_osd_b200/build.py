@@ -43,6 +43,8 @@ def units(only_class=None):
             d = [f"-DBPOSD_INST_REAL={real}", f"-DBPOSD_INST_DC={dc}", f"-DBPOSD_INST_DV={dv}"]
             out.append((f"fast_{tag}_{dc}", "bp_fast_inst.cu", d))
             out.append((f"cluster_{tag}_{dc}", "bp_cluster_inst.cu", d))
+        if not only_class or only_class == (7, 4):  # rows of 7 slots: a class of the cluster kernel alone
+            out.append((f"cluster_{tag}_7", "bp_cluster_inst.cu", [f"-DBPOSD_INST_REAL={real}", "-DBPOSD_INST_DC=7", "-DBPOSD_INST_DV=4"]))
     return out
 
 

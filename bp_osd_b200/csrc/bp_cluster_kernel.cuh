@@ -66,25 +66,37 @@ static inline void cluster_free(ClusterTables &t) {
 
 // Shared-memory layout of one CTA, the same arithmetic on host and device.
 struct ClusterLayout { size_t o_meta, o_prior, o_xl, o_flip, total; };
-__host__ __device__ inline ClusterLayout cluster_layout(int RS, int elem, int rpc, int bpc, int nbox_max, int nout_max, int DV, int flip_table) {
+__host__ __device__ inline ClusterLayout cluster_layout(int RS, int elem, int rpc, int bpc, int nbox_max, int nout_max, int DV, int flip_table,
+                                                        int prior_table = 1) {
     ClusterLayout L;
     auto al = [](size_t x) { return (x + 15) / 16 * 16; };
     size_t o = al(((size_t)rpc * RS + nbox_max + kFastDummySlots) * elem); // row slots | mailbox | dummy / zero slots
     L.o_meta = o; o = al(o + (size_t)rpc);                                 // one byte per check
-    L.o_prior = o; o = al(o + (size_t)bpc * elem);                         // priors by position (non-uniform channels)
+    L.o_prior = o; o = al(o + (prior_table ? (size_t)bpc * elem : 0));     // priors by position (non-uniform channels only)
     L.o_xl = o; o = al(o + (size_t)(nout_max > 0 ? nout_max : 1) * 8);     // exchange list (byte offset, cluster address)
     L.o_flip = o; o = al(o + (flip_table ? (size_t)bpc * DV * 4 : 0));     // parity-flip descriptors
     L.total = o + 16;
     return L;
 }
 template <typename real>
-static inline size_t cluster_smem_need(const ClusterTables &t, int flip_table) {
-    return cluster_layout(fast_row_stride(t.DC, (int)sizeof(real)), (int)sizeof(real), t.rows_per_cta, t.bits_per_cta, t.nbox_max, t.nout_max, t.DV, flip_table).total;
+static inline size_t cluster_smem_need(const ClusterTables &t, int flip_table, int prior_table = 1) {
+    return cluster_layout(fast_row_stride(t.DC, (int)sizeof(real)), (int)sizeof(real), t.rows_per_cta, t.bits_per_cta, t.nbox_max, t.nout_max, t.DV, flip_table,
+                          prior_table).total;
 }
 // lower bound before the partition is known (no mailbox, no exchange list): filters cluster sizes that cannot fit
 template <typename real>
-static inline size_t cluster_smem_min(int DC, int rows_per_cta, int bits_per_cta) {
-    return cluster_layout(fast_row_stride(DC, (int)sizeof(real)), (int)sizeof(real), rows_per_cta, bits_per_cta, 0, 0, 0, 0).total;
+static inline size_t cluster_smem_min(int DC, int rows_per_cta, int bits_per_cta, int prior_table = 1) {
+    return cluster_layout(fast_row_stride(DC, (int)sizeof(real)), (int)sizeof(real), rows_per_cta, bits_per_cta, 0, 0, 0, 0, prior_table).total;
+}
+
+// Degree class of the cluster kernel: the single-CTA classes, plus rows of exactly 7 slots when no check has more than 7
+// edges (hypergraph products of (3,4)-regular codes, BASELINE config 5): 56-byte rows moved element by element instead
+// of 80-byte padded rows moved in 16-byte pieces -- 30 % less shared memory per shot (a cluster of 8 CTAs holds config 5
+// where the padded rows need 16: 18 shots in flight on 144 SMs instead of 7 on 112) and 14 instead of 20 wavefronts per
+// warp and row access.
+static inline void cluster_class(int max_col_deg, int max_row_deg, int *DC, int *DV) {
+    fast_class(max_col_deg, max_row_deg, DC, DV);
+    if (*DC == 8 && max_row_deg == 7) *DC = 7;
 }
 
 // Host partition pass: alternate "every bit goes to the CTA that holds most of its checks" and "every check
@@ -98,7 +110,7 @@ static inline cudaError_t cluster_build(ClusterTables &t, int CL, int m, int n, 
     for (int i = 0; i < m; i++) { int d = row_ptr[i + 1] - row_ptr[i]; mr = std::max(mr, d); minr = std::min(minr, d); }
     for (int j = 0; j < n; j++) { int d = col_ptr[j + 1] - col_ptr[j]; mc = std::max(mc, d); minc = std::min(minc, d); }
     cluster_free(t);
-    fast_class(mc, mr, &t.DC, &t.DV);
+    cluster_class(mc, mr, &t.DC, &t.DV);
     const int rpc = (m + CL - 1) / CL, bpc = (n + CL - 1) / CL;
     t.CL = CL; t.rows_per_cta = rpc; t.bits_per_cta = bpc;
     t.regular = (m > 0 && minr == t.DC && mr == t.DC && minc == t.DV && mc == t.DV && m % CL == 0) ? 1 : 0;
@@ -225,7 +237,7 @@ __device__ __forceinline__ void xor_dsmem_u32(uint32_t a, uint32_t v) { asm vola
 // fast_check_row (min is exact; on a tie both forms give the tied value).  "<= 0" counts zero as negative.
 template <typename real, int DC, bool REG>
 __device__ __forceinline__ void cluster_check_row(real *row, unsigned mt, real alpha) {
-    constexpr int CH = (sizeof(real) == 8) ? 2 : ((DC % 4 == 0) ? 4 : 2); // elements per vector access
+    constexpr int CH = (DC % 2) ? 1 : (sizeof(real) == 8) ? 2 : ((DC % 4 == 0) ? 4 : 2); // elements per vector access
     real min1 = real_max<real>(), min2 = real_max<real>();
     int arg = -1;
     unsigned par = mt >> 7;
@@ -273,7 +285,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
     const int rpc = t.rows_per_cta, bpc = t.bits_per_cta, CL = t.CL;
     const uint32_t rank = cluster_ctarank();
     constexpr int RS = fast_row_stride(DC, (int)sizeof(real)); // row stride in elements
-    const ClusterLayout L = cluster_layout(RS, (int)sizeof(real), rpc, bpc, t.nbox_max, t.nout_max, DV, t.flip_table);
+    const ClusterLayout L = cluster_layout(RS, (int)sizeof(real), rpc, bpc, t.nbox_max, t.nout_max, DV, t.flip_table, a.uniform_prior ? 0 : 1);
     const unsigned nslot = (unsigned)rpc * RS + (unsigned)t.nbox_max;      // row slots, then the mailbox; dummy / zero slots follow
     real *msg = reinterpret_cast<real *>(smem_raw);
     uint8_t *meta = smem_raw + L.o_meta;                                   // bit0 mismatch, bits1-5 degree, bit7 syndrome
@@ -530,7 +542,10 @@ cudaError_t ClusterInst<real, DC, DV>::prepare(const ClusterTables &t, int threa
     cudaError_t e = cudaSuccess;
     BPOSD_CL_GEOM(t, {
         auto kern = (bp_cluster_kernel<real, DC, DV, VPT, MAXT, REG>);
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, kern);
+        // only ever raised: two plans (with / without a prior array) may share an instantiation
+        if (e == cudaSuccess && (int)smem > fa.maxDynamicSharedSizeBytes) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess && t.CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e == cudaSuccess) {
             cudaLaunchConfig_t cfg = {};
@@ -562,10 +577,20 @@ cudaError_t ClusterInst<real, DC, DV>::launch(const ClusterTables &t, const BpAr
 }
 #endif // BPOSD_CLUSTER_INSTANTIATE
 
+#ifdef BPOSD_DEV_CLASS_ONLY
+#define BPOSD_CLUSTER_CLASS(t, EXPR) do { constexpr int DC = BPOSD_DEV_DC, DV = (BPOSD_DEV_DC + 1) / 2; EXPR; } while (0)
+#else
+#define BPOSD_CLUSTER_CLASS(t, EXPR)                                                             \
+    do {                                                                                         \
+        if (t.DC == 7) { constexpr int DC = 7, DV = 4; EXPR; }                                   \
+        else BPOSD_FAST_CLASS(t, EXPR);                                                          \
+    } while (0)
+#endif
+
 template <typename real>
 static inline cudaError_t cluster_prepare(const ClusterTables &t, int threads, size_t smem, int *max_clusters) {
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_CLASS(t, (e = ClusterInst<real, DC, DV>::prepare(t, threads, smem, max_clusters)));
+    BPOSD_CLUSTER_CLASS(t, (e = ClusterInst<real, DC, DV>::prepare(t, threads, smem, max_clusters)));
     return e;
 }
 
@@ -579,7 +604,7 @@ static inline cudaError_t cluster_launch(const ClusterTables &t, const BpArgs<re
     d.nbox_max = t.nbox_max; d.nout_max = t.nout_max;
     d.flip_table = flip_table;
     cudaError_t e = cudaSuccess;
-    BPOSD_FAST_CLASS(t, (e = ClusterInst<real, DC, DV>::launch(t, a, d, nclusters, threads, smem, st)));
+    BPOSD_CLUSTER_CLASS(t, (e = ClusterInst<real, DC, DV>::launch(t, a, d, nclusters, threads, smem, st)));
     return e;
 }
 

@@ -366,35 +366,52 @@ static inline size_t fast_smem_bytes(const FastTables &t, int n, int m, bool wit
 
 // ---- vector row load/store helpers -----------------------------------------------------------
 template <typename real, int DC> struct RowIO;
+// Even DC: 16-byte accesses (rows are 16-byte aligned, see fast_row_stride).  Odd DC (the cluster kernel's rows of 7): one
+// element per access -- an odd stride in elements is conflict free as it is, and a row of 7 doubles moves 14 wavefronts
+// per warp where the padded row of 8 + 2 moves 20.
 template <int DC> struct RowIO<double, DC> {
-    static_assert(DC % 2 == 0, "row stride must keep 16-byte alignment");
     __device__ static __forceinline__ void load(const double *p, double (&v)[DC]) {
+        if constexpr (DC % 2 == 0) {
 #pragma unroll
-        for (int k = 0; k < DC; k += 2) { double2 t = *reinterpret_cast<const double2 *>(p + k); v[k] = t.x; v[k + 1] = t.y; }
+            for (int k = 0; k < DC; k += 2) { double2 t = *reinterpret_cast<const double2 *>(p + k); v[k] = t.x; v[k + 1] = t.y; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < DC; k++) v[k] = p[k];
+        }
     }
     __device__ static __forceinline__ void store(double *p, const double (&v)[DC]) {
+        if constexpr (DC % 2 == 0) {
 #pragma unroll
-        for (int k = 0; k < DC; k += 2) *reinterpret_cast<double2 *>(p + k) = make_double2(v[k], v[k + 1]);
+            for (int k = 0; k < DC; k += 2) *reinterpret_cast<double2 *>(p + k) = make_double2(v[k], v[k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < DC; k++) p[k] = v[k];
+        }
     }
 };
 template <int DC> struct RowIO<float, DC> {
-    static_assert(DC % 2 == 0, "row stride must keep 8-byte alignment");
     __device__ static __forceinline__ void load(const float *p, float (&v)[DC]) {
-        if (DC % 4 == 0) {
+        if constexpr (DC % 4 == 0) {
 #pragma unroll
             for (int k = 0; k < DC; k += 4) { float4 t = *reinterpret_cast<const float4 *>(p + k); v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w; }
-        } else {
+        } else if constexpr (DC % 2 == 0) {
 #pragma unroll
             for (int k = 0; k < DC; k += 2) { float2 t = *reinterpret_cast<const float2 *>(p + k); v[k] = t.x; v[k + 1] = t.y; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < DC; k++) v[k] = p[k];
         }
     }
     __device__ static __forceinline__ void store(float *p, const float (&v)[DC]) {
-        if (DC % 4 == 0) {
+        if constexpr (DC % 4 == 0) {
 #pragma unroll
             for (int k = 0; k < DC; k += 4) *reinterpret_cast<float4 *>(p + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-        } else {
+        } else if constexpr (DC % 2 == 0) {
 #pragma unroll
             for (int k = 0; k < DC; k += 2) *reinterpret_cast<float2 *>(p + k) = make_float2(v[k], v[k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < DC; k++) p[k] = v[k];
         }
     }
 };

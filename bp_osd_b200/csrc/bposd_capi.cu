@@ -39,6 +39,10 @@ struct bposd_handle {
     // cluster-kernel tables (built on demand, when the messages exceed one SM's shared memory)
     ClusterTables clus;
     int clus_nclusters = 0, clus_flip_table = 0;
+    // the same for launches whose bits all share one prior: no prior array in shared memory, so a smaller cluster may hold
+    // the code (more shots in flight, fewer remote edges); CL == 0: no separate plan, such launches use `clus`
+    ClusterTables clus_u;
+    int clus_u_nclusters = 0, clus_u_flip_table = 0, clus_u_threads = 0, clus_u_smem = 0;
     // Two decode slots: each owns its control words, failed-shot workspace, staging buffers, events and
     // (for the host-buffer pipeline) a stream, so chunk i+1 can be copied in while chunk i decodes.
     struct Slot {
@@ -213,42 +217,56 @@ static int plan_geometry_t(bposd_handle *h) {
     // cluster kernel: min-sum, supported degrees, and either forced or nothing smem-resident fits
     if ((want == 3 || (want < 0 && kernel == 0)) && h->bp_method == 1 && fast_supported(h->max_col_deg, h->max_row_deg, h->bp_method) && m > 0) {
         int DCc = 0, DVc = 0;
-        fast_class(h->max_col_deg, h->max_row_deg, &DCc, &DVc);
+        cluster_class(h->max_col_deg, h->max_row_deg, &DCc, &DVc);
         // candidate cluster sizes: the smallest cluster whose per-CTA slice fits in shared memory first (fewer remote
         // edges, more shots in flight), larger ones as fall-backs if the device cannot schedule it
-        std::vector<int> cand;
-        for (int c : {2, 4, 8, 16}) {
-            if (h->force_cluster > 0 && c != h->force_cluster) continue;
-            const int rpc = (m + c - 1) / c, bpc = (n + c - 1) / c;
-            if (cluster_smem_min<real>(DCc, rpc, bpc) > (size_t)h->smem_optin || cluster_vpt(bpc) == 0) continue;
-            cand.push_back(c);
-        }
+        struct Plan { int CL = 0, threads = 0, smem = 0, ncl = 0, flip = 0; };
+        auto plan_cluster = [&](ClusterTables &tab, int prior_table, Plan &out) -> int {
+            out = Plan();
+            for (int CL : {2, 4, 8, 16}) {
+                if (h->force_cluster > 0 && CL != h->force_cluster) continue;
+                const int rpc = (m + CL - 1) / CL, bpc = (n + CL - 1) / CL;
+                if (cluster_smem_min<real>(DCc, rpc, bpc, prior_table) > (size_t)h->smem_optin || cluster_vpt(bpc) == 0) continue;
+                if (tab.CL != CL || tab.elem_bytes != (int)rs) {
+                    cudaError_t e = cluster_build(tab, CL, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot, (int)rs);
+                    if (e != cudaSuccess) return fail(h, BPOSD_ECUDA, std::string("cluster_build: ") + cudaGetErrorString(e));
+                }
+                const int ct = cluster_threads(tab.bits_per_cta);
+                size_t csmem = cluster_smem_need<real>(tab, 1, prior_table);
+                int flip = 1; // parity-flip descriptors in shared memory when they fit
+                if (csmem > (size_t)h->smem_optin) { csmem = cluster_smem_need<real>(tab, 0, prior_table); flip = 0; }
+                if (csmem > (size_t)h->smem_optin) continue; // rows + mailbox + exchange list of the fullest CTA do not fit: next size
+                int ncl = 0;
+                cudaError_t e = (ct > 0 && ct <= 1024) ? cluster_prepare<real>(tab, ct, csmem, &ncl) : cudaErrorInvalidConfiguration;
+                if (e == cudaSuccess && ncl >= 1) {
+                    out.CL = CL; out.threads = ct; out.smem = (int)csmem; out.ncl = ncl; out.flip = flip;
+                    return BPOSD_OK;
+                }
+                cudaGetLastError();
+            }
+            return BPOSD_OK;
+        };
+        Plan pg, pu;
+        int prc = plan_cluster(h->clus, 1, pg);
+        if (prc != BPOSD_OK) return prc;
         bool done = false;
-        for (int CL : cand) {
-            if (h->clus.CL != CL || h->clus.elem_bytes != (int)rs) {
-                cudaError_t e = cluster_build(h->clus, CL, m, n, h->row_ptr, h->col_idx, h->col_ptr, h->row_idx, h->csc_slot, (int)rs);
-                if (e != cudaSuccess) return fail(h, BPOSD_ECUDA, std::string("cluster_build: ") + cudaGetErrorString(e));
+        if (pg.CL) {
+            h->bp_kernel = 3; h->bp_threads = pg.threads; h->bp_smem = pg.smem; h->bp_ctas_per_sm = 1;
+            h->clus_nclusters = pg.ncl; h->bp_grid = pg.ncl * pg.CL; h->clus_flip_table = pg.flip;
+            kernel = 3;
+            done = true;
+            // uniform-prior launches: kept only if a smaller cluster does (the tables of a plan are a few MB of HBM)
+            prc = plan_cluster(h->clus_u, 0, pu);
+            if (prc != BPOSD_OK) return prc;
+            if (pu.CL && pu.CL < pg.CL) {
+                h->clus_u_threads = pu.threads; h->clus_u_smem = pu.smem; h->clus_u_nclusters = pu.ncl; h->clus_u_flip_table = pu.flip;
+            } else {
+                cluster_free(h->clus_u);
+                h->clus_u_nclusters = 0;
             }
-            const int ct = cluster_threads(h->clus.bits_per_cta);
-            size_t csmem = cluster_smem_need<real>(h->clus, 1);
-            h->clus_flip_table = 1; // parity-flip descriptors in shared memory when they fit
-            if (csmem > (size_t)h->smem_optin) {
-                csmem = cluster_smem_need<real>(h->clus, 0);
-                h->clus_flip_table = 0;
-            }
-            if (csmem > (size_t)h->smem_optin) continue; // rows + mailbox + exchange list of the fullest CTA do not fit: next size
-            int ncl = 0;
-            cudaError_t e = (ct > 0 && ct <= 1024) ? cluster_prepare<real>(h->clus, ct, csmem, &ncl) : cudaErrorInvalidConfiguration;
-            if (e == cudaSuccess && ncl >= 1) {
-                h->bp_kernel = 3; h->bp_threads = ct; h->bp_smem = (int)csmem; h->bp_ctas_per_sm = 1;
-                h->clus_nclusters = ncl; h->bp_grid = ncl * CL;
-                kernel = 3;
-                done = true;
-                break;
-            }
-            cudaGetLastError();
         }
-        if (!done && want == 3) return fail(h, BPOSD_EUNSUP, "the cluster BP kernel cannot be launched for this matrix / cluster size");
+        if (!done && (want == 3 || h->force_cluster > 0))
+            return fail(h, BPOSD_EUNSUP, "the cluster BP kernel cannot be launched for this matrix / cluster size");
     } else if (want == 3) return fail(h, BPOSD_EUNSUP, "the cluster BP kernel needs min-sum and row/column degrees up to 16/8");
     int occ = 0;
     h->lat_geom = -1; h->lat_max_shots = 0;
@@ -445,6 +463,7 @@ extern "C" void bposd_destroy(bposd_t *h) {
     cudaFree(h->d_prior64); cudaFree(h->d_prior32); cudaFree(h->d_weight);
     fast_free(h->fast);
     cluster_free(h->clus);
+    cluster_free(h->clus_u);
     for (auto &sl : h->slot) {
         cudaFree(sl.d_ctrl); cudaFree(sl.d_fail_list); cudaFree(sl.d_fail_llr);
         if (sl.h_ctrl) cudaFreeHost(sl.h_ctrl);
@@ -702,9 +721,12 @@ extern "C" int bposd_get_info(const bposd_t *h, bposd_info_t *info) {
     info->osd_variant = !h->osd_supported ? 0 : (h->osd_clus ? 4 : (h->osd_large ? 2 : (h->osd_reg ? 3 : 1)));
     if (h->osd_clus) { info->osd_threads = kOsdcThreads; info->osd_smem_bytes = h->osdc[0].smem; }
     if (h->osd_reg) { info->osd_threads = h->osdr_threads; info->osd_smem_bytes = h->osdr_smem; }
-    info->bp_layout_excess = h->bp_kernel == 3 ? (int32_t)(1000 * h->clus.remote_edges / std::max<long long>(h->clus.total_edges, 1))
+    const bool plan_u = h->bp_kernel == 3 && h->uniform_prior && h->clus_u.CL > 0; // what a launch with the static channel uses
+    const ClusterTables &ct = plan_u ? h->clus_u : h->clus;
+    if (plan_u) { info->bp_threads = h->clus_u_threads; info->bp_smem_bytes = h->clus_u_smem; }
+    info->bp_layout_excess = h->bp_kernel == 3 ? (int32_t)(1000 * ct.remote_edges / std::max<long long>(ct.total_edges, 1))
                                                : (int32_t)h->fast.conflicts_after;
-    info->bp_cluster_size = h->bp_kernel == 3 ? h->clus.CL : 1;
+    info->bp_cluster_size = h->bp_kernel == 3 ? ct.CL : 1;
     return BPOSD_OK;
 }
 
@@ -887,8 +909,13 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     const int grid = (int)std::min<long long>(Bc, h->bp_grid);
     CU_TRY(h, cudaEventRecord(sl.ev[0], st));
     if (h->bp_kernel == 3) {
-        const int ncl = (int)std::min<long long>(Bc, h->clus_nclusters);
-        CU_TRY(h, cluster_launch<real>(h->clus, a, ncl, h->bp_threads, (size_t)h->bp_smem, h->clus_flip_table, st));
+        if (a.uniform_prior && h->clus_u.CL > 0) {
+            const int ncl = (int)std::min<long long>(Bc, h->clus_u_nclusters);
+            CU_TRY(h, cluster_launch<real>(h->clus_u, a, ncl, h->clus_u_threads, (size_t)h->clus_u_smem, h->clus_u_flip_table, st));
+        } else {
+            const int ncl = (int)std::min<long long>(Bc, h->clus_nclusters);
+            CU_TRY(h, cluster_launch<real>(h->clus, a, ncl, h->bp_threads, (size_t)h->bp_smem, h->clus_flip_table, st));
+        }
     } else if (h->bp_kernel == 2) {
         if (a.uniform_prior) // no prior array in shared memory: smaller footprint, possibly one more CTA per SM
             fast_launch<real>(h->fast, h->bp_geom, a, (int)std::min<long long>(Bc, h->bp_grid_uni), h->bp_threads, h->bp_smem_uni, st);

@@ -156,8 +156,9 @@ def test_device_math_is_the_host_math(torch_cuda, oracle_mod, cfg_codes):
     same("div", f, 2.0 + f)                                             # inside log
     x = np.tanh(logu(N, -30, 5))
     x[:8] = [1.0, -1.0, 0.0, -0.0, np.nan, 1 - 2.0 ** -53, -1 + 2.0 ** -53, 0.5]
-    same("div", 1 + x[8:], 1 - x[8:])
-    same("ratio", x)                                                    # x = 1: division by zero -> +inf
+    inside = x[8:][np.abs(x[8:]) < 1]                                   # bpm_div's contract excludes b = 0 ...
+    same("div", 1 + inside, 1 - inside)
+    same("ratio", x)                                                    # ... which ps_ratio selects around: x = 1 -> +inf
     # tanh over the message range, tiny and huge arguments, specials
     t = np.concatenate([rng.uniform(-25, 25, N // 2), logu(N // 2 - 8, -40, 8),
                         [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-300, 22.0, 1.7976931348623157e308]])
@@ -635,6 +636,30 @@ def test_cluster_kernel_irregular_and_per_shot_priors(torch_cuda, oracle_mod):
         out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
                    llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
         assert_exact(out, ref)
+
+
+def test_cluster_kernel_rows_of_seven_nonuniform(torch_cuda, oracle_mod, cfg_codes):
+    """The cluster kernel's own degree class (rows of exactly 7 slots moved element by element, no padding: what lets a
+    cluster of 8 hold config 5) with non-uniform priors -- the prior array in shared memory -- and with a uniform channel
+    (no prior array), against the oracle."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(2).hz
+    n = H.shape[1]
+    assert int(np.diff(H.tocsr().indptr).max()) == 7
+    kw = dict(max_iter=30, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=7)
+    rng = np.random.default_rng(5)
+    _, syn = random_syndromes(H, 0.06, 600, seed=8)
+    for probs in (rng.uniform(0.03, 0.09, size=n), np.full(n, 0.06)):
+        ref = oracle_mod.OracleDecoder(H, channel_probs=probs, **kw).decode_batch(syn)
+        for cl in (4, 16):
+            d = BpOsdDecoder(H, channel_probs=probs, **kw)
+            d.set_tuning(bp_kernel=3)
+            d.set_cluster_size(cl)
+            r = d.decode_batch(torch.tensor(syn, device="cuda"))
+            out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
+                       llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
+            assert_exact(out, ref)
 
 
 @pytest.mark.parametrize("variant", [1, 3])
