@@ -385,6 +385,26 @@ def run_gpu(args, cfg, c):
         "mean_iterations": iters / (S * args.steps), "bp_shot_iterations_per_s": iters / (ms_bp * 1e-3) if ms_bp else None,
     }
 
+    if c["bp_method"] == "ps" and prec == 64:
+        # Product-sum is not memory bound: tanh, log and three divisions per edge make it an fp64-pipe kernel.  Algorithmic
+        # fp64 operations per edge, counted from include/bposd_math.h and the update's own arithmetic: b2c / 2 (1),
+        # tanh (37: expm1 25, u + 2, eight for the division sequence, 1 - q, NaN select), forward / reverse products (3),
+        # (1 + x) / (1 - x) (11), log (32), sign (1) on the check side; two additions per edge on the bit side = 87.
+        # The peak is the DFMA issue rate measured in this run.
+        PS_FP64_OPS_PER_EDGE = 87
+        fp64_peak = dec.fp64_peak() / 1e12
+        ops = iters * E * PS_FP64_OPS_PER_EDGE
+        ach = ops / (ms_bp * 1e-3) / 1e12 if ms_bp > 0 else None
+        roofline = {"bound": "fp64", "kernel": roofline["kernel"], "achieved": ach, "peak": fp64_peak, "unit": "T fp64 op/s",
+                    "frac": (ach / fp64_peak) if ach else None, "traffic": traffic,
+                    "peak_source": "measured in this run: bposd_fp64_peak (independent DFMA chains, all SMs)",
+                    "algorithmic_ops_per_launch": ops / max(args.steps, 1),
+                    "note": f"achieved = {PS_FP64_OPS_PER_EDGE} fp64 operations per edge and iteration (see bench.py) x E x shot-iterations / "
+                            "CUDA-event time of the BP launches",
+                    "smem": {k: roofline[k] for k in ("bound", "achieved", "peak", "unit", "frac", "peak_source")},
+                    "hbm": roofline["hbm"], "bp_ms_per_step": roofline["bp_ms_per_step"], "osd_ms_per_step": roofline["osd_ms_per_step"],
+                    "mean_iterations": roofline["mean_iterations"], "bp_shot_iterations_per_s": roofline["bp_shot_iterations_per_s"]}
+
     # ---- end to end through the public API: pre-staged pinned host batches, bit-packed both ways ----
     Se = min(S, args.e2e_shots_per_gpu or S)
     mb, nb = (m + 7) // 8, (n + 7) // 8
