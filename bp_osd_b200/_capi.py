@@ -63,6 +63,7 @@ SIGNATURES = {
     "bposd_smem_peak": (C.c_int, [P, C.POINTER(C.c_double)]),
     "bposd_fp64_peak": (C.c_int, [P, C.POINTER(C.c_double)]),
     "bposd_math_probe": (C.c_int, [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "bposd_set_schedule": (C.c_int, [P, C.c_int32, C.c_void_p]),
     "bposd_set_cluster_size": (C.c_int, [P, C.c_int32]),
     "bposd_set_osd_variant": (C.c_int, [P, C.c_int32, C.c_int64]),
     "bposd_last_error": (C.c_char_p, [P]),

@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
     __shared__ long long sh_shot;
     __shared__ int sh_slot;
     __shared__ unsigned sh_vote[2][16];
+    __shared__ unsigned sh_big[2][16];
     const uint32_t msg_s = smem_u32(msg), meta_s = smem_u32(meta);
     const int nout = t.nout[rank];
     for (int x = tid; x < nout; x += T) {
@@ -404,6 +405,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
 
         bool conv = false;
         int iters = 0;
+        int danger = 0; // overflow guard (llr_near_overflow): some LLR of the cluster came near overflow in the last bit sweep
         real pow2 = 1;
         for (int it = 1;; it++) {
             const bool last = it > a.max_iter;
@@ -411,6 +413,10 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
             const real alpha = (a.alpha0 == (real)0) ? (real)1 - pow2 : a.alpha0;
             const uint32_t alpha_w = sign_word(alpha);
             bool ok = true;
+            if (danger && !last) { // rare: +-inf in the rows (local and pulled values alike) become +-max
+                for (int p = tid; p < rpc; p += T)
+                    for (int k = 0; k < DC; k++) msg[(size_t)p * RS + k] = clamp_inf<real>(msg[(size_t)p * RS + k]);
+            }
             // ---- check sweep over this CTA's rows (a4) + local convergence vote for the previous pass (a7)
             for (int p = tid; p < rpc; p += T) {
                 const unsigned mt = meta[p];
@@ -444,7 +450,18 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                         }
                     }
             }
+            const bool guard = it >= a.safe_it; // the same in every CTA of the cluster
+            if (guard) {
+                bool big = false;
+#pragma unroll
+                for (int r = 0; r < VPT; r++) big |= llr_near_overflow<real>(llr[r]) && ((valid >> r) & 1u);
+                const int cta_big = __syncthreads_or(big ? 1 : 0);
+                if (tid < CL) st_dsmem_u32(mapa_u32(smem_u32(&sh_big[it & 1][rank]), tid), (uint32_t)cta_big);
+            }
             cluster_sync_all();
+            danger = 0;
+            if (guard)
+                for (int c = 0; c < CL; c++) danger |= (int)sh_big[it & 1][c];
             pull_rows(); // new bit-to-check values of the remote edges back into the rows
             __syncthreads();
         }

@@ -551,11 +551,24 @@ __device__ __forceinline__ void fast_check_compute_ps(real (&v)[DC], real (&out)
 
 template <typename real, int DC, bool REG, bool PS = false>
 __device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alpha, uint32_t alpha_w) {
-    real v[DC], out[DC];
-    RowIO<real, DC>::load(row, v);
-    if constexpr (PS) fast_check_compute_ps<real, DC, REG>(v, out, mt);
-    else fast_check_compute<real, DC, REG>(v, out, mt, alpha, alpha_w);
-    RowIO<real, DC>::store(row, out);
+    if constexpr (DC % 2 == 1 && !PS) {
+        // rows of an odd number of slots (the cluster kernel's rows of 7): computed as the next even class with a constant
+        // +max in the last position -- the pad slot the padded layout keeps in memory -- so that both layouts give the same
+        // bits in every case, overflowed fp32 shots included (the pad caps a check message at the largest finite value,
+        // like the reference's running minimum, which starts from it)
+        real v[DC + 1], out[DC + 1];
+        real (&vr)[DC] = reinterpret_cast<real (&)[DC]>(v);
+        RowIO<real, DC>::load(row, vr);
+        v[DC] = real_max<real>();
+        fast_check_compute<real, DC + 1, REG>(v, out, mt, alpha, alpha_w);
+        RowIO<real, DC>::store(row, reinterpret_cast<real (&)[DC]>(out));
+    } else {
+        real v[DC], out[DC];
+        RowIO<real, DC>::load(row, v);
+        if constexpr (PS) fast_check_compute_ps<real, DC, REG>(v, out, mt);
+        else fast_check_compute<real, DC, REG>(v, out, mt, alpha, alpha_w);
+        RowIO<real, DC>::store(row, out);
+    }
 }
 
 // Bit sweep (rows a6 + a8) of one thread: VPT positions, each a bit with <= DV edges.  Sums run in the reference's
@@ -755,6 +768,7 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG,
 
         bool conv = false;
         int iters = 0;
+        int danger = 0; // some LLR came near overflow in the previous pass: rows may hold +-inf (see llr_near_overflow)
         real pow2 = 1; // 2^-it, exact
         for (int it = 1;; it++) {
             const bool last = it > a.max_iter;
@@ -762,6 +776,10 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG,
             const real alpha = (a.alpha0 == (real)0) ? (real)1 - pow2 : a.alpha0;
             const uint32_t alpha_w = sign_word(alpha);
             bool ok = true;
+            if (!PS && danger && !last) { // rare: rewrite +-inf as +-max in this thread's rows (the reference's check update cannot tell them apart)
+                for (int p = tid; p < m; p += T)
+                    for (int k = 0; k < DC; k++) msg[(size_t)p * RS + k] = clamp_inf<real>(msg[(size_t)p * RS + k]);
+            }
             // ---- check sweep (a4) + convergence vote for the previous pass (a7) ----
             // (prefetching the thread's next row into a second register set before updating the current one was measured:
             // 111 vs 128 M shot-iterations/s -- the second set spills at the 128-register cap; profiles/r03i_ab_probe.log)
@@ -797,7 +815,12 @@ __global__ void __launch_bounds__(MAXT, (fast_minb<real, MAXT, DC, DV, VPT, REG,
                             }
                     }
             }
-            __syncthreads();
+            if (!PS && it >= a.safe_it) {
+                bool big = false;
+#pragma unroll
+                for (int r = 0; r < VPT; r++) big |= llr_near_overflow<real>(llr[r]) && ((valid >> r) & 1u);
+                danger = __syncthreads_or(big ? 1 : 0);
+            } else __syncthreads();
         }
 
         // ---- results ----

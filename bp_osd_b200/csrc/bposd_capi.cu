@@ -10,6 +10,7 @@
 #include "bp_cluster_kernel.cuh"
 #include "osd_reg_kernel.cuh"
 #include "osd_cluster_kernel.cuh"
+#include "bp_serial_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -48,6 +49,8 @@ struct bposd_handle {
     struct Slot {
         // control words: [0] queue, [1] converged, [2] iterations, [3] osd invocations, [4] (int) fail_count
         unsigned long long *d_ctrl = nullptr;
+        unsigned char *d_serial_ws = nullptr; // serial-schedule BP: per-warp message workspace (bp_serial_kernel.cuh)
+        size_t serial_ws_bytes = 0;
         unsigned long long *h_ctrl = nullptr; // pinned copy of words 0..3
         int *d_fail_list = nullptr;
         void *d_fail_llr = nullptr;
@@ -98,6 +101,8 @@ struct bposd_handle {
     unsigned *d_osdc_idx = nullptr;
     OsdcPivot *d_osdc_piv = nullptr;
     int force_kernel = 0, force_threads = 0, force_cluster = 0;
+    int schedule = 0;       // 0 parallel (flooding), 1 serial (bit after bit)
+    int *d_order = nullptr; // serial schedule: bit order (nullptr: 0 .. n-1)
     bool geometry_ready = false;
     // harness
     uint32_t *d_t1 = nullptr, *d_t2 = nullptr, *d_t3 = nullptr;
@@ -161,6 +166,30 @@ static int host_rank(const bposd_handle *h) {
         r++;
     }
     return r;
+}
+
+// First pass at which a message could have overflowed (overflow guard of the prefix / suffix check update, see
+// llr_near_overflow in bposd_kernels.cuh).  With P the largest |prior| and d the largest column degree, the largest
+// magnitude of any message or LLR after pass t is at most P (d + 1)^t: a check message never exceeds the largest
+// bit-to-check message, and a bit sums its prior and at most d check messages.  Guarding starts while that bound is
+// still below the threshold the kernels test against (1e300 / 1e30).  Per-shot priors are not known on the host: 0.
+static int overflow_safe_iterations(const bposd_handle *h, bool per_shot_priors, bool fp32) {
+    // fp32 fast mode: not guarded.  It promises no bit-exactness, a shot whose messages overflow is a shot that does not
+    // converge (OSD takes it either way), and fp32 would reach the guarded range at pass ~48, inside the bulk of the
+    // iterations: 247.9 -> 232.9 M shot-iterations/s on the bench workload (profiles/r2y_bench_fp32.json).
+    if (fp32) return 0x7fffffff;
+    if (per_shot_priors) return 0;
+    double P = 1.0;
+    for (int j = 0; j < h->n; j++) {
+        const double p = h->probs[j];
+        const double l = std::fabs(std::log((1.0 - p) / p));
+        if (!(l <= 1e30)) return 0; // p = 0 or 1: infinite priors from the start
+        P = std::max(P, l);
+    }
+    const double lim = std::log(fp32 ? 1e30 : 1e300) - std::log(P) - std::log(4.0);
+    const double per = std::log((double)std::max(h->max_col_deg, 1) + 1.0);
+    const double t = lim / per;
+    return t < 1.0 ? 0 : (t > 1e9 ? 1000000000 : (int)t);
 }
 
 static int upload_probs(bposd_handle *h) {
@@ -464,8 +493,9 @@ extern "C" void bposd_destroy(bposd_t *h) {
     fast_free(h->fast);
     cluster_free(h->clus);
     cluster_free(h->clus_u);
+    cudaFree(h->d_order);
     for (auto &sl : h->slot) {
-        cudaFree(sl.d_ctrl); cudaFree(sl.d_fail_list); cudaFree(sl.d_fail_llr);
+        cudaFree(sl.d_ctrl); cudaFree(sl.d_fail_list); cudaFree(sl.d_fail_llr); cudaFree(sl.d_serial_ws);
         if (sl.h_ctrl) cudaFreeHost(sl.h_ctrl);
         cudaFree(sl.b_synd); cudaFree(sl.b_err); cudaFree(sl.b_osdw); cudaFree(sl.b_osd0); cudaFree(sl.b_bp);
         cudaFree(sl.b_conv); cudaFree(sl.b_llr); cudaFree(sl.b_iter);
@@ -688,6 +718,28 @@ extern "C" int bposd_math_probe(bposd_t *h, int32_t fn, const double *a, const d
     return BPOSD_OK;
 }
 
+extern "C" int bposd_set_schedule(bposd_t *h, int32_t schedule, const int32_t *order) {
+    if (!h) return BPOSD_EINVAL;
+    if (schedule != 0 && schedule != 1) return fail(h, BPOSD_EINVAL, "schedule must be 0 (parallel) or 1 (serial)");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (order) {
+        std::vector<char> seen((size_t)h->n, 0);
+        for (int k = 0; k < h->n; k++) {
+            if (order[k] < 0 || order[k] >= h->n || seen[order[k]]) return fail(h, BPOSD_EINVAL, "serial_schedule_order must be a permutation of 0 .. n-1");
+            seen[order[k]] = 1;
+        }
+    }
+    CU_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->d_order);
+    h->d_order = nullptr;
+    if (schedule == 1 && order && h->n > 0) {
+        CU_TRY(h, cudaMalloc((void **)&h->d_order, (size_t)h->n * sizeof(int)));
+        CU_TRY(h, cudaMemcpy(h->d_order, order, (size_t)h->n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    h->schedule = schedule;
+    return BPOSD_OK;
+}
+
 extern "C" int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size) {
     if (!h) return BPOSD_EINVAL;
     if (cluster_size != 0 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8 && cluster_size != 16)
@@ -889,6 +941,7 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     a.max_iter = h->max_iter;
     a.method = h->bp_method;
     a.alpha0 = (real)h->alpha;
+    a.safe_it = overflow_safe_iterations(h, d_priors != nullptr, sizeof(real) == 4);
     a.uniform_prior = d_priors ? 0 : h->uniform_prior;
     if (d_priors) { a.prior = static_cast<const real *>(d_priors); a.prior_stride = n; }
     else { a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32; a.prior_stride = 0; }
@@ -908,7 +961,21 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     a.g_dec = h->d_scratch_dec;
     const int grid = (int)std::min<long long>(Bc, h->bp_grid);
     CU_TRY(h, cudaEventRecord(sl.ev[0], st));
-    if (h->bp_kernel == 3) {
+    if (h->schedule == 1) {
+        // serial schedule: one thread per shot, a warp's 32 shots in lockstep, messages in an HBM workspace per warp
+        const size_t wb = serial_warp_bytes<real>(m, n, h->nnz);
+        const long long want_warps = std::min<long long>((Bc + 31) / 32, (long long)h->sm_count * 16);
+        const long long fit_warps = std::max<long long>(1, (long long)(((size_t)4 << 30) / wb)); // at most 4 GiB of workspace
+        const int wpb = 4; // warps per CTA; the grid is whole CTAs and every warp of it owns a workspace
+        const int warps = ((int)std::min(want_warps, fit_warps) + wpb - 1) / wpb * wpb;
+        if ((size_t)warps * wb > sl.serial_ws_bytes) {
+            cudaFree(sl.d_serial_ws);
+            sl.d_serial_ws = nullptr; sl.serial_ws_bytes = 0;
+            CU_TRY(h, cudaMalloc((void **)&sl.d_serial_ws, (size_t)warps * wb));
+            sl.serial_ws_bytes = (size_t)warps * wb;
+        }
+        bp_serial_kernel<real><<<warps / wpb, wpb * 32, 0, st>>>(a, h->d_order, sl.d_serial_ws, wb);
+    } else if (h->bp_kernel == 3) {
         if (a.uniform_prior && h->clus_u.CL > 0) {
             const int ncl = (int)std::min<long long>(Bc, h->clus_u_nclusters);
             CU_TRY(h, cluster_launch<real>(h->clus_u, a, ncl, h->clus_u_threads, (size_t)h->clus_u_smem, h->clus_u_flip_table, st));
@@ -1126,6 +1193,7 @@ static int decode_latency_t(bposd_handle *h, const uint8_t *h_synd, long long B,
     a.max_iter = h->max_iter;
     a.method = h->bp_method;
     a.alpha0 = (real)h->alpha;
+    a.safe_it = overflow_safe_iterations(h, false, sizeof(real) == 4);
     a.uniform_prior = h->uniform_prior;
     a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32;
     a.prior_stride = 0;
@@ -1194,7 +1262,7 @@ static int decode_host_t(bposd_handle *h, const uint8_t *h_synd, long long B, ui
     if (rc) return rc;
     // bytes per shot on the host side: one per bit, or bit-packed (syndromes ceil(m/8), decodings ceil(n/8))
     const size_t sb = packed ? ((size_t)m + 7) / 8 : (size_t)m, db = packed ? ((size_t)n + 7) / 8 : (size_t)n;
-    if (h->bp_kernel == 2 && h->lat_geom >= 0 && B <= h->lat_max_shots) {
+    if (h->bp_kernel == 2 && h->lat_geom >= 0 && B <= h->lat_max_shots && h->schedule == 0) {
         bool taken = false;
         if (!packed) {
             rc = decode_latency_t<real>(h, h_synd, B, h_osdw, h_osd0, h_bp, h_llr, h_conv, h_iter, &taken);

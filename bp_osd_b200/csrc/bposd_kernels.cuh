@@ -36,6 +36,7 @@ struct BpArgs {
     int max_iter;
     int method;   // 0 product-sum, 1 min-sum
     real alpha0;  // 0 => 1 - 2^-it
+    int safe_it;  // no message can have overflowed before this pass (see overflow_safe_iterations); 0: always check
     const real *prior;
     long long prior_stride; // 0: one prior vector for all shots, n: per-shot rows
     int uniform_prior;      // 1: every bit has the same prior (a scalar in registers)
@@ -59,6 +60,22 @@ struct BpArgs {
 template <typename real> __device__ __forceinline__ real real_max();
 template <> __device__ __forceinline__ double real_max<double>() { return DBL_MAX; }
 template <> __device__ __forceinline__ float real_max<float>() { return FLT_MAX; }
+
+// Overflow guard of the prefix / suffix check update (fast_check_compute).  The reference's running minimum starts from the
+// largest finite value (`temp = numeric_limits<double>::max(); if (abs(b2c) < temp) temp = abs(b2c)`), so a check message
+// never exceeds it even when every incoming message has overflowed to +-inf; the prefix / suffix form starts from the
+// row's own entries and would pass the infinity on.  Messages of shots that do not converge grow geometrically (cfg 3
+// reaches 6e234 after 1 922 passes), so this matters for max_iter beyond a few thousand passes -- config 5 runs 40 000.
+// An infinite bit-to-check message and +-max are the same thing to the reference's check update (neither is smaller than
+// the starting value; `<= 0` sees the same sign), so: from the pass where an overflow is conceivable (safe_it, host side)
+// every thread tests its bits' LLRs after the bit sweep; a sum that is not finite-and-small raises a CTA-wide flag, and
+// the next check sweep first rewrites +-inf in its rows as +-max.  Nothing is added to passes before safe_it.
+template <typename real> __device__ __forceinline__ bool llr_near_overflow(real t);
+template <> __device__ __forceinline__ bool llr_near_overflow<double>(double t) { return !(fabs(t) <= 1e300); }
+template <> __device__ __forceinline__ bool llr_near_overflow<float>(float t) { return !(fabsf(t) <= 1e30f); }
+template <typename real> __device__ __forceinline__ real clamp_inf(real v);
+template <> __device__ __forceinline__ double clamp_inf<double>(double v) { return (fabs(v) > DBL_MAX) ? copysign(DBL_MAX, v) : v; }
+template <> __device__ __forceinline__ float clamp_inf<float>(float v) { return (fabsf(v) > FLT_MAX) ? copysignf(FLT_MAX, v) : v; }
 
 // syndrome bit of check i of a shot, from the byte-per-check or the bit-packed layout
 __device__ __forceinline__ unsigned synd_bit(const uint8_t *synd, long long shot, int m, int i, int packed) {

@@ -100,13 +100,21 @@ class BpOsdDecoder:
                  bp_method="minimum_sum", ms_scaling_factor=1.0, osd_method="osd_0", osd_order=0,
                  error_channel=None, schedule="parallel", input_vector_type="syndrome",
                  precision=64, device=None, **ignored):
-        # keywords of ldpc's BpOsdDecoder that have no effect on the results of the parallel schedule are accepted and
-        # ignored; anything else is a spelling mistake and must not be swallowed
+        # keywords of ldpc's BpOsdDecoder that have no effect on the results are accepted and ignored; anything else is a
+        # spelling mistake and must not be swallowed
         unknown = set(ignored) - {"omp_thread_count", "random_schedule_seed", "serial_schedule_order", "random_serial_schedule"}
         if unknown:
             raise TypeError(f"unexpected keyword argument(s): {sorted(unknown)}")
-        if schedule not in ("parallel", 0, "0"):
-            raise ValueError("only the parallel (flooding) BP schedule is implemented")
+        # BP schedule (ldpc v2 option, not reachable from the reference): 'parallel' (flooding, the default) or 'serial'
+        # (bit after bit, in `serial_schedule_order` or 0 .. n-1).  The randomised serial schedule reshuffles the order
+        # with the C++ standard library's generator every iteration; that stream is not reproducible here and is refused.
+        sched = {"parallel": 0, 0: 0, "0": 0, "serial": 1, 1: 1, "1": 1}.get(schedule.lower() if isinstance(schedule, str) else schedule)
+        if sched is None:
+            raise ValueError("schedule must be 'parallel' or 'serial'")
+        if ignored.get("random_serial_schedule") not in (None, False, 0) or ignored.get("random_schedule_seed") not in (None, False, 0, -1):
+            raise ValueError("the randomised serial schedule (random_serial_schedule / random_schedule_seed) is not implemented")
+        order = ignored.get("serial_schedule_order")
+        self.schedule = "serial" if sched else "parallel"
         ivt = {"syndrome": 0, 0: 0, "0": 0, "received_vector": 1, 1: 1, "1": 1, "auto": 2, 2: 2, "2": 2}.get(
             input_vector_type.lower() if isinstance(input_vector_type, str) else input_vector_type)
         if ivt is None:
@@ -176,6 +184,13 @@ class BpOsdDecoder:
                               self.precision, self.device, C.byref(handle))
         _capi.check(None, rc)
         self._h = handle
+        if sched:
+            o = None
+            if order is not None:
+                o = np.ascontiguousarray(order, dtype=np.int32)
+                if o.shape != (self.n,):
+                    raise ValueError(f"serial_schedule_order must have length {self.n}")
+            self._check(lib.bposd_set_schedule(self._h, 1, _ptr(o)))
         info = self.info()
         self.rank, self.k = info["rank"], info["k"]
         self.max_iter = info["max_iter"]

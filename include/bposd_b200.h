@@ -205,6 +205,11 @@ int bposd_fp64_peak(bposd_t *h, double *fma_per_s);
  * the tests can compare it bit for bit with the host side (the oracle).  fn: 0 out = a / b (the in-range division
  * sequence), 1 tanh(a), 2 log(a), 3 (1 + a) / (1 - a) as the product-sum update forms it; b is read for fn = 0 only. */
 int bposd_math_probe(bposd_t *h, int32_t fn, const double *a, const double *b, double *out, int64_t count);
+/* BP schedule (ldpc.BpOsdDecoder's `schedule` / `serial_schedule_order`; /root/reference never passes them, SURVEY row
+ * f4).  schedule 0: parallel (flooding), the default.  1: serial -- inside an iteration the bits are visited one after the
+ * other in `order` (host array, a permutation of 0 .. n-1; NULL = 0, 1, ..., n-1), each recomputing the check-to-bit
+ * messages of its edges from the current bit-to-check messages.  One thread per shot (bp_serial_kernel.cuh). */
+int bposd_set_schedule(bposd_t *h, int32_t schedule, const int32_t *order);
 /* Thread-block-cluster size of BP kernel variant 3 (messages split over the shared memory of 2, 4, 8 or
  * 16 CTAs, reached through distributed shared memory); 0 = smallest size that fits. */
 int bposd_set_cluster_size(bposd_t *h, int32_t cluster_size);

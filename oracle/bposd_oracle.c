@@ -59,6 +59,8 @@ typedef struct {
     long stat_elim_wordxors;
     long total_elim_wordxors, total_osd; /* accumulated over decodes (algorithmic-op count of SURVEY.md 8d) */
     int math_mode;                       /* ORACLE_MATH_SHARED (default) or ORACLE_MATH_LIBM */
+    int schedule;                        /* 0 parallel (flooding), 1 serial (row f4) */
+    int *sched_order;                    /* serial schedule: bit order, NULL = 0 .. n-1 */
 } oracle_t;
 
 static double o_tanh(const oracle_t *o, double x) { return o->math_mode == ORACLE_MATH_LIBM ? tanh(x) : bpm_tanh(x); }
@@ -111,7 +113,7 @@ void oracle_destroy(oracle_t *o) {
     free(o->row_ptr); free(o->col_idx); free(o->col_ptr); free(o->row_idx); free(o->to_csr);
     free(o->probs); free(o->b2c); free(o->c2b); free(o->prior); free(o->llr);
     free(o->bp_dec); free(o->cand); free(o->osd0); free(o->osdw);
-    free(o->order); free(o->piv_col); free(o->nonpiv); free(o->work);
+    free(o->order); free(o->piv_col); free(o->nonpiv); free(o->work); free(o->sched_order);
     free(o);
 }
 
@@ -182,7 +184,88 @@ void oracle_update_channel_probs(oracle_t *o, const double *probs) {
 
 /* ------------------------------------------------------------------ BP (rows a3-a8) */
 
+/* row f4: ldpc's BpOsdDecoder(schedule="serial", serial_schedule_order=...), an option the reference never passes.
+ * order: a permutation of 0 .. n-1 (copied), or NULL for the natural order. */
+void oracle_set_schedule(oracle_t *o, int schedule, const int *order) {
+    free(o->sched_order);
+    o->sched_order = NULL;
+    o->schedule = schedule;
+    if (schedule == 1 && order) {
+        o->sched_order = (int *)malloc(sizeof(int) * (size_t)(o->n > 0 ? o->n : 1));
+        memcpy(o->sched_order, order, sizeof(int) * (size_t)o->n);
+    }
+}
+
+/* Serial schedule, restated from upstream ldpc's bp_decode_serial (src_cpp/bp.hpp of ldpc >= 2.0; absent from
+ * /root/reference, "parity unpinned" like the rest of this file).  Inside an iteration the bits are visited one after the
+ * other; bit j, for each of its edges in ascending check order: the check-to-bit message from the CURRENT bit-to-check
+ * messages of the check's other edges (min-sum: smallest magnitude, sign = syndrome + count of messages <= 0, scaled by
+ * alpha as in the parallel schedule; product-sum: product of tanh(b2c / 2) over the others in ascending column order,
+ * +-log((1 + x) / (1 - x))); the edge's bit-to-check message becomes the running sum "prior + messages of the edges
+ * before it", the message is added to the sum.  The sum is the bit's log-probability ratio (hard decision: 1 iff <= 0);
+ * then, from the last edge backwards, every bit-to-check message also receives the messages of the edges after it.  The
+ * candidate syndrome is tested at the end of every iteration. */
+static void bp_decode_serial(oracle_t *o, const uint8_t *synd) {
+    const int m = o->m, n = o->n;
+    double *b2c = o->b2c, *c2b = o->c2b;
+    o->converge = 0;
+    o->iter = 0;
+    for (int j = 0; j < n; j++) {
+        o->prior[j] = log((1.0 - o->probs[j]) / o->probs[j]);
+        o->llr[j] = o->prior[j];
+        o->bp_dec[j] = 0;
+        for (int p = o->col_ptr[j]; p < o->col_ptr[j + 1]; p++) b2c[o->to_csr[p]] = o->prior[j];
+    }
+    for (int it = 1; it <= o->max_iter; it++) {
+        const double alpha = (o->ms_scaling_factor == 0.0) ? 1.0 - pow(2.0, -1.0 * it) : o->ms_scaling_factor;
+        for (int k = 0; k < n; k++) {
+            const int j = o->sched_order ? o->sched_order[k] : k;
+            double llr = o->prior[j];
+            for (int p = o->col_ptr[j]; p < o->col_ptr[j + 1]; p++) {
+                const int e = o->to_csr[p], i = o->row_idx[p];
+                double c;
+                if (o->bp_method == BP_PRODUCT_SUM) {
+                    double x = 1.0;
+                    for (int g = o->row_ptr[i]; g < o->row_ptr[i + 1]; g++)
+                        if (g != e) x *= o_tanh(o, b2c[g] / 2);
+                    c = (synd[i] ? -1.0 : 1.0) * o_log(o, (1 + x) / (1 - x));
+                } else {
+                    int sgn = synd[i];
+                    double t = DBL_MAX;
+                    for (int g = o->row_ptr[i]; g < o->row_ptr[i + 1]; g++) {
+                        if (g == e) continue;
+                        const double a = fabs(b2c[g]);
+                        if (a < t) t = a;
+                        if (b2c[g] <= 0) sgn += 1;
+                    }
+                    c = ((sgn % 2 == 0) ? 1.0 : -1.0) * alpha * t;
+                }
+                c2b[e] = c;
+                b2c[e] = llr;
+                llr += c;
+            }
+            o->llr[j] = llr;
+            o->bp_dec[j] = (llr <= 0) ? 1 : 0;
+            double t = 0;
+            for (int p = o->col_ptr[j + 1] - 1; p >= o->col_ptr[j]; p--) {
+                const int e = o->to_csr[p];
+                b2c[e] += t;
+                t += c2b[e];
+            }
+        }
+        int same = 1;
+        for (int i = 0; i < m && same; i++) {
+            int par = 0;
+            for (int e = o->row_ptr[i]; e < o->row_ptr[i + 1]; e++) par ^= o->bp_dec[o->col_idx[e]];
+            if (par != (synd[i] & 1)) same = 0;
+        }
+        o->iter = it;
+        if (same) { o->converge = 1; return; }
+    }
+}
+
 static void bp_decode(oracle_t *o, const uint8_t *synd) {
+    if (o->schedule == 1) { bp_decode_serial(o, synd); return; }
     const int m = o->m, n = o->n;
     double *b2c = o->b2c, *c2b = o->c2b;
     o->converge = 0;

@@ -50,6 +50,7 @@ def lib():
             f = getattr(L, "oracle_" + name)
             f.restype, f.argtypes = P, [P]
         L.oracle_set_math.argtypes = [P, C.c_int]
+        L.oracle_set_schedule.restype, L.oracle_set_schedule.argtypes = None, [P, C.c_int, P]
         for name in ("tanh", "log", "expm1"):
             f = getattr(L, "oracle_math_" + name)
             f.restype, f.argtypes = C.c_double, [C.c_double]
@@ -91,7 +92,8 @@ def csr_of(h):
 
 class OracleDecoder:
     def __init__(self, parity_check_matrix, error_rate=None, channel_probs=None, max_iter=0,
-                 bp_method="ms", ms_scaling_factor=1.0, osd_method="osd0", osd_order=0, math="shared"):
+                 bp_method="ms", ms_scaling_factor=1.0, osd_method="osd0", osd_order=0, math="shared",
+                 schedule="parallel", serial_schedule_order=None):
         """math: "shared" = the portable tanh/log of include/bposd_math.h (the functions the CUDA kernels use, so
         product-sum compares bit for bit), "libm" = the host libm, as ldpc itself calls (last bits machine dependent)."""
         h = csr_of(parity_check_matrix)
@@ -114,6 +116,12 @@ class OracleDecoder:
         if math not in ("shared", "libm"):
             raise ValueError("math must be 'shared' or 'libm'")
         lib().oracle_set_math(self._h, 1 if math == "libm" else 0)
+        if schedule not in ("parallel", "serial"):
+            raise ValueError("schedule must be 'parallel' or 'serial'")
+        if schedule == "serial":   # row f4: an ldpc option the reference never passes
+            o = None if serial_schedule_order is None else np.ascontiguousarray(serial_schedule_order, dtype=np.int32)
+            assert o is None or sorted(o.tolist()) == list(range(self.n))
+            lib().oracle_set_schedule(self._h, 1, _ptr(o))
         self.rank = lib().oracle_rank(self._h)
         self.k = lib().oracle_k(self._h)
         if om != 0 and int(osd_order) > self.k:

@@ -23,7 +23,8 @@ DBL_MAX = sys.float_info.max
 
 
 class SlowDecoder:
-    def __init__(self, h, probs, max_iter, bp_method, ms_scaling_factor, osd_method, osd_order, tanh=None, log=None):
+    def __init__(self, h, probs, max_iter, bp_method, ms_scaling_factor, osd_method, osd_order, tanh=None, log=None,
+                 schedule="parallel", serial_schedule_order=None):
         # tanh / log: the product-sum functions (default: the host libm, as ldpc calls them; the goldens pass the portable
         # functions of include/bposd_math.h through oracle.oracle.lib() so that both restatements agree bit for bit)
         self._tanh = tanh or math.tanh
@@ -43,9 +44,57 @@ class SlowDecoder:
         self.alpha0 = float(ms_scaling_factor)
         self.osd_method = osd_method  # "osd0" | "osd_e" | "osd_cs"
         self.osd_order = 0 if osd_method == "osd0" else int(osd_order)
+        self.schedule = schedule
+        self.serial_order = list(range(self.n)) if serial_schedule_order is None else [int(j) for j in serial_schedule_order]
+
+    # ---- BP, serial schedule (ldpc option `schedule="serial"`) ----
+    def bp_serial(self, synd):
+        """Bit after bit: every edge of the bit gets a fresh check-to-bit message from the check's other edges, the bit's
+        outgoing messages are the sum of the prior and the OTHER incoming messages (accumulated as a prefix in ascending
+        check order plus a suffix from the last edge backwards, the reference's order of additions)."""
+        n, m = self.n, self.m
+        with np.errstate(divide="ignore"):
+            prior = [float(np.log(np.float64(1.0 - p) / np.float64(p))) for p in self.probs]
+        out = {(i, j): prior[j] for i in range(m) for j in self.rows[i]}      # bit-to-check
+        self.converge, self.iter = False, 0
+        llr, dec = list(prior), [0] * n
+        for it in range(1, self.max_iter + 1):
+            alpha = (1.0 - 2.0 ** (-it)) if self.alpha0 == 0.0 else self.alpha0
+            for j in self.serial_order:
+                inc = []
+                total = prior[j]
+                for i in self.cols[j]:
+                    others = [out[(i, jj)] for jj in self.rows[i] if jj != j]
+                    if self.bp_method == "ps":
+                        x = 1.0
+                        for v in others:
+                            x *= self._tanh(v / 2)
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            msg = float((-1.0 if synd[i] else 1.0) * self._log(float(np.float64(1 + x) / np.float64(1 - x))))
+                    else:
+                        mag = min([abs(v) for v in others], default=DBL_MAX)
+                        neg = int(synd[i]) + sum(1 for v in others if v <= 0)
+                        msg = (1.0 if neg % 2 == 0 else -1.0) * alpha * mag
+                    out[(i, j)] = total
+                    total = total + msg
+                    inc.append(msg)
+                llr[j] = total
+                dec[j] = 1 if total <= 0 else 0
+                tail = 0.0
+                for i, msg in zip(reversed(self.cols[j]), reversed(inc)):
+                    out[(i, j)] = out[(i, j)] + tail
+                    tail = tail + msg
+            self.iter = it
+            if all(sum(dec[j] for j in self.rows[i]) % 2 == (int(synd[i]) & 1) for i in range(m)):
+                self.converge = True
+                break
+        self.llr, self.bp_decoding = llr, dec
+        return dec
 
     # ---- BP, flooding schedule -----------------------------------------
     def bp(self, synd):
+        if self.schedule == "serial":
+            return self.bp_serial(synd)
         n, m = self.n, self.m
         with np.errstate(divide="ignore"):
             prior = [float(np.log(np.float64(1.0 - p) / np.float64(p))) for p in self.probs]

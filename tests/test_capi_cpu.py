@@ -92,7 +92,9 @@ def test_python_layer_argument_errors():
     with pytest.raises(ValueError):
         BpOsdDecoder(H, error_rate=1.5)
     with pytest.raises(ValueError):
-        bposd_decoder(H, error_rate=0.1, schedule="serial")
+        bposd_decoder(H, error_rate=0.1, schedule="layered")
+    with pytest.raises(ValueError):   # the randomised serial schedule depends on the C++ library's shuffle: refused
+        bposd_decoder(H, error_rate=0.1, schedule="serial", random_serial_schedule=True)
 
 
 def test_product_does_not_import_the_oracle():

@@ -149,6 +149,15 @@ def test_device_math_is_the_host_math(torch_cuda, oracle_mod, cfg_codes):
 
     # division: generic operands over the whole range the header allows, then the three shapes that occur
     same("div", logu(N, -60, 70), logu(N, -60, 70))
+    # hard cases: divisors whose mantissa is all ones or nearly (where an unbiased reciprocal seed ties), and quotients
+    # within a few ulps of a representable number or of a midpoint between two
+    k = rng.integers(1, 64, N).astype(np.float64)
+    same("div", logu(N, -40, 40), (2.0 - k * 2.0 ** -52) * np.exp2(rng.integers(-30, 30, N)) * sign(N))
+    bq, tq = logu(N, -20, 20), logu(N, -20, 20)
+    near = np.nextafter(bq * tq, np.where(rng.random(N) < 0.5, np.inf, -np.inf))
+    same("div", np.where(rng.random(N) < 0.3, bq * tq, near), bq)
+    half = tq * (1 + 2.0 ** -53)                                         # t + half an ulp (rounded): products near midpoints
+    same("div", bq * half, bq)
     u = np.expm1(rng.uniform(-2, 44, N))
     same("div", np.where(u > 1, 2.0, -u), u + 2.0)                      # inside tanh
     f = rng.uniform(np.sqrt(0.5) - 1, np.sqrt(2) - 1, N)
@@ -217,6 +226,44 @@ def test_received_vector_input_and_method_aliases(torch_cuda, oracle_mod, cfg_co
         BpOsdDecoder(H, error_rate=0.05, bp_method="ms", schedule="serial", **kw)
     with pytest.raises(ValueError):
         BpOsdDecoder(H, error_rate=0.05, bp_method="ms", input_vector_type="codeword", **kw)
+
+
+@pytest.mark.parametrize("cfg,p,B,method,alpha,max_iter,osd_method,osd_order,custom_order,nonuniform", [
+    (1, 0.10, 700, "ms", 0.0, 8, "osd_cs", 7, False, False),
+    (1, 0.10, 300, "ps", 0.0, 8, "osd_e", 6, True, False),
+    (2, 0.06, 300, "ms", 0.75, 20, "osd_cs", 7, True, True),
+    (2, 0.06, 100, "ps", 0.0, 12, "osd0", 0, False, False),
+    (3, 0.05, 70, "ms", 0.0, 30, "osd_cs", 7, False, False),   # 70 shots: three warps, the last one partly idle
+])
+def test_serial_schedule(torch_cuda, oracle_mod, cfg_codes, cfg, p, B, method, alpha, max_iter, osd_method, osd_order, custom_order,
+                         nonuniform):
+    """ldpc's serial BP schedule (an option the reference never passes) -- one thread per shot on the GPU --
+    bit for bit against the oracle: min-sum and product-sum, natural and given bit order, non-uniform channel, followed
+    by OSD on the shots that did not converge; device and host input, and the single-shot decode()."""
+    from bp_osd_b200 import BpOsdDecoder
+    torch = torch_cuda
+    H = cfg_codes(cfg).hz
+    n = H.shape[1]
+    rng = np.random.default_rng(100 + cfg)
+    order = rng.permutation(n) if custom_order else None
+    probs = rng.uniform(0.5 * p, 1.5 * p, size=n) if nonuniform else np.full(n, p)
+    kw = dict(max_iter=max_iter, bp_method=method, ms_scaling_factor=alpha, osd_method=osd_method, osd_order=osd_order)
+    e = (rng.random((B, n)) < probs).astype(np.uint8)
+    syn = np.asarray((H @ e.T) % 2, dtype=np.uint8).T.copy()
+    ref = oracle_mod.OracleDecoder(H, channel_probs=probs, schedule="serial", serial_schedule_order=order, **kw).decode_batch(syn)
+    assert 0 < (ref["converge"] == 0).sum() < B
+    d = BpOsdDecoder(H, channel_probs=probs, schedule="serial", serial_schedule_order=order, **kw)
+    r = d.decode_batch(torch.tensor(syn, device="cuda"))
+    out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
+               llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
+    assert_exact(out, ref)
+    rh = d.decode_batch(syn[:40], return_llr=False)          # host input, LLRs through the failed-shot workspace
+    assert (np.asarray(rh.osdw_decoding) == ref["osdw"][:40]).all() and (np.asarray(rh.iter) == ref["iter"][:40]).all()
+    x = d.decode(syn[0])
+    assert (np.asarray(x) == ref["osdw"][0]).all() and d.iter == ref["iter"][0] and bool(d.converge) == bool(ref["converge"][0])
+    # the parallel schedule on the same decoder arguments is a different algorithm: it must not be what ran
+    par = oracle_mod.OracleDecoder(H, channel_probs=probs, **kw).decode_batch(syn)
+    assert (par["iter"] != ref["iter"]).any()
 
 
 def test_nonuniform_and_zero_probabilities(torch_cuda, oracle_mod, cfg_codes):

@@ -103,3 +103,49 @@ def test_config5_max_iter_n_nonconverged(torch_cuda, oracle_mod, cfg_codes):
     compare(out, ref)
     assert int((ref["converge"] == 0).sum()) >= 4
     assert int(ref["iter"].max()) == H.shape[1]
+
+
+def test_config5_three_hundred_shots_every_iteration_count(torch_cuda, oracle_mod, cfg_codes):
+    """Config 5 at its bench error rate (p = 0.02), 320 shots, max_iter = 300: converge flag, iteration count, BP decoding
+    and every LLR bit of EVERY shot against the oracle -- slow shots (hundreds of iterations, many hard-decision flips:
+    the incremental parity tracking of the cluster kernel) and shots that do not converge included."""
+    from bp_osd_b200 import BpOsdDecoder
+    H = cfg_codes(5).hz
+    kw = dict(max_iter=300, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)
+    _, syn = random_syndromes(H, 0.02, 320, seed=77)
+    ref = oracle_decode_parallel(H, syn, 0.02, dict(kw, osd_method="osd0"), chunk=8)
+    d = BpOsdDecoder(H, error_rate=0.02, **dict(kw, osd_method="off"))
+    info = d.info()
+    assert info["bp_kernel"] == 3
+    r = d.decode_batch(torch_cuda.tensor(syn, device="cuda"))
+    conv, it = r.converge.cpu().numpy(), r.iter.cpu().numpy()
+    bad = np.flatnonzero((conv != ref["converge"].astype(bool)) | (it != ref["iter"]))
+    assert bad.size == 0, f"cluster size {info['bp_cluster_size']}: shots {bad[:8]} gpu iter {it[bad[:8]]} oracle iter {ref['iter'][bad[:8]]}"
+    assert (r.bp_decoding.cpu().numpy() == ref["bp"]).all()
+    assert np.array_equal(r.log_prob_ratios.cpu().numpy(), ref["llr"])
+    assert int((ref["iter"] > 100).sum()) >= 5 and int((ref["converge"] == 0).sum()) >= 3
+
+
+@pytest.mark.parametrize("cfg,p,p_syn,max_iter", [(3, 0.05, 0.09, 4000), (2, 0.06, 0.10, 3000)])
+def test_overflow_regime_beyond_max_iter_n(torch_cuda, oracle_mod, cfg_codes, cfg, p, p_syn, max_iter):
+    """max_iter far beyond n on shots that do not converge: their messages grow geometrically and overflow to +-inf after
+    a few thousand passes.  The reference's running minimum starts from the largest finite double, so its check messages
+    stay finite; the prefix / suffix kernels reproduce that through their overflow guard (llr_near_overflow).  Every
+    kernel, bit for bit: LLRs (with +-inf in the same places), decodings, iteration counts."""
+    from bp_osd_b200 import BpOsdDecoder
+    H = cfg_codes(cfg).hz
+    kw = dict(max_iter=max_iter, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)
+    _, syn = random_syndromes(H, p_syn, 32, seed=5)
+    ref = oracle_decode_parallel(H, syn, p, kw, chunk=2)
+    assert np.isinf(ref["llr"]).any(), "the case is meant to reach the overflow regime"
+    variants = [(None, 0), (1, 0)] + ([(3, 4), (3, 16)] if cfg == 2 else [])
+    for kernel, cl in variants:
+        d = BpOsdDecoder(H, error_rate=p, **kw)
+        if kernel is not None:
+            d.set_tuning(bp_kernel=kernel)
+        if cl:
+            d.set_cluster_size(cl)
+        r = d.decode_batch(torch_cuda.tensor(syn, device="cuda"))
+        out = dict(osdw=r.osdw_decoding.cpu().numpy(), osd0=r.osd0_decoding.cpu().numpy(), bp=r.bp_decoding.cpu().numpy(),
+                   llr=r.log_prob_ratios.cpu().numpy(), converge=r.converge.cpu().numpy(), iter=r.iter.cpu().numpy())
+        compare(out, ref)

@@ -213,3 +213,33 @@ def test_product_sum_shared_vs_libm_modes(oracle_mod, cfg_codes):
     assert (a["iter"][quick] == b["iter"][quick]).all() and (a["bp"][quick] == b["bp"][quick]).all()
     assert np.allclose(a["llr"][quick], b["llr"][quick], rtol=1e-9, atol=0)
     assert (a["osdw"] == b["osdw"]).all(1).mean() >= 0.95
+
+
+@pytest.mark.parametrize("cfg,p,method,alpha,max_iter", [(1, 0.1, "ms", 0.0, 10), (1, 0.1, "ps", 0.0, 10), (2, 0.06, "ms", 0.8, 12)])
+def test_serial_schedule_two_restatements_agree(oracle_mod, cfg_codes, cfg, p, method, alpha, max_iter):
+    """SURVEY row f4 (ldpc's `schedule="serial"`, never passed by the reference): the C oracle and the independently
+    written Python restatement agree bit for bit, in the natural order and in a given `serial_schedule_order`; on an
+    acyclic graph (repetition code) the serial schedule converges to the same decoding as the parallel one."""
+    from oracle.slow_ref import SlowDecoder
+    H = cfg_codes(cfg).hz
+    n = H.shape[1]
+    rng = np.random.default_rng(cfg)
+    tanh, log = oracle_mod.lib().oracle_math_tanh, oracle_mod.lib().oracle_math_log
+    for order in (None, rng.permutation(n)):
+        _, syn = random_syndromes(H, p, 8, seed=3)
+        kw = dict(max_iter=max_iter, bp_method=method, ms_scaling_factor=alpha, osd_method="osd_cs", osd_order=4)
+        ref = oracle_mod.OracleDecoder(H, error_rate=p, schedule="serial", serial_schedule_order=order, **kw).decode_batch(syn)
+        slow = SlowDecoder(H, [p] * n, max_iter, method, alpha, "osd_cs", 4, tanh=tanh, log=log, schedule="serial",
+                           serial_schedule_order=order)
+        for b in range(syn.shape[0]):
+            x = slow.decode(syn[b])
+            assert (np.array(x) == ref["osdw"][b]).all() and (np.array(slow.bp_decoding) == ref["bp"][b]).all()
+            assert np.array_equal(np.array(slow.llr), ref["llr"][b], equal_nan=True)
+            assert slow.iter == ref["iter"][b] and slow.converge == bool(ref["converge"][b])
+    from bp_osd_b200 import codes
+    R = codes.rep_code(9)
+    _, syn = random_syndromes(R, 0.1, 40, seed=5)
+    a = oracle_mod.OracleDecoder(R, error_rate=0.1, max_iter=20, bp_method="ms", ms_scaling_factor=1.0, schedule="serial").decode_batch(syn)
+    b = oracle_mod.OracleDecoder(R, error_rate=0.1, max_iter=20, bp_method="ms", ms_scaling_factor=1.0).decode_batch(syn)
+    assert a["converge"].all() and b["converge"].all() and (a["bp"] == b["bp"]).all()
+    assert (a["iter"] <= b["iter"]).all()   # information travels the whole chain within one serial pass
