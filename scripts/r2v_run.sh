@@ -12,6 +12,7 @@ python bench.py --ms-scaling-factor 0.625 --shots-per-gpu 200000 --steps 3 --war
 python bench.py --precision 32 --no-cpu-baseline > gpurun_out/${TAG}_bench_fp32.json 2> gpurun_out/${TAG}_bench_fp32.err; echo "fp32 rc=$?"; tail -c 1200 gpurun_out/${TAG}_bench_fp32.json
 python bench.py --config 4 --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_cfg4.json 2> gpurun_out/${TAG}_bench_cfg4.err; echo "cfg4 rc=$?"; tail -c 2500 gpurun_out/${TAG}_bench_cfg4.json; tail -3 gpurun_out/${TAG}_bench_cfg4.err
 python bench.py --config 5 --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_cfg5.json 2> gpurun_out/${TAG}_bench_cfg5.err; echo "cfg5 rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_cfg5.json; tail -3 gpurun_out/${TAG}_bench_cfg5.err
-python scripts/cfg5_sweep.py --batches 1 64 4096 32768 262144 > gpurun_out/${TAG}_cfg5_sweep_1gpu.jsonl 2> gpurun_out/${TAG}_cfg5.err; tail -n 2 gpurun_out/${TAG}_cfg5.err; cut -c1-250 gpurun_out/${TAG}_cfg5_sweep_1gpu.jsonl
+python scripts/cfg5_sweep.py --batches 1 8 64 512 4096 32768 262144 > gpurun_out/${TAG}_cfg5_sweep_1gpu.jsonl 2> gpurun_out/${TAG}_cfg5.err; tail -n 2 gpurun_out/${TAG}_cfg5.err; cut -c1-250 gpurun_out/${TAG}_cfg5_sweep_1gpu.jsonl
+python scripts/cfg5_sweep.py --batches 262144 1048576 --chunk 262144 > gpurun_out/${TAG}_cfg5_sweep_1gpu_bigchunk.jsonl 2>> gpurun_out/${TAG}_cfg5.err; cut -c1-250 gpurun_out/${TAG}_cfg5_sweep_1gpu_bigchunk.jsonl
 scripts/profile.sh ${TAG}
 bash scripts/r2_ncu.sh ${TAG}_ps bp_fast python scripts/bp_speed.py --cfg 4 --method ps --osd osd_e --order 10 --shots 20000 --reps 1
