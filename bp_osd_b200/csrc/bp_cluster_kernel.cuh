@@ -25,6 +25,7 @@
 // traffic for 0.33 TB/s of payload.  Blocked, the crossbar carries each remote value once per direction in
 // fully used sectors, and 71 % of the edges never leave the SM.
 #pragma once
+#include <cstdlib>
 #include "bp_fast_kernel.cuh"
 
 namespace bposd {
@@ -53,7 +54,8 @@ struct ClusterDev {
     const uint32_t *row_of;
     const uint32_t *bit_of;
     int rows_per_cta, bits_per_cta, CL, nbox_max, nout_max;
-    int flip_table; // 1: per-edge parity-flip descriptors live in shared memory (bits_per_cta * DV words)
+    int flip_table; // parity-flip descriptors of the REMOTE edges in shared memory, one per mailbox entry: 1 32-bit cluster
+                    // addresses, 2 16-bit (CTA << 12 | row) words (rows_per_cta <= 4096), 0 none (global table at flip time)
 };
 
 static inline void cluster_free(ClusterTables &t) {
@@ -74,7 +76,7 @@ __host__ __device__ inline ClusterLayout cluster_layout(int RS, int elem, int rp
     L.o_meta = o; o = al(o + (size_t)rpc);                                 // one byte per check
     L.o_prior = o; o = al(o + (prior_table ? (size_t)bpc * elem : 0));     // priors by position (non-uniform channels only)
     L.o_xl = o; o = al(o + (size_t)(nout_max > 0 ? nout_max : 1) * 8);     // exchange list (byte offset, cluster address)
-    L.o_flip = o; o = al(o + (flip_table ? (size_t)bpc * DV * 4 : 0));     // parity-flip descriptors
+    L.o_flip = o; o = al(o + (flip_table == 1 ? (size_t)nbox_max * 4 : flip_table == 2 ? (size_t)nbox_max * 2 : 0)); // flip descriptors of the mailbox entries
     L.total = o + 16;
     return L;
 }
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
     uint8_t *meta = smem_raw + L.o_meta;                                   // bit0 mismatch, bits1-5 degree, bit7 syndrome
     real *prior_s = reinterpret_cast<real *>(smem_raw + L.o_prior);        // [bpc] priors by position (non-uniform only)
     uint2 *xl = reinterpret_cast<uint2 *>(smem_raw + L.o_xl);              // [nout] (byte offset of the row slot, cluster address of the mailbox entry)
-    uint32_t *flip_desc = reinterpret_cast<uint32_t *>(smem_raw + L.o_flip); // [bpc * DV]
+    uint32_t *flip_desc = reinterpret_cast<uint32_t *>(smem_raw + L.o_flip); // [nbox_max] flip descriptors of the mailbox entries
     __shared__ long long sh_shot;
     __shared__ int sh_slot;
     __shared__ unsigned sh_vote[2][16];
@@ -302,17 +304,26 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
         const uint32_t loc = t.xloc[(size_t)rank * t.nout_max + x], rem = t.xrem[(size_t)rank * t.nout_max + x];
         xl[x] = make_uint2(loc * (unsigned)sizeof(real), mapa_u32(msg_s + (rem & 0xFFFFFFu) * (unsigned)sizeof(real), rem >> 24));
     }
-    // A hard-decision flip toggles the parity-mismatch bit of every neighbouring check, wherever it lives.  The
-    // cluster address of that check's meta word (4-byte aligned) and its byte lane (low two bits) are resolved once
-    // per CTA; doing it at flip time costs a global load per edge that always misses L1 (barrier.cluster invalidates
-    // it), and flips are frequent on the shots that matter for the tail (BP that oscillates for thousands of passes).
+    // A hard-decision flip toggles the parity-mismatch bit of every neighbouring check, wherever it lives.  A check of this
+    // CTA (three edges in four) is found by arithmetic on the slot offset and toggled with a local shared-memory atomic.
+    // A remote check needs its cluster address: one descriptor per MAILBOX ENTRY, resolved once per CTA (32-bit cluster
+    // address | byte lane, or 16 bits (CTA << 12 | row) when shared memory is short); without a table it costs a global
+    // load per edge at flip time that always misses L1 (barrier.cluster invalidates it), with every other thread of the
+    // CTA waiting at the next barrier -- and some bit flips in most passes.
     auto flip_descriptor = [&](uint32_t f) -> uint32_t {
         if (f == BPC_NONE) return 0u;
         const uint32_t lp = f & 0xFFFFFFu;
         return mapa_u32(meta_s + (lp & ~3u), f >> 24) | (lp & 3u);
     };
+    uint16_t *flip_desc16 = reinterpret_cast<uint16_t *>(flip_desc);
     if (t.flip_table)
-        for (int e = tid; e < bpc * DV; e += T) flip_desc[e] = flip_descriptor(t.flip[(size_t)rank * bpc * DV + e]);
+        for (int e = tid; e < bpc * DV; e += T) {
+            const uint32_t sl = t.vslot[(size_t)rank * bpc * DV + e];
+            if (sl == BPC_NONE || sl < (uint32_t)rpc * RS) continue;
+            const uint32_t f = t.flip[(size_t)rank * bpc * DV + e];
+            if (t.flip_table == 1) flip_desc[sl - (uint32_t)rpc * RS] = flip_descriptor(f);
+            else flip_desc16[sl - (uint32_t)rpc * RS] = (uint16_t)(((f >> 24) << 12) | (f & 0xFFFu));
+        }
 
     // byte offsets (inside this CTA's shared memory) of the slots of this thread's bits: a row slot for an edge whose
     // check lives here, a mailbox entry otherwise (shot independent)
@@ -445,7 +456,17 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                     if ((flip >> r) & 1u) {
                         const int lq = tid + r * T;
                         for (int k = 0; k < dj[r]; k++) {
-                            const uint32_t d = t.flip_table ? flip_desc[lq * DV + k] : flip_descriptor(t.flip[((size_t)rank * bpc + lq) * DV + k]);
+                            const unsigned o = off[r][k];
+                            if (o < (unsigned)rpc * RS * (unsigned)sizeof(real)) { // the check lives here
+                                const unsigned p = o / (unsigned)(RS * sizeof(real));
+                                atomicXor(reinterpret_cast<unsigned *>(meta + (p & ~3u)), 1u << ((p & 3u) * 8u));
+                                continue;
+                            }
+                            const unsigned b = (o - (unsigned)rpc * RS * (unsigned)sizeof(real)) / (unsigned)sizeof(real);
+                            uint32_t d;
+                            if (t.flip_table == 1) d = flip_desc[b];
+                            else if (t.flip_table == 2) { const uint32_t w = flip_desc16[b]; d = mapa_u32(meta_s + (w & 0xFFCu), w >> 12) | (w & 3u); }
+                            else d = flip_descriptor(t.flip[((size_t)rank * bpc + lq) * DV + k]);
                             xor_dsmem_u32(d & ~3u, 1u << ((d & 3u) * 8u));
                         }
                     }
@@ -506,6 +527,10 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
 // ---- dispatch ------------------------------------------------------------------------------------
 // bits per thread: the smallest of {1, 2, 3, 4, 6, 8} that lets a CTA of <= 1024 threads cover its bits
 static inline int cluster_vpt(int bits_per_cta) {
+    if (const char *f = std::getenv("BPOSD_CLUSTER_VPT")) { // tuning knob (A/B of the CTA size): 6 or 8 bits per thread
+        const int v = std::atoi(f);
+        if ((v == 6 || v == 8) && (bits_per_cta + v - 1) / v <= 1024) return v;
+    }
     for (int v : {1, 2, 3, 4, 6, 8}) // prefer CTAs of <= 640 threads: 96+ registers per thread, no spills in fp64
         if ((bits_per_cta + v - 1) / v <= 640) return v;
     for (int v : {6, 8})

@@ -261,8 +261,10 @@ static int plan_geometry_t(bposd_handle *h) {
                     if (e != cudaSuccess) return fail(h, BPOSD_ECUDA, std::string("cluster_build: ") + cudaGetErrorString(e));
                 }
                 const int ct = cluster_threads(tab.bits_per_cta);
+                // parity-flip descriptors of the remote edges in shared memory when they fit: 32-bit, else 16-bit, else none
                 size_t csmem = cluster_smem_need<real>(tab, 1, prior_table);
-                int flip = 1; // parity-flip descriptors in shared memory when they fit
+                int flip = 1;
+                if (csmem > (size_t)h->smem_optin && tab.rows_per_cta <= 4096 && CL <= 16) { csmem = cluster_smem_need<real>(tab, 2, prior_table); flip = 2; }
                 if (csmem > (size_t)h->smem_optin) { csmem = cluster_smem_need<real>(tab, 0, prior_table); flip = 0; }
                 if (csmem > (size_t)h->smem_optin) continue; // rows + mailbox + exchange list of the fullest CTA do not fit: next size
                 int ncl = 0;

@@ -222,8 +222,8 @@ def test_received_vector_input_and_method_aliases(torch_cuda, oracle_mod, cfg_co
     ps = oracle_mod.OracleDecoder(H, error_rate=0.05, bp_method="ps", **kw)
     ps.decode(syn)
     assert (BpOsdDecoder(H, error_rate=0.05, bp_method="ps_log", **kw).decode(syn) == ps.osdw_decoding).all()
-    with pytest.raises(ValueError):
-        BpOsdDecoder(H, error_rate=0.05, bp_method="ms", schedule="serial", **kw)
+    with pytest.raises(ValueError):   # the randomised serial schedule is refused (test_serial_schedule covers the serial one)
+        BpOsdDecoder(H, error_rate=0.05, bp_method="ms", schedule="serial", random_serial_schedule=True, **kw)
     with pytest.raises(ValueError):
         BpOsdDecoder(H, error_rate=0.05, bp_method="ms", input_vector_type="codeword", **kw)
 
