@@ -35,6 +35,7 @@ struct bposd_handle {
     double *d_prior64 = nullptr, *d_weight = nullptr;
     float *d_prior32 = nullptr;
     int uniform = 0, uniform_prior = 0;
+    int safe_it = 0; // overflow guard: first pass at which a message could have overflowed with the static channel (fp64)
     // fast-kernel tables
     FastTables fast;
     // cluster-kernel tables (built on demand, when the messages exceed one SM's shared memory)
@@ -205,6 +206,7 @@ static int upload_probs(bposd_handle *h) {
         if (!(p == h->probs[0])) uni = false;
     }
     h->uniform_prior = uni ? 1 : 0; // all priors bit-identical (any value, including +-inf)
+    h->safe_it = overflow_safe_iterations(h, false, false);
     if (uni && !(h->probs[0] > 0.0 && h->probs[0] < 1.0)) uni = false;
     h->uniform = uni ? 1 : 0;       // OSD weights: popcount ordering is exact only for 0 < p < 1
     CU_TRY(h, cudaMemcpy(h->d_prior64, prior.data(), n * sizeof(double), cudaMemcpyHostToDevice));
@@ -943,7 +945,7 @@ static int launch_chunk(bposd_handle *h, bposd_handle::Slot &sl, cudaStream_t st
     a.max_iter = h->max_iter;
     a.method = h->bp_method;
     a.alpha0 = (real)h->alpha;
-    a.safe_it = overflow_safe_iterations(h, d_priors != nullptr, sizeof(real) == 4);
+    a.safe_it = sizeof(real) == 4 ? 0x7fffffff : (d_priors ? 0 : h->safe_it);
     a.uniform_prior = d_priors ? 0 : h->uniform_prior;
     if (d_priors) { a.prior = static_cast<const real *>(d_priors); a.prior_stride = n; }
     else { a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32; a.prior_stride = 0; }
@@ -1195,7 +1197,7 @@ static int decode_latency_t(bposd_handle *h, const uint8_t *h_synd, long long B,
     a.max_iter = h->max_iter;
     a.method = h->bp_method;
     a.alpha0 = (real)h->alpha;
-    a.safe_it = overflow_safe_iterations(h, false, sizeof(real) == 4);
+    a.safe_it = sizeof(real) == 4 ? 0x7fffffff : h->safe_it; // computed once per channel (a loop of n logarithms: 10 us on this path)
     a.uniform_prior = h->uniform_prior;
     a.prior = (sizeof(real) == 8) ? (const real *)h->d_prior64 : (const real *)h->d_prior32;
     a.prior_stride = 0;

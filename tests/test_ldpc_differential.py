@@ -97,3 +97,48 @@ def test_sort_tie_order_u1(oracle_mod):
     ora = oracle_mod.OracleDecoder(H, error_rate=0.06, **kw)
     for b in range(200):
         assert (np.asarray(ref.decode(syn[b])).astype(np.uint8) == ora.decode(syn[b])).all(), f"shot {b}"
+
+
+@pytest.mark.parametrize("method,custom_order", [("ms", False), ("ms", True), ("ps", False)])
+def test_serial_schedule_equals_ldpc(oracle_mod, cfg_codes, method, custom_order):
+    """the serial schedule, restated from a recollection of upstream's bp_decode_serial like everything
+    else in the oracle -- iteration counts, LLRs and decodings against the real thing, natural and given bit order."""
+    H = cfg_codes(2).hz
+    n = H.shape[1]
+    order = np.random.default_rng(9).permutation(n) if custom_order else None
+    kw = dict(max_iter=15, bp_method=method, ms_scaling_factor=0.8 if method == "ms" else 0, osd_method="osd_cs", osd_order=5)
+    _, syn = random_syndromes(H, 0.06, 300, seed=31)
+    extra = dict(schedule="serial") if order is None else dict(schedule="serial", serial_schedule_order=[int(j) for j in order])
+    ref = ldpc.BpOsdDecoder(H, channel_probs=np.full(n, 0.06), max_iter=15, bp_method=method, ms_scaling_factor=float(kw["ms_scaling_factor"]),
+                            osd_method="osd_cs", osd_order=5, **extra)
+    ora = oracle_mod.OracleDecoder(H, error_rate=0.06, math="libm", schedule="serial", serial_schedule_order=order, **kw)
+    for b in range(300):
+        want = np.asarray(ref.decode(syn[b])).astype(np.uint8)
+        got = ora.decode(syn[b]).astype(np.uint8)
+        assert (got == want).all(), f"osdw_decoding, shot {b}"
+        if hasattr(ref, "iter"):
+            assert int(ref.iter) == ora.iter, f"iter, shot {b}"
+        if hasattr(ref, "log_prob_ratios") and method == "ms":
+            assert np.array_equal(np.asarray(ref.log_prob_ratios, dtype=np.float64), ora.log_prob_ratios, equal_nan=True), f"shot {b}"
+
+
+def test_overflow_regime_equals_ldpc(oracle_mod, cfg_codes):
+    """far beyond max_iter = n the messages of shots that do not converge overflow; the reference's running
+    minimum starts from the largest finite double, which keeps its check messages finite.  The oracle (and through the
+    overflow guard the kernels) reproduce that: LLRs with +-inf in the same places."""
+    H = cfg_codes(2).hz
+    n = H.shape[1]
+    kw = dict(max_iter=3000, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)
+    _, syn = random_syndromes(H, 0.10, 32, seed=5)
+    ref = _ref_decoder(H, 0.06, kw)
+    ora = oracle_mod.OracleDecoder(H, error_rate=0.06, **kw)
+    seen_inf = False
+    for b in range(32):
+        want = np.asarray(ref.decode(syn[b])).astype(np.uint8)
+        got = ora.decode(syn[b]).astype(np.uint8)
+        assert (got == want).all(), f"shot {b}"
+        if hasattr(ref, "log_prob_ratios"):
+            a = np.asarray(ref.log_prob_ratios, dtype=np.float64)
+            assert np.array_equal(a, ora.log_prob_ratios, equal_nan=True), f"log_prob_ratios, shot {b}"
+            seen_inf |= bool(np.isinf(a).any())
+    assert seen_inf or not hasattr(ref, "log_prob_ratios"), "the case is meant to reach the overflow regime"
