@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
             if (!REG && s == BPC_NONE) off[r][k] = (nslot + (unsigned)kFastZeroSlot) * (unsigned)sizeof(real); // the constant-zero slot
         }
     }
+    const unsigned zoff = (nslot + (unsigned)kFastZeroSlot) * (unsigned)sizeof(real); // offset of an absent edge (irregular codes)
     unsigned long long n_conv = 0, n_iter = 0;
     const bool uniform = a.uniform_prior != 0;
     const real prior_u = a.prior[0];
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                 llr[r] = pj;
 #pragma unroll
                 for (int k = 0; k < DV; k++)
-                    if (REG || k < dj[r]) *reinterpret_cast<real *>(smem_raw + off[r][k]) = pj;
+                    if (REG || off[r][k] != zoff) *reinterpret_cast<real *>(smem_raw + off[r][k]) = pj;
             }
         }
         cluster_sync_all(); // every mailbox holds the priors of its bits
@@ -445,8 +446,8 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
             if (it > 1 && all_ok) { conv = true; iters = it - 1; break; }
             if (last) { iters = a.max_iter; break; }
             // ---- bit sweep (a6 + a8): rows and mailbox of this CTA only
-            const unsigned dnow = valid & (uniform ? fast_bit_sweep<real, DV, VPT, REG, true>(smem_raw, off, dj, llr, prior_u, prior_s, tid, T, bpc)
-                                                   : fast_bit_sweep<real, DV, VPT, REG, false>(smem_raw, off, dj, llr, prior_u, prior_s, tid, T, bpc));
+            const unsigned dnow = valid & (uniform ? fast_bit_sweep<real, DV, VPT, REG, true, true>(smem_raw, off, dj, llr, prior_u, prior_s, tid, T, bpc, zoff)
+                                                   : fast_bit_sweep<real, DV, VPT, REG, false, true>(smem_raw, off, dj, llr, prior_u, prior_s, tid, T, bpc, zoff));
             if (dnow != dprev) {
                 // a hard decision flipped (rare): toggle the parity-mismatch bit of every neighbouring check
                 unsigned flip = dnow ^ dprev;
@@ -455,14 +456,18 @@ __global__ void __launch_bounds__(MAXT, 1) bp_cluster_kernel(BpArgs<real> a, Clu
                 for (int r = 0; r < VPT; r++)
                     if ((flip >> r) & 1u) {
                         const int lq = tid + r * T;
-                        for (int k = 0; k < dj[r]; k++) {
-                            const unsigned o = off[r][k];
-                            if (o < (unsigned)rpc * RS * (unsigned)sizeof(real)) { // the check lives here
-                                const unsigned p = o / (unsigned)(RS * sizeof(real));
+                        // the slots come from the global table here (a flip is rare): indexing `off` with a run-time k would
+                        // move the whole array to local memory, and its LDLs into every bit position of every sweep
+#pragma unroll 1
+                        for (int k = 0; k < DV; k++) {
+                            const uint32_t sl = t.vslot[((size_t)rank * bpc + lq) * DV + k];
+                            if (sl == BPC_NONE) continue; // absent edge
+                            if (sl < (uint32_t)rpc * RS) { // the check lives here
+                                const unsigned p = sl / (unsigned)RS;
                                 atomicXor(reinterpret_cast<unsigned *>(meta + (p & ~3u)), 1u << ((p & 3u) * 8u));
                                 continue;
                             }
-                            const unsigned b = (o - (unsigned)rpc * RS * (unsigned)sizeof(real)) / (unsigned)sizeof(real);
+                            const unsigned b = sl - (unsigned)rpc * RS;
                             uint32_t d;
                             if (t.flip_table == 1) d = flip_desc[b];
                             else if (t.flip_table == 2) { const uint32_t w = flip_desc16[b]; d = mapa_u32(meta_s + (w & 0xFFCu), w >> 12) | (w & 3u); }

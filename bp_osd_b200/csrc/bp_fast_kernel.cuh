@@ -589,9 +589,14 @@ __device__ __forceinline__ void fast_check_row(real *row, unsigned mt, real alph
 #define BPOSD_BIT_GROUP 1 // positions whose messages are loaded together before the first store (regular codes); measured on
                           // B200 (profiles/r03h_ab_probe.log): 1 -> 128.4, 2 -> 128.1, 4 -> 127.4, 8 -> 127.1 M shot-iterations/s
 #endif
-template <typename real, int DV, int VPT, bool REG, bool UNI>
+// ZOFF (cluster kernel, irregular codes): an edge is present iff its offset is not the constant-zero slot's (`zoff`), so the
+// per-position degrees `dj` need no registers of their own (8 positions x 4 edges + 8 LLRs + 8 degrees do not fit the 96
+// registers of a 640-thread CTA: the offsets went to local memory and every position's first LDS waited for an LDL that
+// misses L1 after a cluster barrier -- 20 % of the stall samples, profiles/r2ag_cluster_hot_lines.txt).
+template <typename real, int DV, int VPT, bool REG, bool UNI, bool ZOFF = false>
 __device__ __forceinline__ unsigned fast_bit_sweep(unsigned char *smem_raw, const unsigned (&off)[VPT][DV], const int (&dj)[VPT],
-                                                   real (&llr)[VPT], real prior_u, const real *prior_s, int tid, int T, int n) {
+                                                   real (&llr)[VPT], real prior_u, const real *prior_s, int tid, int T, int n,
+                                                   unsigned zoff = 0) {
     unsigned dnow = 0;
     if constexpr (BPOSD_BIT_GUARDS == 0 && REG) {
         // regular code: every position has DV slots (real ones or its dummies), nothing is conditional.  The messages of
@@ -642,7 +647,7 @@ __device__ __forceinline__ unsigned fast_bit_sweep(unsigned char *smem_raw, cons
             real sfx = 0;
 #pragma unroll
             for (int k = DV - 1; k >= 0; k--) {
-                if (k < dj[r]) *reinterpret_cast<real *>(smem_raw + off[r][k]) = pre[k] + sfx;
+                if (ZOFF ? (off[r][k] != zoff) : (k < dj[r])) *reinterpret_cast<real *>(smem_raw + off[r][k]) = pre[k] + sfx;
                 sfx = sfx + c[k];
             }
         }
