@@ -31,6 +31,14 @@ CASES = {
     "lp882_ps_e10": dict(cfg=4, p=0.06, shots=24, kw=dict(max_iter=30, bp_method="ps", ms_scaling_factor=0, osd_method="osd_e", osd_order=10)),
     # the large-H code (H beyond 228 KB): two shots that do not converge in 6 iterations -> HBM-resident OSD-0; the second
     # restatement is pure Python and is skipped at this size 
+    # row f4: the serial schedule in a given bit order (min-sum) and in the natural order (product-sum)
+    "d5_ms_serial_cs5": dict(cfg=1, p=0.10, shots=120, kw=dict(max_iter=8, bp_method="ms", ms_scaling_factor=0, osd_method="osd_cs", osd_order=5,
+                                                             schedule="serial", serial_schedule_order=[int(j) for j in np.random.default_rng(7).permutation(41)])),
+    "hgp400_ps_serial": dict(cfg=2, p=0.06, shots=16, kw=dict(max_iter=10, bp_method="ps", ms_scaling_factor=0, osd_method="osd0", osd_order=0, schedule="serial")),
+    # far beyond max_iter = n on syndromes that do not converge: messages overflow, LLRs hold +-inf
+    # (12 000 passes: too long for the pure-Python restatement, which is skipped here; it agrees on the same case at 3 000)
+    "hgp400_ms_overflow": dict(cfg=2, p=0.06, p_syn=0.10, shots=12, slow=False,
+                               kw=dict(max_iter=12000, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)),
     "hgp40k_ms_osd0": dict(cfg=5, p=0.03, shots=2, slow=False, kw=dict(max_iter=6, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)),
 }
 
@@ -44,14 +52,15 @@ def main():
         H = codes.config_code(c["cfg"], logicals=False).hz
         n = H.shape[1]
         rng = np.random.default_rng(20251018)
-        e = (rng.random((c["shots"], n)) < c["p"]).astype(np.uint8)
+        e = (rng.random((c["shots"], n)) < c.get("p_syn", c["p"])).astype(np.uint8)
         s = np.asarray((H @ e.T) % 2, dtype=np.uint8).T.copy()
         kw = c["kw"]
         o = OracleDecoder(H, error_rate=c["p"], **kw)
         ref = o.decode_batch(s)
         slow = SlowDecoder(H, [c["p"]] * n, kw["max_iter"], kw["bp_method"], kw["ms_scaling_factor"],
                            "osd0" if kw["osd_method"] == "osd0" else kw["osd_method"], kw["osd_order"],
-                           tanh=oracle_lib().oracle_math_tanh, log=oracle_lib().oracle_math_log)
+                           tanh=oracle_lib().oracle_math_tanh, log=oracle_lib().oracle_math_log,
+                           schedule=kw.get("schedule", "parallel"), serial_schedule_order=kw.get("serial_schedule_order"))
         for b in range(c["shots"] if c.get("slow", True) else 0):
             x = slow.decode(s[b])
             assert (np.array(x) == ref["osdw"][b]).all(), (name, b)
