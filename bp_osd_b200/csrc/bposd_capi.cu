@@ -173,7 +173,7 @@ static int host_rank(const bposd_handle *h) {
 // llr_near_overflow in bposd_kernels.cuh).  With P the largest |prior| and d the largest column degree, the largest
 // magnitude of any message or LLR after pass t is at most P (d + 1)^t: a check message never exceeds the largest
 // bit-to-check message, and a bit sums its prior and at most d check messages.  Guarding starts while that bound is
-// still below the threshold the kernels test against (1e300 / 1e30).  Per-shot priors are not known on the host: 0.
+// still below the threshold the kernels test against (1e291).  Per-shot priors are not known on the host: 0.
 static int overflow_safe_iterations(const bposd_handle *h, bool per_shot_priors, bool fp32) {
     // fp32 fast mode: not guarded.  It promises no bit-exactness, a shot whose messages overflow is a shot that does not
     // converge (OSD takes it either way), and fp32 would reach the guarded range at pass ~48, inside the bulk of the
@@ -187,7 +187,7 @@ static int overflow_safe_iterations(const bposd_handle *h, bool per_shot_priors,
         if (!(l <= 1e30)) return 0; // p = 0 or 1: infinite priors from the start
         P = std::max(P, l);
     }
-    const double lim = std::log(fp32 ? 1e30 : 1e300) - std::log(P) - std::log(4.0);
+    const double lim = std::log(fp32 ? 1e30 : 1e291) - std::log(P) - std::log(4.0);
     const double per = std::log((double)std::max(h->max_col_deg, 1) + 1.0);
     const double t = lim / per;
     return t < 1.0 ? 0 : (t > 1e9 ? 1000000000 : (int)t);

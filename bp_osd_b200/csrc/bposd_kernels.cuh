@@ -68,10 +68,12 @@ template <> __device__ __forceinline__ float real_max<float>() { return FLT_MAX;
 // reaches 6e234 after 1 922 passes), so this matters for max_iter beyond a few thousand passes -- config 5 runs 40 000.
 // An infinite bit-to-check message and +-max are the same thing to the reference's check update (neither is smaller than
 // the starting value; `<= 0` sees the same sign), so: from the pass where an overflow is conceivable (safe_it, host side)
-// every thread tests its bits' LLRs after the bit sweep; a sum that is not finite-and-small raises a CTA-wide flag, and
+// every thread tests its bits' LLRs after the bit sweep; a sum that is not finite and below 1e291 raises a CTA-wide flag, and
 // the next check sweep first rewrites +-inf in its rows as +-max.  Nothing is added to passes before safe_it.
 template <typename real> __device__ __forceinline__ bool llr_near_overflow(real t);
-template <> __device__ __forceinline__ bool llr_near_overflow<double>(double t) { return !(fabs(t) <= 1e300); }
+// Threshold: below half an ulp of the largest finite value (1e292), so that a bit whose LLR passes the test cannot have
+// produced an infinite bit-to-check message either: such a message is the LLR minus one finite check message.
+template <> __device__ __forceinline__ bool llr_near_overflow<double>(double t) { return !(fabs(t) <= 1e291); }
 template <> __device__ __forceinline__ bool llr_near_overflow<float>(float t) { return !(fabsf(t) <= 1e30f); }
 template <typename real> __device__ __forceinline__ real clamp_inf(real v);
 template <> __device__ __forceinline__ double clamp_inf<double>(double v) { return (fabs(v) > DBL_MAX) ? copysign(DBL_MAX, v) : v; }
