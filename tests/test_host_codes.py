@@ -1,4 +1,5 @@
 """Host GF(2) toolkit and code builders against the reference's doc/test known answers."""
+import os
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -164,3 +165,19 @@ def test_regenerated_code_files_match_the_shipped_ones(tmp_path):
         assert not ((hx @ lz_ref.T) % 2).any() and not ((hz @ lx_ref.T) % 2).any()  # the shipped logicals commute with them
         assert (c["lz"].toarray() == lz_ref).all()
         assert mod2.rank(hx) + mod2.rank(hz) == N - K
+
+
+def test_reference_package_name_shim():
+    """A script written against the reference imports `bposd`, `bposd.hgp`, `bposd.css`, `bposd.css_decode_sim`
+    (/root/reference/src/bposd/__init__.py:1, README.md:150-216): the shim package resolves every name to bp_osd_b200."""
+    import bposd
+    from bposd import bposd_decoder, BpOsdDecoder          # noqa: F401
+    from bposd.css import css_code
+    from bposd.hgp import hgp, hgp_single                  # noqa: F401
+    from bposd.css_decode_sim import css_decode_sim
+    import bp_osd_b200
+    assert bposd_decoder is bp_osd_b200.bposd_decoder and css_code is bp_osd_b200.css_code
+    assert css_decode_sim.__module__ == "bp_osd_b200.css_decode_sim"
+    q = hgp(codes.rep_code(3))                              # README.md:176-180
+    assert (q.N, q.K) == (13, 1)
+    assert os.path.exists(os.path.join(bposd.get_include(), "bposd_b200.h"))
