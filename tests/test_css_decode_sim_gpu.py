@@ -75,3 +75,37 @@ def test_invalid_code_raises(sim_cls):
     h = codes.rep_code(3)
     with pytest.raises(Exception, match="invalid CSS code"):
         sim_cls(h, h, error_rate=0.1, run_sim=0)     # README.md:125-136: hx = hz = rep code is not a CSS code
+
+
+def test_reference_style_script_through_the_shim(cuda_lib, tmp_path):
+    """The flow of the reference's example and README (examples/qldpc_decode_example.py, README.md:150-216) written with
+    the REFERENCE's import lines -- `from bposd.hgp import hgp`, `from bposd.css_decode_sim import css_decode_sim`,
+    `from bposd import bposd_decoder` -- runs on the B200 decoder through the bposd/ import shim."""
+    script = '''
+import numpy as np
+from bposd.hgp import hgp
+from bposd.css_decode_sim import css_decode_sim
+from bposd import bposd_decoder
+
+h = np.array(H_SEED)
+qcode = hgp(h)
+qcode.test()
+osd_options = {"error_rate": 0.05, "target_runs": 600, "xyz_error_bias": [0, 0, 1], "output_file": OUT, "bp_method": "ms",
+               "ms_scaling_factor": 0, "osd_method": "osd_cs", "osd_order": 42, "channel_update": None, "seed": 42,
+               "max_iter": 0, "tqdm_disable": 1}
+lk = css_decode_sim(hx=qcode.hx, hz=qcode.hz, **osd_options)
+bpd = bposd_decoder(qcode.hz, error_rate=0.05, channel_probs=[None], max_iter=qcode.N, bp_method="ms", ms_scaling_factor=0,
+                    osd_method="osd_cs", osd_order=7)
+error = np.zeros(qcode.N).astype(int)
+error[[5, 12]] = 1
+bpd.decode(qcode.hz @ error % 2)
+residual = (bpd.osdw_decoding + error) % 2
+RESULT.update(N=lk.N, K=lk.K, runs=lk.run_count, ler=lk.osdw_logical_error_rate, ok=not (qcode.lz @ residual % 2).any())
+'''
+    out = str(tmp_path / "test.json")
+    env = dict(H_SEED=np.asarray(codes.mkmn_16_4_6()).tolist(), OUT=out, RESULT={})
+    exec(compile(script, "reference_style_script", "exec"), env)
+    r = env["RESULT"]
+    assert (r["N"], r["K"]) == (400, 16) and r["runs"] == 600 and r["ok"]
+    assert 0 <= r["ler"] < 0.2
+    assert json.load(open(out))["run_count"] == 600   # the output file holds the JSON text of the run, as in the reference
